@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's native operator API for the segmentation hot path.
+
+Same names, argument meaning and error behaviour as ``dynamont._dynamont`` (reference
+src/cpp/aligner_bindings.cpp:180-219): ``Aligner(model_file, pore, mode="basic", threads=1, band=400)``,
+``.align(signal, sequence, calc_probabilities=False) -> dict``, ``.train(signal, sequence) -> dict``,
+``PoreType`` and ``pore_type()``.  Added on top (the reference processes one read per call; a B200 needs
+thousands in flight): ``.align_batch`` / ``.train_batch``.
+
+Everything numeric happens in the CUDA library behind the C ABI (include/dynamont_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _capi
+from ._capi import ReadResult, TrainResult, f64p, u64p
+
+
+class PoreType(enum.Enum):  # aligner.hpp:26-33 / aligner_bindings.cpp:184-189
+    RNA002 = 0
+    RNA004 = 1
+    DNA_R9 = 2
+    DNA_R10_260 = 3
+    DNA_R10_400 = 4
+
+
+_PORE_STR = {
+    "rna002": PoreType.RNA002, "rna004": PoreType.RNA004, "dna_r9": PoreType.DNA_R9,
+    "dna_r10_260bps": PoreType.DNA_R10_260, "dna_r10_400bps": PoreType.DNA_R10_400,
+}
+_PORE_NAME = {v: k for k, v in _PORE_STR.items()}
+
+
+def pore_type(pore: str) -> PoreType:
+    """aligner_bindings.cpp:18-32."""
+    try:
+        return _PORE_STR[pore]
+    except KeyError:
+        raise ValueError("Unknown pore type: " + str(pore))
+
+
+def _message(lib, status: int, bad_char: bytes) -> str:
+    msg = lib.dyn_status_message(status).decode()
+    if status == 4:
+        msg += bad_char.decode("latin-1")
+    return msg
+
+
+class Aligner:
+    def __init__(self, model_file: str, pore, mode: str = "basic", threads: int = 1, band: int = 400,
+                 device: int = -1, _lib_path: str | None = None):
+        self._lib = _capi.load(_lib_path)
+        if isinstance(pore, PoreType):
+            pore = _PORE_NAME[pore]
+        err = C.create_string_buffer(1024)
+        kind = C.c_int(0)
+        self._h = self._lib.dyn_create(str(model_file).encode(), str(pore).encode(), str(mode).encode(),
+                                       int(threads), int(band), int(device), err, 1024, C.byref(kind))
+        if not self._h:
+            msg = err.value.decode()
+            raise (ValueError if kind.value == 1 else RuntimeError)(msg)
+        self.kmer_size = self._lib.dyn_kmer_size(self._h)
+        self.num_kmers = int(self._lib.dyn_num_kmers(self._h))
+        self.rna = bool(self._lib.dyn_is_rna(self._h))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.dyn_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def model(self):
+        mean = np.empty(self.num_kmers)
+        sd = np.empty(self.num_kmers)
+        self._lib.dyn_model(self._h, mean.ctypes.data_as(f64p), sd.ctypes.data_as(f64p))
+        return mean, sd
+
+    def set_model(self, mean, stdev) -> None:
+        mean = np.ascontiguousarray(mean, dtype=np.float64)
+        stdev = np.ascontiguousarray(stdev, dtype=np.float64)
+        assert mean.size == self.num_kmers and stdev.size == self.num_kmers
+        self._lib.dyn_set_model(self._h, mean.ctypes.data_as(f64p), stdev.ctypes.data_as(f64p))
+
+    def set_option(self, key: str, value: float) -> None:
+        if self._lib.dyn_set_option(self._h, key.encode(), float(value)) != 0:
+            raise KeyError(key)
+
+    def read_cells(self, S: int, L: int) -> int:
+        return int(self._lib.dyn_read_cells(self._h, int(S), int(L)))
+
+    def last_timing(self):
+        t = np.zeros(3)
+        self._lib.dyn_last_timing(self._h, t.ctypes.data_as(f64p))
+        return {"encode_ms": t[0], "dp_ms": t[1], "launches": int(t[2])}
+
+    @staticmethod
+    def _pack(signals, sequences, dtype):
+        n = len(signals)
+        sig_off = np.zeros(n + 1, dtype=np.uint64)
+        seq_off = np.zeros(n + 1, dtype=np.uint64)
+        arrs = []
+        for i, s in enumerate(signals):
+            a = np.ascontiguousarray(s, dtype=dtype)
+            if a.ndim != 1:
+                raise ValueError("Signal must be a one-dimensional array")  # aligner_bindings.cpp:138
+            arrs.append(a)
+            sig_off[i + 1] = sig_off[i] + a.size
+        sig = np.concatenate(arrs) if arrs else np.zeros(0, dtype=dtype)
+        if sig.size == 0:
+            sig = np.zeros(1, dtype=dtype)  # keep a valid pointer
+        seqb = [q.encode("latin-1") if isinstance(q, str) else bytes(q) for q in sequences]
+        for i, q in enumerate(seqb):
+            seq_off[i + 1] = seq_off[i] + len(q)
+        seq = b"".join(seqb) or b"\0"
+        return sig, sig_off, seq, seq_off
+
+    # --------------------------------------------------------------------------------------------- align
+    def align_batch(self, signals, sequences, calc_probabilities: bool = False, raise_errors: bool = False):
+        """Batched ``align``: returns one dict per read (same keys as ``align``) or an Exception instance for
+        reads the reference would have thrown on (``raise_errors`` re-raises the first)."""
+        n = len(signals)
+        assert len(sequences) == n
+        dtype = np.float64 if any(np.asarray(s).dtype == np.float64 for s in signals) else np.float32
+        sig, sig_off, seq, seq_off = self._pack(signals, sequences, dtype)
+        res = (ReadResult * max(n, 1))()
+        nseg = int(self._lib.dyn_count_segments(self._h, seq_off.ctypes.data_as(u64p), n))
+        seqpos = np.zeros(max(nseg, 1), dtype=np.uint64)
+        sigpos = np.zeros(max(nseg, 1), dtype=np.uint64)
+        prob = np.zeros(max(nseg, 1), dtype=np.float64)
+        fn = self._lib.dyn_align_batch_f64 if dtype == np.float64 else self._lib.dyn_align_batch
+        rc = fn(self._h, sig.ctypes.data, sig_off.ctypes.data_as(u64p), C.cast(C.c_char_p(seq), C.c_void_p),
+                seq_off.ctypes.data_as(u64p), n, int(calc_probabilities), res, seqpos.ctypes.data_as(u64p),
+                sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p))
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        out = []
+        for i in range(n):
+            r = res[i]
+            if r.status != 0:
+                e = RuntimeError(_message(self._lib, r.status, r.bad_char))
+                if raise_errors:
+                    raise e
+                out.append(e)
+                continue
+            a, b = int(r.seg_offset), int(r.seg_offset + r.n_segments)
+            ns = b - a
+            out.append({
+                "Z": r.Z,
+                "sequence_positions": seqpos[a:b].copy(),
+                "signal_positions": sigpos[a:b].copy(),
+                "probabilities": prob[a:b].copy(),
+                "states": ["M"] * ns,       # basic mode only emits match segments (NT:424-430)
+                "polishes": [""] * ns,      # Segment.polish default (aligner.hpp:41)
+            })
+        return out
+
+    def align(self, signal, sequence: str, calc_probabilities: bool = False) -> dict:
+        """aligner_bindings.cpp:132-147 -> NTAligner::align (NT_aligner_api.cpp:230-312)."""
+        sig = np.asarray(signal)
+        if sig.ndim != 1:
+            raise ValueError("Signal must be a one-dimensional array")
+        return self.align_batch([np.ascontiguousarray(sig, dtype=np.float64)], [sequence], calc_probabilities,
+                                raise_errors=True)[0]
+
+    # --------------------------------------------------------------------------------------------- train
+    def train_batch(self, signals, sequences, per_read_model: bool = False):
+        """Batched ``train``.  Returns (per-read list, pooled) where pooled = dict(w, x, xx, xi) holds the
+        sufficient statistics summed over the successful reads of the batch (native kmer order)."""
+        n = len(signals)
+        sig, sig_off, seq, seq_off = self._pack(signals, sequences, np.float32)
+        K = self.num_kmers
+        res = (TrainResult * max(n, 1))()
+        w, x, xx = np.zeros(K), np.zeros(K), np.zeros(K)
+        xi = np.zeros(2)
+        pm = ps = None
+        if per_read_model:
+            pm, ps = np.zeros((n, K)), np.zeros((n, K))
+        rc = self._lib.dyn_train_batch(
+            self._h, sig.ctypes.data, sig_off.ctypes.data_as(u64p), C.cast(C.c_char_p(seq), C.c_void_p),
+            seq_off.ctypes.data_as(u64p), n, res, w.ctypes.data_as(f64p), x.ctypes.data_as(f64p),
+            xx.ctypes.data_as(f64p), xi.ctypes.data_as(f64p),
+            pm.ctypes.data_as(f64p) if per_read_model else None, ps.ctypes.data_as(f64p) if per_read_model else None)
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        out = []
+        for i in range(n):
+            r = res[i]
+            if r.status != 0:
+                out.append(RuntimeError(_message(self._lib, r.status, r.bad_char)))
+                continue
+            d = {"Z": r.Z, "transition_params": {"m1": r.m1, "e1": r.e1, "e2": r.e2}}
+            if per_read_model:
+                d["emission_model"] = {"mean": pm[i], "stdev": ps[i]}
+            out.append(d)
+        return out, {"w": w, "x": x, "xx": xx, "xi": xi}
+
+    def train(self, signal, sequence: str, as_dicts: bool = True) -> dict:
+        """aligner_bindings.cpp:149-163 -> NTAligner::train (NT_aligner_api.cpp:567-639).  ``emission_model`` is the
+        reference's list of 4^k ``{"mean","stdev"}`` dicts (aligner_bindings.cpp:93-100) unless as_dicts=False."""
+        sig = np.asarray(signal)
+        if sig.ndim != 1:
+            raise ValueError("Signal must be a one-dimensional array")
+        out, _ = self.train_batch([sig], [sequence], per_read_model=True)
+        r = out[0]
+        if isinstance(r, Exception):
+            raise r
+        if as_dicts:
+            m, s = r["emission_model"]["mean"], r["emission_model"]["stdev"]
+            r["emission_model"] = [{"mean": float(a), "stdev": float(b)} for a, b in zip(m, s)]
+        return r

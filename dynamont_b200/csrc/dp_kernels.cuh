@@ -1,0 +1,982 @@
+// Warp-per-read banded forward/backward/posterior-decoding kernels for Dynamont's basic ("NT") mode.
+//
+// What the reference computes (NT_aligner_api.cpp:110-456, restated in SURVEY.md Appendix A) and how it is
+// mapped here:
+//
+//   * one warp owns one read; the band row (<= 2*bw+1 lattice columns) lives in registers, CPL consecutive
+//     columns per lane ("ring slots": column n -> slot n mod 32*CPL, lane = slot / CPL).  The band slides by
+//     at most one column per row, which retires one slot and activates another; nothing else moves.
+//   * the n-1 / n+1 neighbour of a lane's first / last column comes from one warp shuffle per row.
+//   * all arithmetic is FP32 in the log2 domain; every lane carries its own double offset (block floating
+//     point), renormalised from the lane-local maximum every RN rows.  No cross-lane reduction is needed.
+//   * pass 1 (backward, t descending) keeps only a checkpoint every CK rows (bM, bE slots + lane offsets).
+//   * pass 2 (t ascending) recomputes backward rows block-wise into shared memory, runs the forward
+//     recurrence normalised by the backward offsets (so that fM+bM and fE+bE ARE the log2 posteriors),
+//     feeds them into the posterior-Viterbi fill (NT:338-363), stores 1 decision bit per cell and the few
+//     cells per row whose posterior is not negligible (sparse records).
+//   * pass 3 walks the decision bits backwards (NT:383-456), looks the path cells' posteriors up in the
+//     sparse records (normalising every row by its own recorded mass) and takes the per-segment median.
+//
+// Nothing lattice-sized is ever written to HBM except 1 bit per cell.
+#pragma once
+
+#include "dp_common.cuh"
+
+namespace dyn
+{
+
+template <int CPL_, int CK_, int RN_, int RV_>
+struct Cfg
+{
+	static constexpr int CPL = CPL_;         // lattice columns per lane
+	static constexpr int SLOTS = 32 * CPL_;  // ring capacity; needs 2*bw + 2 <= SLOTS
+	static constexpr int CK = CK_;           // checkpoint spacing (rows); multiple of RN
+	static constexpr int RN = RN_;           // renormalisation period of the backward pass (rows)
+	static constexpr int RV = RV_;           // renormalisation period of the posterior-Viterbi scores
+	static constexpr int NRN = CK_ / RN_ + 1;
+	static constexpr int CKF = 2 * CPL_ * 32;  // floats per checkpoint
+	static constexpr size_t CK_BYTES = CKF * 4 + 32 * 8;
+	static constexpr size_t SMEM_BYTES = (size_t)(CK_ + 1) * CPL_ * 32 * 4 + (size_t)NRN * 32 * (8 + 4);
+	static_assert(CK_ % RN_ == 0, "CK must be a multiple of RN");
+};
+
+// Scratch memory of one resident warp ("slot"), sized by the host for the longest read of the batch.
+struct SlotScratch
+{
+	float* ckpt;        // [nck][CKF] floats followed by ... (see ck_f / ck_ob)
+	double* ckpt_ob;    // [nck][32]
+	uint16_t* bits;     // [T][32]   decision bits: bit j of word (t, lane) = cell in slot lane*CPL+j came from M
+	uint32_t* rowptr;   // [T+1]     first sparse record of row t
+	PostRec* recs;      // [rec_cap]
+	uint32_t* pn;       // [T]       path column of row t (bit 31: match state)
+	float* pp;          // [T]       posterior of the path cell of row t
+};
+
+struct BatchArgs
+{
+	const ReadDesc* reads;
+	const uint32_t* order;      // processing order (longest first)
+	uint32_t n_reads;
+	uint32_t* queue;            // atomic work counter
+	const float* signal;
+	const PosConst* pc;
+	const SlotScratch* slots;   // [gridDim.x]
+	uint64_t rec_cap;           // sparse records per slot
+	ReadOut* out;               // [n_reads]
+	uint32_t* out_sigpos;       // [sum Kc]
+	double* out_prob;           // [sum Kc]
+	float m1, e2;               // log2 transition scores (e1 = log 1 = 0 is omitted, NT:33,85)
+	float thr2;                 // sparse-record threshold on max(log2 pM, log2 pE)
+	int mode;                   // 0: Z only (backward pass), 1: full alignment, 2: training statistics
+	// training (mode 2)
+	double* stat_w;             // [K] pooled sum of gamma              (NT:510)
+	double* stat_x;             // [K] pooled sum of gamma * x          (NT:511)
+	double* stat_xx;            // [K] pooled sum of gamma * x^2        (NT:512)
+	const int32_t* kmers;       // [sum N] kmer id of column n (kmer[n-1]; entry 0 unused), parallel to pc
+	double* read_w;             // optional per-read per-column statistics [sum N] (reference per-read M-step)
+	double* read_x;
+	double* read_xx;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// ring-slot helpers
+// ------------------------------------------------------------------------------------------------------
+DYN_DEV int pmod(int x, int m)
+{
+	int r = x % m;
+	return r < 0 ? r + m : r;
+}
+
+template <int CPL>
+struct Emis
+{
+	float a[CPL], b[CPL], c[CPL];
+};
+
+#define DYN_SLOT_CASE(J) \
+	case J:              \
+		if (J < CPL && lane == ql) { body(J); } \
+		break;
+
+// calls body(j) in the lane that owns ring slot q, with j a compile-time constant (registers stay registers)
+template <int CPL, typename F>
+DYN_DEV void with_slot(int lane, int q, F body)
+{
+	const int ql = q / CPL;
+	const int j = q - ql * CPL;
+	switch (j)
+	{
+		DYN_SLOT_CASE(0) DYN_SLOT_CASE(1) DYN_SLOT_CASE(2) DYN_SLOT_CASE(3)
+		DYN_SLOT_CASE(4) DYN_SLOT_CASE(5) DYN_SLOT_CASE(6) DYN_SLOT_CASE(7)
+		DYN_SLOT_CASE(8) DYN_SLOT_CASE(9) DYN_SLOT_CASE(10) DYN_SLOT_CASE(11)
+		DYN_SLOT_CASE(12) DYN_SLOT_CASE(13) DYN_SLOT_CASE(14) DYN_SLOT_CASE(15)
+		DYN_SLOT_CASE(16) DYN_SLOT_CASE(17) DYN_SLOT_CASE(18) DYN_SLOT_CASE(19)
+		DYN_SLOT_CASE(20) DYN_SLOT_CASE(21) DYN_SLOT_CASE(22) DYN_SLOT_CASE(23)
+		DYN_SLOT_CASE(24) DYN_SLOT_CASE(25) DYN_SLOT_CASE(26) DYN_SLOT_CASE(27)
+		DYN_SLOT_CASE(28) DYN_SLOT_CASE(29) DYN_SLOT_CASE(30) DYN_SLOT_CASE(31)
+	default:
+		break;
+	}
+}
+#undef DYN_SLOT_CASE
+
+// A small functor helper because device lambdas with constant-index register access need a template arg.
+template <int CPL>
+struct SetEmis
+{
+	Emis<CPL>& e;
+	float va, vb, vc;
+	DYN_DEV void operator()(int j) const
+	{
+#pragma unroll
+		for (int jj = 0; jj < CPL; ++jj)
+			if (jj == j)
+			{
+				e.a[jj] = va;
+				e.b[jj] = vb;
+				e.c[jj] = vc;
+			}
+	}
+};
+
+template <int CPL>
+struct SetTwo
+{
+	float (&p)[CPL];
+	float (&q)[CPL];
+	float v;
+	DYN_DEV void operator()(int j) const
+	{
+#pragma unroll
+		for (int jj = 0; jj < CPL; ++jj)
+			if (jj == j)
+			{
+				p[jj] = v;
+				q[jj] = v;
+			}
+	}
+};
+
+template <int CPL>
+struct SetOne
+{
+	float (&p)[CPL];
+	float v;
+	DYN_DEV void operator()(int j) const
+	{
+#pragma unroll
+		for (int jj = 0; jj < CPL; ++jj)
+			if (jj == j) p[jj] = v;
+	}
+};
+
+template <int CPL>
+struct GetOne
+{
+	const float (&p)[CPL];
+	float& out;
+	DYN_DEV void operator()(int j) const
+	{
+#pragma unroll
+		for (int jj = 0; jj < CPL; ++jj)
+			if (jj == j) out = p[jj];
+	}
+};
+
+// The warp-uniform view of one read.
+template <class CFG>
+struct Warp
+{
+	static constexpr int CPL = CFG::CPL;
+	static constexpr int SLOTS = CFG::SLOTS;
+
+	int lane;
+	uint32_t T, N, S;
+	int bw;
+	double ratio;
+	const float* sig;
+	const PosConst* pc;
+	float m1, e2;
+	Emis<CPL> em;
+
+	DYN_DEV void activate(int n)
+	{
+		if (n < 0 || n >= (int)N) return;
+		const PosConst v = pc[n];  // uniform address: one broadcast transaction
+		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, v.a, v.b, v.c});
+	}
+	DYN_DEV void deactivate(int n)
+	{
+		if (n < 0 || n >= (int)N) return;
+		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, 0.0f, 0.0f, CNEG});
+	}
+	// lattice column held by ring slot q when the window starts at column n0 (may be negative)
+	DYN_DEV int col_of_slot(int q, int n0) const { return n0 + pmod(q - n0, SLOTS); }
+
+	// load the emission constants of every column of band(row with centre mid); everything else inactive
+	DYN_DEV void load_window(int mid)
+	{
+		const int n0 = mid - bw;
+		const int nlast = min(mid + bw, (int)N - 1);
+#pragma unroll
+		for (int j = 0; j < CPL; ++j)
+		{
+			const int n = col_of_slot(lane * CPL + j, n0);
+			if (n >= 0 && n <= nlast)
+			{
+				const PosConst v = pc[n];
+				em.a[j] = v.a;
+				em.b[j] = v.b;
+				em.c[j] = v.c;
+			}
+			else
+			{
+				em.a[j] = 0.0f;
+				em.b[j] = 0.0f;
+				em.c[j] = CNEG;
+			}
+		}
+	}
+	// move the emission window from centre mid_from up to centre mid_to (mid_to >= mid_from)
+	DYN_DEV void slide_window_up(int mid_from, int mid_to)
+	{
+		for (int m = mid_from + 1; m <= mid_to; ++m)
+		{
+			deactivate(m - 1 - bw);
+			activate(m + bw);
+		}
+	}
+};
+
+// ------------------------------------------------------------------------------------------------------
+// backward recurrence (NT_aligner_api.cpp:158-207), one row
+// ------------------------------------------------------------------------------------------------------
+template <int CPL>
+struct Bwd
+{
+	float bM[CPL], bE[CPL];
+	double OB;  // this lane's values are (true log2 value) - OB
+	float dR;   // OB(right neighbour lane) - OB(this lane)
+};
+
+template <class CFG>
+DYN_DEV void bwd_row(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x)
+{
+	constexpr int CPL = CFG::CPL;
+	float s[CPL], A[CPL];
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		s[j] = emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]);
+		A[j] = b.bM[j] + (s[j] + w.m1);  // bM[t+1][n] + score(x[t], kmer[n-1]) + m1, consumed by column n-1
+	}
+	const float Ar = __shfl_sync(FULL, A[0], (w.lane + 1) & 31) + b.dR;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		const float ext1 = (j + 1 < CPL) ? A[j + 1] : Ar;
+		const float nm = b.bE[j] + s[j];  // bM[t][n] = bE[t+1][n] + score      (NT:200)
+		b.bE[j] = logplus2(ext1, nm + w.e2);  //                                    (NT:194,201,204)
+		b.bM[j] = nm;
+	}
+}
+
+// lane-local renormalisation; returns the increment that was subtracted (0 for a lane without finite cells)
+template <class CFG>
+DYN_DEV float bwd_renorm(Warp<CFG>& w, Bwd<CFG::CPL>& b)
+{
+	constexpr int CPL = CFG::CPL;
+	float lm = b.bE[0];
+#pragma unroll
+	for (int j = 1; j < CPL; ++j) lm = fmaxf(lm, b.bE[j]);
+	const bool dead = lm < DEADT;
+	const float inc = dead ? 0.0f : lm;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		b.bM[j] -= inc;
+		b.bE[j] -= inc;
+	}
+	b.OB += (double)inc;
+	// a lane without finite cells adopts its right neighbour's offset, so that the first values that
+	// flow into it later are represented at a sane scale
+	double obr = shfl_f64(b.OB, (w.lane + 1) & 31);
+	if (dead) b.OB = obr;
+	obr = shfl_f64(b.OB, (w.lane + 1) & 31);
+	b.dR = (float)(obr - b.OB);
+	return inc;
+}
+
+// one backward step: row t from row t+1, including the band slide between the two rows
+template <class CFG>
+DYN_DEV void bwd_step(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x, bool slide, int& mid)
+{
+	constexpr int CPL = CFG::CPL;
+	// on entry mid = centre of row t+1
+	if (slide) w.activate(mid - 1 - w.bw);  // column mid_t - bw enters the band
+	bwd_row<CFG>(w, b, x);
+	if (slide)
+	{
+		const int ntop = mid + w.bw;  // column that was in band(t+1) but is not in band(t)
+		if (ntop < (int)w.N)
+		{
+			with_slot<CPL>(w.lane, pmod(ntop, CFG::SLOTS), SetTwo<CPL>{b.bM, b.bE, NEG});
+			w.deactivate(ntop);
+		}
+		--mid;
+	}
+}
+
+template <class CFG>
+DYN_DEV void bwd_init_terminal(Warp<CFG>& w, Bwd<CFG::CPL>& b)
+{
+	constexpr int CPL = CFG::CPL;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		b.bM[j] = NEG;
+		b.bE[j] = NEG;
+	}
+	with_slot<CPL>(w.lane, pmod((int)w.N - 1, CFG::SLOTS), SetOne<CPL>{b.bE, 0.0f});  // bE[T-1][N-1] = 0 (NT:170)
+	b.OB = 0.0;
+	b.dR = 0.0f;
+}
+
+template <class CFG>
+DYN_DEV void ckpt_store(const SlotScratch& sc, uint32_t idx, int lane, const Bwd<CFG::CPL>& b)
+{
+	constexpr int CPL = CFG::CPL;
+	float* f = sc.ckpt + (size_t)idx * CFG::CKF;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		f[j * 32 + lane] = b.bM[j];
+		f[(CPL + j) * 32 + lane] = b.bE[j];
+	}
+	sc.ckpt_ob[(size_t)idx * 32 + lane] = b.OB;
+}
+
+template <class CFG>
+DYN_DEV void ckpt_load(const SlotScratch& sc, uint32_t idx, int lane, Bwd<CFG::CPL>& b)
+{
+	constexpr int CPL = CFG::CPL;
+	const float* f = sc.ckpt + (size_t)idx * CFG::CKF;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		b.bM[j] = f[j * 32 + lane];
+		b.bE[j] = f[(CPL + j) * 32 + lane];
+	}
+	b.OB = sc.ckpt_ob[(size_t)idx * 32 + lane];
+	const double obr = shfl_f64(b.OB, (lane + 1) & 31);
+	b.dR = (float)(obr - b.OB);
+}
+
+// per 32-row chunk: the lane's sample and the band-slide mask (bit i <=> centre(base+i) != centre(base+i+1))
+template <class CFG>
+DYN_DEV void chunk_prefetch(const Warp<CFG>& w, uint32_t base, float& xv, unsigned& smask)
+{
+	const uint32_t r = base + w.lane;
+	const uint32_t c0 = band_mid(r, w.ratio), c1 = band_mid(r + 1, w.ratio);
+	smask = __ballot_sync(FULL, c0 != c1);
+	xv = (r < w.S) ? w.sig[r] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pass 1: backward over the whole read.  Returns log2 Zb (double) in every lane; stores checkpoints.
+// ------------------------------------------------------------------------------------------------------
+template <class CFG, bool STORE>
+DYN_DEV double backward_pass(Warp<CFG>& w, const SlotScratch& sc)
+{
+	constexpr int CPL = CFG::CPL;
+	Bwd<CPL> b;
+	int mid = (int)band_mid(w.T - 1, w.ratio);
+	w.load_window(mid);
+	bwd_init_terminal<CFG>(w, b);
+	if (STORE && (w.T - 1) % CFG::CK == 0) ckpt_store<CFG>(sc, (w.T - 1) / CFG::CK, w.lane, b);
+
+	int t = (int)w.T - 2;
+	while (t >= 0)
+	{
+		const uint32_t base = (uint32_t)t & ~31u;
+		float xv;
+		unsigned smask;
+		chunk_prefetch<CFG>(w, base, xv, smask);
+		for (int i = t - (int)base; i >= 0; --i)
+		{
+			const uint32_t tt = base + i;
+			const float x = __shfl_sync(FULL, xv, i);
+			bwd_step<CFG>(w, b, x, (smask >> i) & 1u, mid);
+			if (tt % CFG::RN == 0) bwd_renorm<CFG>(w, b);
+			if (STORE && tt % CFG::CK == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
+		}
+		t = (int)base - 1;
+	}
+	// Zb = bE[0][0] (NT:286): column 0 is ring slot 0 = lane 0, j 0
+	const double z = (double)b.bE[0] + b.OB;
+	return shfl_f64(z, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pass 2 state
+// ------------------------------------------------------------------------------------------------------
+template <int CPL>
+struct Fwd
+{
+	float fM[CPL], fE[CPL];
+	float VM[CPL], VE[CPL];
+	double OF;  // forward values are (true log2 value) - OF, with OF tracking Z2 - OB so that f + b = log2 posterior
+	double OV;  // Viterbi values are (true value) - OV
+	float dL;   // OF(left lane) - OF(this lane)
+	float dVL;  // OV(left lane) - OV(this lane)
+};
+
+template <class CFG>
+struct Smem
+{
+	float* bE;     // [(CK+1)][CPL][32]
+	double* OB;    // [NRN][32]   lane offsets of the backward pass at rows t_lo + i*RN
+	float* inc;    // [NRN][32]   increment subtracted at those rows
+	DYN_DEV explicit Smem(unsigned char* p)
+	{
+		OB = reinterpret_cast<double*>(p);
+		bE = reinterpret_cast<float*>(p + (size_t)CFG::NRN * 32 * 8);
+		inc = bE + (size_t)(CFG::CK + 1) * CFG::CPL * 32;
+	}
+};
+
+// re-express the forward values of this lane relative to the offset target (a double); tracks the offset
+// actually applied so that rounding of the shift never accumulates
+template <class CFG>
+DYN_DEV void fwd_shift_to(Warp<CFG>& w, Fwd<CFG::CPL>& f, double target)
+{
+	constexpr int CPL = CFG::CPL;
+	const float sh = (float)(f.OF - target);
+	if (sh != 0.0f)
+	{
+#pragma unroll
+		for (int j = 0; j < CPL; ++j)
+		{
+			f.fM[j] += sh;
+			f.fE[j] += sh;
+		}
+		f.OF -= (double)sh;
+	}
+	const double ofl = shfl_f64(f.OF, (w.lane + 31) & 31);
+	f.dL = (float)(ofl - f.OF);
+}
+
+template <class CFG>
+DYN_DEV void vit_renorm(Warp<CFG>& w, Fwd<CFG::CPL>& f)
+{
+	constexpr int CPL = CFG::CPL;
+	float lm = fmaxf(f.VM[0], f.VE[0]);
+#pragma unroll
+	for (int j = 1; j < CPL; ++j) lm = fmaxf(lm, fmaxf(f.VM[j], f.VE[j]));
+	const bool dead = lm < DEADT;
+	const float inc = dead ? 0.0f : lm;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		f.VM[j] -= inc;
+		f.VE[j] -= inc;
+	}
+	f.OV += (double)inc;
+	double ovl = shfl_f64(f.OV, (w.lane + 31) & 31);
+	if (dead) f.OV = ovl;
+	ovl = shfl_f64(f.OV, (w.lane + 31) & 31);
+	f.dVL = (float)(ovl - f.OV);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pass 2: forward + posterior + posterior-Viterbi fill.  Returns (Zf - Zb) in log2 units.
+// ------------------------------------------------------------------------------------------------------
+template <class CFG>
+DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
+	double Z2, uint32_t& nrec_out, bool& overflow)
+{
+	constexpr int CPL = CFG::CPL;
+	constexpr int CK = CFG::CK;
+	constexpr int RN = CFG::RN;
+	Smem<CFG> sm(smem_raw);
+	Fwd<CPL> f;
+	Bwd<CPL> b;
+	const int lane = w.lane;
+	const uint32_t T = w.T;
+	uint32_t nrec = 0;
+	overflow = false;
+	float lpe_end = 0.0f;
+
+	int mid_f = 0;  // band centre of the forward row
+	w.load_window(0);
+	const uint32_t kb = (T - 1) / CK;
+	float bEcur[CPL];  // bE of the current forward row
+
+	for (uint32_t k = 0; k <= kb; ++k)
+	{
+		const uint32_t t_lo = k * CK;
+		const uint32_t t_hi = t_lo + CK;
+		// ---- step a: recompute the backward rows of this block into shared memory -----------------------
+		uint32_t src_row;
+		if (t_hi <= T - 1)
+		{
+			src_row = t_hi;
+			const int mid_src = (int)band_mid(src_row, w.ratio);
+			w.slide_window_up(mid_f, mid_src);
+			ckpt_load<CFG>(sc, k + 1, lane, b);
+		}
+		else
+		{
+			src_row = T - 1;
+			const int mid_src = (int)band_mid(src_row, w.ratio);
+			w.slide_window_up(mid_f, mid_src);
+			bwd_init_terminal<CFG>(w, b);
+		}
+		int mid_b = (int)band_mid(src_row, w.ratio);
+		{
+			float* dst = sm.bE + (size_t)(src_row - t_lo) * CPL * 32;
+#pragma unroll
+			for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
+			// offsets in force for the rows above the last renormalisation row of this block
+			sm.OB[((src_row - t_lo + RN - 1) / RN) * 32 + lane] = b.OB;
+			sm.inc[((src_row - t_lo + RN - 1) / RN) * 32 + lane] = 0.0f;
+		}
+		{
+			int t = (int)src_row - 1;
+			while (t >= (int)t_lo)
+			{
+				const uint32_t base = max((uint32_t)t & ~31u, t_lo);
+				// chunk_prefetch works on 32-aligned bases; blocks are CK-aligned with CK <= 32 dividing 32 or not,
+				// so prefetch relative to the aligned base and index with (row - abase)
+				const uint32_t abase = (uint32_t)t & ~31u;
+				float xv;
+				unsigned smask;
+				chunk_prefetch<CFG>(w, abase, xv, smask);
+				for (int tt = t; tt >= (int)base; --tt)
+				{
+					const int i = tt - (int)abase;
+					const float x = __shfl_sync(FULL, xv, i);
+					bwd_step<CFG>(w, b, x, (smask >> i) & 1u, mid_b);
+					float inc = 0.0f;
+					if (tt % RN == 0) inc = bwd_renorm<CFG>(w, b);
+					float* dst = sm.bE + (size_t)(tt - t_lo) * CPL * 32;
+#pragma unroll
+					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
+					if (tt % RN == 0)
+					{
+						sm.OB[((tt - t_lo) / RN) * 32 + lane] = b.OB;
+						sm.inc[((tt - t_lo) / RN) * 32 + lane] = inc;
+					}
+				}
+				t = (int)base - 1;
+			}
+		}
+		__syncwarp();
+		// emission window is now band(t_lo) again (mid_b == mid_f)
+
+		// ---- step b: forward rows t_lo .. min(t_hi, T) - 1 ----------------------------------------------
+		if (k == 0)
+		{
+			// row 0: fE[0][0] = 0 (NT:120) expressed relative to OF = Z2 - OB(0); VE[0][0] = 0 (NT:336)
+#pragma unroll
+			for (int j = 0; j < CPL; ++j)
+			{
+				f.fM[j] = NEG;
+				f.fE[j] = NEG;
+				f.VM[j] = NEG;
+				f.VE[j] = NEG;
+			}
+			f.OF = Z2 - sm.OB[lane];
+			f.OV = 0.0;
+			f.dVL = 0.0f;
+			if (lane == 0)
+			{
+				f.fE[0] = -sm.bE[0];  // exact: Z2 - OB(0)[lane 0] = bE[0][0]
+				f.VE[0] = 0.0f;
+			}
+			const double ofl = shfl_f64(f.OF, (lane + 31) & 31);
+			f.dL = (float)(ofl - f.OF);
+		}
+		{
+			const float* src = sm.bE;
+#pragma unroll
+			for (int j = 0; j < CPL; ++j) bEcur[j] = src[j * 32 + lane];
+		}
+		const uint32_t t_end = min(t_hi, T);
+		uint32_t t = t_lo;
+		while (t < t_end)
+		{
+			const uint32_t abase = t & ~31u;
+			const uint32_t cend = min(abase + 32, t_end);
+			float xv;
+			unsigned smask;
+			chunk_prefetch<CFG>(w, abase, xv, smask);
+			for (; t < cend; ++t)
+			{
+				const int i = (int)(t - abase);
+				const bool last = (t == T - 1);
+				const float x = __shfl_sync(FULL, xv, i);
+				const bool slide = !last && ((smask >> i) & 1u);
+				if (slide) w.activate(mid_f + 1 + w.bw);  // column entering band(t+1)
+
+				// backward values of this row: bE(t) is in bEcur; bM(t) = bE(t+1) + s(x[t]) - inc(t) (NT:200)
+				float s[CPL], bEn[CPL], LPM[CPL], LPE[CPL];
+				const float* nxt = sm.bE + (size_t)(t + 1 - t_lo) * CPL * 32;
+				const bool rn_row = (t % RN == 0);
+				const float inc_t = rn_row ? sm.inc[((t - t_lo) / RN) * 32 + lane] : 0.0f;
+#pragma unroll
+				for (int j = 0; j < CPL; ++j)
+				{
+					s[j] = emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]);
+					bEn[j] = last ? NEG : nxt[j * 32 + lane];
+					float bMj = last ? NEG : (bEn[j] + s[j]);
+					if (rn_row) bMj -= inc_t;
+					LPM[j] = f.fM[j] + bMj;
+					LPE[j] = f.fE[j] + bEcur[j];
+				}
+				if (last)
+				{
+					// (Zf - Zb) in log2 units = log2-posterior of E(T-1, N-1)
+					float v = 0.0f;
+					with_slot<CPL>(lane, pmod((int)w.N - 1, CFG::SLOTS), GetOne<CPL>{LPE, v});
+					lpe_end = __shfl_sync(FULL, v, pmod((int)w.N - 1, CFG::SLOTS) / CPL);
+				}
+
+				if (t >= 1)
+				{
+					// posterior-Viterbi fill (NT:357-362) + decision bits (the test of NT:448 evaluated at fill time)
+					const float vl = __shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31) + f.dVL;
+					unsigned bitsw = 0;
+					float lmax = NEG;
+					float nVM[CPL];
+#pragma unroll
+					for (int j = 0; j < CPL; ++j)
+					{
+						const float left = (j > 0) ? f.VE[j - 1] : vl;
+						nVM[j] = left + LPM[j];
+					}
+#pragma unroll
+					for (int j = 0; j < CPL; ++j)
+					{
+						const float av = f.VM[j] + LPE[j];
+						const float bv = f.VE[j] + LPE[j];
+						f.VE[j] = fmaxf(av, bv);
+						bitsw |= (av >= bv) ? (1u << j) : 0u;
+						f.VM[j] = nVM[j];
+						lmax = fmaxf(lmax, fmaxf(LPM[j], LPE[j]));
+					}
+					if (t % CFG::RV == 0) vit_renorm<CFG>(w, f);
+					sc.bits[(size_t)t * 32 + lane] = (uint16_t)bitsw;
+
+					// sparse posterior records: the few cells per row with a non-negligible posterior
+					if (lane == 0) sc.rowptr[t] = nrec;
+					if (__any_sync(FULL, lmax > args.thr2))
+					{
+						const int n0 = mid_f - w.bw;
+#pragma unroll
+						for (int j = 0; j < CPL; ++j)
+						{
+							const bool hit = fmaxf(LPM[j], LPE[j]) > args.thr2;
+							const unsigned hm = __ballot_sync(FULL, hit);
+							if (hm)
+							{
+								if (hit)
+								{
+									const uint32_t pos = nrec + __popc(hm & ((1u << lane) - 1u));
+									if (pos < args.rec_cap)
+									{
+										PostRec r;
+										r.n = (uint32_t)w.col_of_slot(lane * CPL + j, n0);
+										r.lpm = LPM[j];
+										r.lpe = LPE[j];
+										sc.recs[pos] = r;
+									}
+								}
+								nrec += __popc(hm);
+							}
+						}
+						if (nrec > args.rec_cap)
+						{
+							overflow = true;
+							nrec = (uint32_t)args.rec_cap;
+						}
+					}
+				}
+
+				if (!last)
+				{
+					// forward step to row t+1 (NT:141-150)
+					const float fl = __shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) + f.dL;
+					float nfM[CPL];
+#pragma unroll
+					for (int j = 0; j < CPL; ++j)
+					{
+						const float left = (j > 0) ? f.fE[j - 1] : fl;
+						nfM[j] = left + (s[j] + w.m1);
+					}
+#pragma unroll
+					for (int j = 0; j < CPL; ++j)
+					{
+						f.fE[j] = logplus2(f.fM[j], f.fE[j] + w.e2) + s[j];
+						f.fM[j] = nfM[j];
+						bEcur[j] = bEn[j];
+					}
+					if (slide)
+					{
+						const int nold = mid_f - w.bw;  // column of band(t) that is not in band(t+1)
+						if (nold >= 0)
+						{
+							with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetTwo<CPL>{f.fM, f.fE, NEG});
+							w.deactivate(nold);
+						}
+						++mid_f;
+					}
+					if (rn_row) fwd_shift_to<CFG>(w, f, Z2 - sm.OB[((t - t_lo) / RN + 1) * 32 + lane]);
+				}
+			}
+		}
+		__syncwarp();
+	}
+	if (lane == 0) sc.rowptr[T] = nrec;
+	nrec_out = nrec;
+	return lpe_end;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pass 3: traceback (NT:383-456), path posteriors, per-segment medians (aligner.cpp:247-263)
+// ------------------------------------------------------------------------------------------------------
+DYN_DEV float select_kth(const float* v, uint32_t d, uint32_t kth)
+{
+	// kth smallest (0-based) of d non-negative floats by binary search on the bit pattern
+	uint32_t lo = 0u, hi = 0x7f800000u;  // answer in [lo, hi]
+	while (lo < hi)
+	{
+		const uint32_t midv = lo + (hi - lo) / 2;
+		uint32_t cnt = 0;  // #elements <= midv
+		for (uint32_t i = 0; i < d; ++i) cnt += (__float_as_uint(v[i]) <= midv) ? 1u : 0u;
+		if (cnt >= kth + 1) hi = midv;
+		else lo = midv + 1;
+	}
+	return __uint_as_float(lo);
+}
+
+template <class CFG>
+DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
+	const ReadDesc& rd)
+{
+	constexpr int CPL = CFG::CPL;
+	constexpr int SLOTS = CFG::SLOTS;
+	const int lane = w.lane;
+	const uint32_t T = w.T, N = w.N;
+	uint32_t* border = args.out_sigpos + rd.out_off;  // Kc = N-1 entries
+	uint16_t* sbits = reinterpret_cast<uint16_t*>(smem_raw);  // 32 rows x 32 lanes
+
+	// phase 1: walk the decision bits from (T-1, N-1) in state E
+	uint32_t t = T - 1, n = N - 1;
+	int inM = 0;
+	int ok = 1;
+	while (true)
+	{
+		const uint32_t cbase = t & ~31u;
+		// all lanes stage rows cbase .. cbase+31
+		{
+			const uint32_t r = cbase + lane;
+			const uint4* src = reinterpret_cast<const uint4*>(sc.bits + (size_t)r * 32);
+			uint4* dst = reinterpret_cast<uint4*>(sbits + lane * 32);
+			if (r < T)
+			{
+#pragma unroll
+				for (int q = 0; q < 4; ++q) dst[q] = src[q];
+			}
+		}
+		__syncwarp();
+		if (lane == 0)
+		{
+			while (t >= cbase && t > 0 && n > 0)
+			{
+				if (inM)
+				{
+					sc.pn[t] = n | 0x80000000u;
+					border[n - 1] = t - 1;  // Segment.signalPosition (NT:424-430)
+					--t;
+					--n;
+					inM = 0;
+				}
+				else
+				{
+					sc.pn[t] = n;
+					const int q = (int)(n % SLOTS);
+					const int ql = q / CPL, j = q - ql * CPL;
+					inM = (sbits[(t - cbase) * 32 + ql] >> j) & 1;
+					--t;
+				}
+				if (t < cbase) break;
+			}
+		}
+		__syncwarp();
+		t = __shfl_sync(FULL, t, 0);
+		n = __shfl_sync(FULL, n, 0);
+		inM = __shfl_sync(FULL, inM, 0);
+		if (t == 0 || n == 0) break;
+	}
+	// a complete path consumes every column: n == 0 and the first match sits at row 1
+	const uint32_t t_first = t + 1;  // first path row
+	ok = (n == 0) && !inM;
+	if (!ok) return false;
+	__threadfence_block();
+	__syncwarp();
+
+	// phase 2: posterior of the path cell of every row, normalised by the row's recorded mass
+	for (uint32_t r = t_first + lane; r < T; r += 32)
+	{
+		const uint32_t v = sc.pn[r];
+		const uint32_t col = v & 0x7fffffffu;
+		const bool isM = (v >> 31) != 0;
+		const uint32_t r0 = sc.rowptr[r], r1 = sc.rowptr[r + 1];
+		float mass = 0.0f, lp = 0.0f;
+		bool found = false;
+		for (uint32_t i = r0; i < r1; ++i)
+		{
+			const PostRec rec = sc.recs[i];
+			mass += exp2f(rec.lpm) + exp2f(rec.lpe);
+			if (rec.n == col)
+			{
+				found = true;
+				lp = isM ? rec.lpm : rec.lpe;
+			}
+		}
+		sc.pp[r] = (found && mass > 0.0f) ? exp2f(lp - log2f(mass)) : 0.0f;
+	}
+	__threadfence_block();
+	__syncwarp();
+
+	// phase 3: per-segment median of the path posteriors (NT:418-422, aligner.cpp:247-263)
+	double* prob = args.out_prob + rd.out_off;
+	const uint32_t Kc = N - 1;
+	for (uint32_t sgm = lane; sgm < Kc; sgm += 32)
+	{
+		const uint32_t rs = border[sgm] + 1;
+		const uint32_t re = (sgm + 1 < Kc) ? border[sgm + 1] : (T - 1);  // inclusive
+		const uint32_t d = re - rs + 1;
+		const float* v = sc.pp + rs;
+		double med;
+		if (d & 1u)
+			med = (double)select_kth(v, d, d / 2);
+		else
+		{
+			const float up = select_kth(v, d, d / 2);
+			const float dn = select_kth(v, d, d / 2 - 1);
+			med = ((double)dn + (double)up) / 2.0;
+		}
+		prob[sgm] = med;
+	}
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// training statistics (NT_aligner_api.cpp:494-514 and :641-725) from the sparse posterior records
+// ------------------------------------------------------------------------------------------------------
+// gamma(t,n) = pM + pE is accumulated per lattice column (one kmer per column) into read_w/x/xx; a later
+// kernel folds columns into kmers.  Expected transition counts follow from the state posteriors:
+//   #(E->M) = sum pM(t,n)            (every M(t+1,n) is entered from E(t,n-1))
+//   #(E->E) = sum pE(t,n) - sum pM   (every E is entered from E or from the M directly before it)
+template <class CFG>
+DYN_DEV void train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd,
+	double& xi_m, double& xi_e)
+{
+	const int lane = w.lane;
+	double sm_ = 0.0, se_ = 0.0;
+	for (uint32_t r = 1 + lane; r < w.T; r += 32)
+	{
+		const uint32_t r0 = sc.rowptr[r], r1 = sc.rowptr[r + 1];
+		double mass = 0.0;
+		for (uint32_t i = r0; i < r1; ++i)
+		{
+			const PostRec rec = sc.recs[i];
+			mass += (double)exp2f(rec.lpm) + (double)exp2f(rec.lpe);
+		}
+		if (!(mass > 0.0)) continue;
+		const double inv = 1.0 / mass;
+		const double xo = (double)w.sig[r - 1];
+		for (uint32_t i = r0; i < r1; ++i)
+		{
+			const PostRec rec = sc.recs[i];
+			const double pm = (double)exp2f(rec.lpm) * inv, pe = (double)exp2f(rec.lpe) * inv;
+			const double g = pm + pe;
+			atomicAdd(&args.read_w[rd.pc_off + rec.n], g);
+			atomicAdd(&args.read_x[rd.pc_off + rec.n], g * xo);
+			atomicAdd(&args.read_xx[rd.pc_off + rec.n], g * xo * xo);
+			sm_ += pm;
+			se_ += pe;
+		}
+	}
+	for (int o = 16; o; o >>= 1)
+	{
+		sm_ += shfl_f64(sm_, (lane + o) & 31);
+		se_ += shfl_f64(se_, (lane + o) & 31);
+	}
+	xi_m = sm_;
+	xi_e = se_ - sm_;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the persistent kernel: one single-warp CTA per resident read slot, reads pulled from an atomic queue
+// ------------------------------------------------------------------------------------------------------
+template <class CFG, int MODE>
+DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx, const SlotScratch& sc,
+	unsigned char* smem_raw, int lane)
+{
+	Warp<CFG> w;
+	w.lane = lane;
+	w.S = rd.S;
+	w.T = rd.S + 1;
+	w.N = rd.N;
+	w.bw = (int)rd.bw;
+	w.ratio = rd.ratio;
+	w.sig = args.signal + rd.sig_off;
+	w.pc = args.pc + rd.pc_off;
+	w.m1 = args.m1;
+	w.e2 = args.e2;
+
+	ReadOut out;
+	out.Z = 0.0;
+	out.dZ = 0.0;
+	out.nrec = 0;
+	out.status = ST_OK;
+	out.xi_m = 0.0;
+	out.xi_e = 0.0;
+
+	const double Z2 = (MODE == 0) ? backward_pass<CFG, false>(w, sc) : backward_pass<CFG, true>(w, sc);
+	out.Z = Z2 * LN2;
+	if (!(Z2 > (double)DEADT))
+	{
+		out.status = (MODE == 2) ? ST_TRAIN_FAILED : ST_ALIGN_FAILED;  // Zb is -inf (NT:289)
+	}
+	else if (MODE != 0)
+	{
+		uint32_t nrec = 0;
+		bool overflow = false;
+		const float dz2 = forward_posterior_pass<CFG>(w, sc, args, smem_raw, Z2, nrec, overflow);
+		out.nrec = nrec;
+		out.dZ = (double)dz2 * LN2;
+		// the reference's consistency check (NT:288-291): |Zf - Zb| / (T*B) > 1e-8, B = 2*bw + 3
+		const double cells = (double)w.T * (double)(2 * w.bw + 3);
+		if (!(dz2 > DEADT) || fabs(out.dZ) / cells > 1e-8)
+			out.status = (MODE == 2) ? ST_TRAIN_FAILED : ST_ALIGN_FAILED;
+		else if (overflow)
+			out.status = ST_REC_OVERFLOW;
+		else if (MODE == 1)
+		{
+			if (!traceback_pass<CFG>(w, sc, args, smem_raw, rd)) out.status = ST_INTERNAL;
+		}
+		else
+		{
+			__threadfence_block();
+			__syncwarp();
+			train_stats_pass<CFG>(w, sc, args, rd, out.xi_m, out.xi_e);
+		}
+	}
+	if (lane == 0) args.out[ridx] = out;
+}
+
+} // namespace dyn

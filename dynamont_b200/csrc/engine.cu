@@ -1,0 +1,1135 @@
+// Host engine + C ABI of dynamont_b200 (see include/dynamont_b200.h).
+//
+// Host side of the hot path: model loading (reference aligner.cpp:88-143), input validation (:145-164),
+// batch marshalling, scratch management, kernel launches, result assembly.  Built by nvcc for sm_100a.
+// (tests/emu/ compiles this same file with g++ against a SIMT emulator for GPU-less unit tests of the
+// kernels; that build is test infrastructure and is never loaded by the product.)
+#include "../../include/dynamont_b200.h"
+#include "dp_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace dyn;
+
+// ---------------------------------------------------------------------------------------------------------
+// runtime shim: CUDA runtime in the product, plain memory under the test emulator
+// ---------------------------------------------------------------------------------------------------------
+#ifndef DYN_HOST_EMU
+#define CK_CUDA(x)                                                                                  \
+	do                                                                                              \
+	{                                                                                               \
+		cudaError_t e_ = (x);                                                                       \
+		if (e_ != cudaSuccess)                                                                      \
+			throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + \
+				__FILE__ + ":" + std::to_string(__LINE__));                                         \
+	} while (0)
+
+struct Rt
+{
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	int device = 0;
+	int sms = 148;
+	size_t smem_optin = 0;
+	void init(int dev)
+	{
+		int count = 0;
+		cudaError_t e = cudaGetDeviceCount(&count);
+		if (e != cudaSuccess || count == 0)
+			throw std::runtime_error("dynamont_b200: no usable CUDA device (there is no CPU fallback)");
+		if (dev < 0) CK_CUDA(cudaGetDevice(&dev));
+		device = dev;
+		CK_CUDA(cudaSetDevice(device));
+		cudaDeviceProp p;
+		CK_CUDA(cudaGetDeviceProperties(&p, device));
+		sms = p.multiProcessorCount;
+		smem_optin = p.sharedMemPerBlockOptin;
+		CK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		for (auto& v : ev) CK_CUDA(cudaEventCreate(&v));
+	}
+	void fini()
+	{
+		if (stream) cudaStreamDestroy(stream);
+		for (auto& v : ev)
+			if (v) cudaEventDestroy(v);
+	}
+	void bind() { CK_CUDA(cudaSetDevice(device)); }
+	void* dmalloc(size_t n)
+	{
+		void* p = nullptr;
+		CK_CUDA(cudaMalloc(&p, n ? n : 1));
+		return p;
+	}
+	void dfree(void* p) { cudaFree(p); }
+	void h2d(void* d, const void* h, size_t n) { CK_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream)); }
+	void d2h(void* h, const void* d, size_t n) { CK_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream)); }
+	void zero(void* d, size_t n) { CK_CUDA(cudaMemsetAsync(d, 0, n, stream)); }
+	void fill_ff(void* d, size_t n) { CK_CUDA(cudaMemsetAsync(d, 0xff, n, stream)); }
+	void sync() { CK_CUDA(cudaStreamSynchronize(stream)); }
+	size_t free_bytes()
+	{
+		size_t f = 0, t = 0;
+		CK_CUDA(cudaMemGetInfo(&f, &t));
+		return f;
+	}
+	void mark(int i) { CK_CUDA(cudaEventRecord(ev[i], stream)); }
+	double elapsed(int a, int b)
+	{
+		float ms = 0;
+		CK_CUDA(cudaEventElapsedTime(&ms, ev[a], ev[b]));
+		return ms;
+	}
+};
+#else
+#include <chrono>
+struct Rt
+{
+	int device = 0;
+	int sms = 2;
+	size_t smem_optin = 227 * 1024;
+	double tm[4] = {0, 0, 0, 0};
+	void init(int) {}
+	void fini() {}
+	void bind() {}
+	void* dmalloc(size_t n) { return malloc(n ? n : 1); }
+	void dfree(void* p) { free(p); }
+	void h2d(void* d, const void* h, size_t n) { memcpy(d, h, n); }
+	void d2h(void* h, const void* d, size_t n) { memcpy(h, d, n); }
+	void zero(void* d, size_t n) { memset(d, 0, n); }
+	void fill_ff(void* d, size_t n) { memset(d, 0xff, n); }
+	void sync() {}
+	size_t free_bytes() { return (size_t)4 << 30; }
+	void mark(int i) { tm[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	double elapsed(int a, int b) { return tm[b] - tm[a]; }
+};
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+namespace
+{
+
+// Build-time geometry: 13 columns per lane (ring of 416 >= 2*200+2), checkpoints every 16 rows,
+// backward renormalisation every 4 rows, Viterbi renormalisation every 8 rows.
+using CfgDefault = Cfg<13, 16, 4, 8>;
+
+struct EncodeArgs
+{
+	ReadDesc* reads;
+	uint32_t n_reads;
+	const char* seq;
+	const uint64_t* seq_off;
+	int k;
+	const PosConst* table;
+	PosConst* pc;
+	int32_t* kmers;
+	uint32_t* bad_pos;
+};
+
+DYN_DEV int base_digit(unsigned char ch)
+{
+	// aligner.cpp:46-60 (N/n map to 4, which is >= the alphabet size and therefore invalid, :180)
+	switch (ch)
+	{
+	case 'A': case 'a': return 0;
+	case 'C': case 'c': return 1;
+	case 'G': case 'g': return 2;
+	case 'T': case 't': case 'U': case 'u': return 3;
+	case 'N': case 'n': return 4;
+	default: return -1;
+	}
+}
+
+// K1 (emission constants): kmer encoding (aligner.cpp:166-205) fused with the gather of the per-column
+// Gaussian constants from the pore-model table, so the 4^k table is touched N times per read and never in
+// the DP inner loop.  One warp-CTA per read.
+DYN_DEV void encode_read(const EncodeArgs& a, uint32_t r, int lane)
+{
+	ReadDesc rd = a.reads[r];
+	if (rd.status != ST_OK) return;
+	const char* s = a.seq + a.seq_off[r];
+	const uint32_t Kc = rd.N - 1;
+	PosConst* pc = a.pc + rd.pc_off;
+	int32_t* km = a.kmers + rd.pc_off;
+	if (lane == 0)
+	{
+		PosConst z;
+		z.a = 0.0f; z.b = 0.0f; z.c = CNEG; z.pad = 0.0f;
+		pc[0] = z;  // column 0 scores no kmer
+		km[0] = -1;
+	}
+	uint32_t bad = 0xffffffffu;
+	for (uint32_t c = lane; c < Kc; c += 32)
+	{
+		int id = 0;
+		for (int i = 0; i < a.k; ++i)
+		{
+			const int d = base_digit((unsigned char)s[c + i]);
+			if (d < 0 || d > 3)
+			{
+				bad = min(bad, c + (uint32_t)i);
+				id = -1;
+				break;
+			}
+			id = id * 4 + d;
+		}
+		if (id >= 0)
+		{
+			pc[c + 1] = a.table[id];
+			km[c + 1] = id;
+		}
+	}
+	for (int o = 16; o; o >>= 1) bad = min(bad, __shfl_sync(FULL, bad, (lane + o) & 31));
+	if (lane == 0)
+	{
+		a.bad_pos[r] = bad;
+		if (bad != 0xffffffffu) a.reads[r].status = ST_INVALID_NT;
+	}
+}
+
+template <class CFG, int MODE>
+DYN_DEV void align_worker(const BatchArgs& args, unsigned char* smem_raw, int lane, unsigned slot)
+{
+	const SlotScratch sc = args.slots[slot];
+	while (true)
+	{
+		uint32_t i = 0;
+		if (lane == 0) i = atomicAdd(args.queue, 1u);
+		i = __shfl_sync(FULL, i, 0);
+		if (i >= args.n_reads) break;
+		const uint32_t ridx = args.order[i];
+		const ReadDesc rd = args.reads[ridx];
+		if (rd.status != ST_OK)
+		{
+			if (lane == 0)
+			{
+				ReadOut o;
+				o.Z = 0.0; o.dZ = 0.0; o.nrec = 0; o.status = rd.status; o.xi_m = 0.0; o.xi_e = 0.0;
+				args.out[ridx] = o;
+			}
+			continue;
+		}
+		align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
+		__syncwarp();
+	}
+}
+
+struct FoldArgs
+{
+	const ReadDesc* reads;
+	const ReadOut* out;
+	uint32_t n_reads;
+	const int32_t* kmers;
+	const double* read_w;
+	const double* read_x;
+	const double* read_xx;
+	double* stat_w;
+	double* stat_x;
+	double* stat_xx;
+};
+
+// folds per-column training statistics into the pooled per-kmer table (one warp-CTA per read)
+DYN_DEV void fold_read(const FoldArgs& a, uint32_t r, int lane)
+{
+	const ReadDesc rd = a.reads[r];
+	if (a.out[r].status != ST_OK) return;
+	for (uint32_t n = 1 + lane; n < rd.N; n += 32)
+	{
+		const double wv = a.read_w[rd.pc_off + n];
+		if (wv == 0.0) continue;
+		const int32_t q = a.kmers[rd.pc_off + n];
+		atomicAdd(&a.stat_w[q], wv);
+		atomicAdd(&a.stat_x[q], a.read_x[rd.pc_off + n]);
+		atomicAdd(&a.stat_xx[q], a.read_xx[rd.pc_off + n]);
+	}
+}
+
+#ifndef DYN_HOST_EMU
+__global__ void __launch_bounds__(32) k_encode(EncodeArgs a)
+{
+	for (uint32_t r = blockIdx.x; r < a.n_reads; r += gridDim.x) encode_read(a, r, threadIdx.x);
+}
+template <class CFG, int MODE>
+__global__ void __launch_bounds__(32) k_align(BatchArgs args)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	align_worker<CFG, MODE>(args, smem_raw, threadIdx.x, blockIdx.x);
+}
+__global__ void __launch_bounds__(32) k_fold(FoldArgs a)
+{
+	for (uint32_t r = blockIdx.x; r < a.n_reads; r += gridDim.x) fold_read(a, r, threadIdx.x);
+}
+#endif
+
+void launch_encode(Rt& rt, const EncodeArgs& a)
+{
+	if (!a.n_reads) return;
+#ifndef DYN_HOST_EMU
+	const unsigned grid = std::min<uint32_t>(a.n_reads, 65535u * 16u);
+	k_encode<<<grid, 32, 0, rt.stream>>>(a);
+	CK_CUDA(cudaGetLastError());
+#else
+	(void)rt;
+	simt::launch(a.n_reads, 0, [&]() { encode_read(a, blockIdx.x, threadIdx.x); });
+#endif
+}
+
+template <class CFG>
+void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
+{
+	const size_t smem = CFG::SMEM_BYTES;
+#ifndef DYN_HOST_EMU
+	static bool attr_set = false;
+	if (!attr_set)
+	{
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	if (mode == 0) k_align<CFG, 0><<<grid, 32, smem, rt.stream>>>(args);
+	else if (mode == 1) k_align<CFG, 1><<<grid, 32, smem, rt.stream>>>(args);
+	else k_align<CFG, 2><<<grid, 32, smem, rt.stream>>>(args);
+	CK_CUDA(cudaGetLastError());
+#else
+	(void)rt;
+	if (mode == 0) simt::launch(grid, smem, [&]() { align_worker<CFG, 0>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else if (mode == 1) simt::launch(grid, smem, [&]() { align_worker<CFG, 1>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else simt::launch(grid, smem, [&]() { align_worker<CFG, 2>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+#endif
+}
+
+void launch_fold(Rt& rt, const FoldArgs& a)
+{
+	if (!a.n_reads) return;
+#ifndef DYN_HOST_EMU
+	const unsigned grid = std::min<uint32_t>(a.n_reads, 65535u * 16u);
+	k_fold<<<grid, 32, 0, rt.stream>>>(a);
+	CK_CUDA(cudaGetLastError());
+#else
+	(void)rt;
+	simt::launch(a.n_reads, 0, [&]() { fold_read(a, blockIdx.x, threadIdx.x); });
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device buffer that only ever grows
+// ---------------------------------------------------------------------------------------------------------
+struct DevBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	void* get(Rt& rt, size_t n)
+	{
+		if (n > cap)
+		{
+			if (p) rt.dfree(p);
+			p = nullptr;
+			cap = 0;
+			p = rt.dmalloc(n);
+			cap = n;
+		}
+		return p;
+	}
+	void release(Rt& rt)
+	{
+		if (p) rt.dfree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// the aligner handle
+// ---------------------------------------------------------------------------------------------------------
+struct dyn_aligner
+{
+	Rt rt;
+	std::mutex mu;
+	std::string last_error;
+	// pore / model (aligner.cpp:13-143)
+	bool rna = false;
+	int k = 0;
+	int alphabet = 0;
+	uint64_t K = 0;
+	int band = 400;
+	double trans[3] = {0, 0, 0};  // log m1, e1, e2 (NT:84-86)
+	std::vector<double> mean, stdev;
+	// tuning
+	int warps_per_sm = 8;
+	double thr2 = -22.0;
+	double recs_per_row = 8.0;
+	double mem_fraction = 0.85;
+	// device state
+	DevBuf d_table, d_sig, d_seq, d_seqoff, d_desc, d_order, d_pc, d_kmers, d_bad, d_out, d_sigpos, d_prob, d_scratch,
+		d_slots, d_queue, d_rw, d_rx, d_rxx, d_sw, d_sx, d_sxx;
+	bool table_dirty = true;
+	double timing[3] = {0, 0, 0};
+
+	void upload_table();
+};
+
+namespace
+{
+
+struct PoreInfo
+{
+	const char* name;
+	bool rna;
+	int k;
+	double m1, e1, e2;
+};
+// aligner.cpp:62-86 and NT_aligner_api.cpp:36-82
+const PoreInfo PORES[] = {
+	{"rna002", true, 5, 0.019889650396799997, 1.0, 0.9801103496029998},
+	{"rna004", true, 9, 0.031111753637096777, 1.0, 0.9688882463622581},
+	{"dna_r9", false, 5, 1.0, 1.0, 1.0},
+	{"dna_r10_260bps", false, 9, 0.031111753637096777, 1.0, 0.9688882463622581},
+	{"dna_r10_400bps", false, 9, 0.031111753637096777, 1.0, 0.9688882463622581},
+};
+
+int host_digit(unsigned char ch)
+{
+	switch (ch)
+	{
+	case 'A': case 'a': return 0;
+	case 'C': case 'c': return 1;
+	case 'G': case 'g': return 2;
+	case 'T': case 't': case 'U': case 'u': return 3;
+	case 'N': case 'n': return 4;
+	default: return -1;
+	}
+}
+
+// Aligner::loadModel (aligner.cpp:88-143) incl. its error strings
+void load_model(dyn_aligner& A, const std::string& path)
+{
+	std::ifstream file(path);
+	if (!file) throw std::runtime_error("Could not open model file, please prove a valid model path " + path);
+	std::string line;
+	std::getline(file, line);
+	std::set<char> alphabet;
+	std::vector<std::string> rows;
+	while (std::getline(file, line))
+	{
+		const std::string kmer = line.substr(0, line.find('\t'));
+		if (kmer.size() != (size_t)A.k) throw std::runtime_error("Inconsistent kmer size in model");
+		for (char c : kmer) alphabet.insert(c);
+		rows.push_back(line);
+	}
+	A.alphabet = (int)alphabet.size();
+	A.K = (uint64_t)std::pow((double)A.alphabet, (double)A.k);
+	if (A.alphabet != 4)
+		throw std::runtime_error("dynamont_b200: pore models must use a 4-letter alphabet (found " +
+			std::to_string(A.alphabet) + ")");
+	A.mean.assign(A.K, 0.0);
+	A.stdev.assign(A.K, 0.0);
+	for (const std::string& row : rows)
+	{
+		std::stringstream ss(row);
+		std::string kmer, m, s;
+		std::getline(ss, kmer, '\t');
+		std::getline(ss, m, '\t');
+		std::getline(ss, s, '\t');
+		if (A.rna) std::reverse(kmer.begin(), kmer.end());
+		uint64_t v = 0;
+		for (char c : kmer)
+		{
+			const int d = host_digit((unsigned char)c);
+			if (d < 0 || d >= A.alphabet) throw std::runtime_error("Invalid nucleotide in k-mer: " + kmer);
+			v = v * (uint64_t)A.alphabet + (uint64_t)d;
+		}
+		A.mean[v] = std::stod(m);
+		A.stdev[v] = std::stod(s);
+	}
+}
+
+} // namespace
+
+void dyn_aligner::upload_table()
+{
+	// per-kmer constants of log2 N(x; mu, sigma) = c - (x*a - b)^2  (aligner.cpp:287-292 in the log2 domain)
+	std::vector<PosConst> t(K);
+	for (uint64_t q = 0; q < K; ++q)
+	{
+		const double sd = stdev[q], mu = mean[q];
+		const double a = std::sqrt(0.5 * LOG2E) / sd;
+		t[q].a = (float)a;
+		t[q].b = (float)(mu * a);
+		t[q].c = (float)(-std::log2(sd) - 0.5 * std::log2(2.0 * M_PI));
+		t[q].pad = 0.0f;
+	}
+	void* d = d_table.get(rt, K * sizeof(PosConst));
+	rt.h2d(d, t.data(), K * sizeof(PosConst));
+	rt.sync();
+	table_dirty = false;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch driver
+// ---------------------------------------------------------------------------------------------------------
+namespace
+{
+
+struct BatchIO
+{
+	const float* sig_host = nullptr;    // exactly one of sig_host / sig_host64 / sig_dev is set
+	const double* sig_host64 = nullptr;
+	const float* sig_dev = nullptr;
+	const char* seq_host = nullptr;     // or seq_dev
+	const char* seq_dev = nullptr;
+	const uint64_t* sig_off = nullptr;
+	const uint64_t* seq_off = nullptr;
+	uint32_t n = 0;
+};
+
+struct BatchResult
+{
+	std::vector<ReadOut> out;
+	std::vector<uint32_t> bad_pos;
+	std::vector<uint64_t> seg_off;  // n+1
+	std::vector<ReadDesc> desc;
+};
+
+// mode: 0 Z only, 1 align, 2 train.  sigpos/prob (host) receive the segment arrays for mode 1.
+void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
+	double* pooled, double* per_read_w)
+{
+	using CFG = CfgDefault;
+	Rt& rt = A.rt;
+	rt.bind();
+	if (A.table_dirty) A.upload_table();
+	const uint32_t n = io.n;
+	res.out.assign(n, ReadOut{});
+	res.bad_pos.assign(n, 0xffffffffu);
+	res.seg_off.assign((size_t)n + 1, 0);
+	res.desc.assign(n, ReadDesc{});
+	A.timing[0] = A.timing[1] = A.timing[2] = 0.0;
+	if (n == 0) return;
+
+	// ---- host: validation (aligner.cpp:145-164) and geometry (NT:240-247) ------------------------------------
+	uint64_t pc_total = 0, seg_total = 0;
+	uint32_t maxT = 0;
+	std::vector<uint32_t> order;
+	order.reserve(n);
+	for (uint32_t r = 0; r < n; ++r)
+	{
+		ReadDesc& d = res.desc[r];
+		const uint64_t S = io.sig_off[r + 1] - io.sig_off[r];
+		const uint64_t L = io.seq_off[r + 1] - io.seq_off[r];
+		d.sig_off = io.sig_off[r];
+		d.status = ST_OK;
+		res.seg_off[r] = seg_total;
+		if (S < 1) d.status = ST_SIGNAL_EMPTY;
+		else if (L < (uint64_t)A.k) d.status = ST_SEQ_SHORT;
+		else if (S < 2 * (L - A.k + 1)) d.status = ST_SIGNAL_SHORT;
+		else if (S >= 0x7fffff00ull) d.status = ST_INTERNAL;
+		if (L >= (uint64_t)A.k) seg_total += L - A.k + 1;
+		if (d.status != ST_OK)
+		{
+			d.S = 0; d.N = 0; d.bw = 0; d.ratio = 0; d.pc_off = pc_total; d.out_off = res.seg_off[r];
+			continue;
+		}
+		const uint64_t Kc = L - A.k + 1;
+		d.S = (uint32_t)S;
+		d.N = (uint32_t)(Kc + 1);
+		d.bw = (uint32_t)std::min<uint64_t>((uint64_t)A.band / 2, (uint64_t)d.N / 2);
+		d.ratio = (double)d.N / (double)(S + 1);
+		d.pc_off = pc_total;
+		d.out_off = res.seg_off[r];
+		pc_total += d.N;
+		if (2 * (int)d.bw + 2 > CFG::SLOTS) d.status = ST_BAND_UNSUPPORTED;
+		else
+		{
+			order.push_back(r);
+			maxT = std::max(maxT, d.S + 1);
+		}
+	}
+	res.seg_off[n] = seg_total;
+	// longest first: the work queue then behaves like LPT scheduling
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+		return (uint64_t)res.desc[x].S * (2 * res.desc[x].bw + 1) > (uint64_t)res.desc[y].S * (2 * res.desc[y].bw + 1);
+	});
+	for (uint32_t r = 0; r < n; ++r)
+		if (res.desc[r].status != ST_OK) res.out[r].status = res.desc[r].status;
+	if (order.empty()) return;
+
+	// ---- device inputs --------------------------------------------------------------------------------------------
+	const uint64_t sig_total = io.sig_off[n];
+	const uint64_t seq_total = io.seq_off[n];
+	const float* d_sig = io.sig_dev;
+	std::vector<float> conv;
+	if (!d_sig)
+	{
+		float* p = (float*)A.d_sig.get(rt, sig_total * sizeof(float));
+		if (io.sig_host64)
+		{
+			conv.resize(sig_total);
+			for (uint64_t i = 0; i < sig_total; ++i) conv[i] = (float)io.sig_host64[i];
+			rt.h2d(p, conv.data(), sig_total * sizeof(float));
+		}
+		else
+			rt.h2d(p, io.sig_host, sig_total * sizeof(float));
+		d_sig = p;
+	}
+	const char* d_seq = io.seq_dev;
+	if (!d_seq)
+	{
+		char* p = (char*)A.d_seq.get(rt, seq_total);
+		rt.h2d(p, io.seq_host, seq_total);
+		d_seq = p;
+	}
+	uint64_t* d_seqoff = (uint64_t*)A.d_seqoff.get(rt, ((size_t)n + 1) * 8);
+	rt.h2d(d_seqoff, io.seq_off, ((size_t)n + 1) * 8);
+	ReadDesc* d_desc = (ReadDesc*)A.d_desc.get(rt, (size_t)n * sizeof(ReadDesc));
+	rt.h2d(d_desc, res.desc.data(), (size_t)n * sizeof(ReadDesc));
+	uint32_t* d_order = (uint32_t*)A.d_order.get(rt, order.size() * 4);
+	rt.h2d(d_order, order.data(), order.size() * 4);
+	PosConst* d_pc = (PosConst*)A.d_pc.get(rt, pc_total * sizeof(PosConst));
+	int32_t* d_kmers = (int32_t*)A.d_kmers.get(rt, pc_total * 4);
+	uint32_t* d_bad = (uint32_t*)A.d_bad.get(rt, (size_t)n * 4);
+	rt.fill_ff(d_bad, (size_t)n * 4);
+	ReadOut* d_out = (ReadOut*)A.d_out.get(rt, (size_t)n * sizeof(ReadOut));
+	rt.zero(d_out, (size_t)n * sizeof(ReadOut));
+	uint32_t* d_queue = (uint32_t*)A.d_queue.get(rt, 64);
+	rt.zero(d_queue, 64);
+	uint32_t* d_sigpos = nullptr;
+	double* d_prob = nullptr;
+	if (mode == 1)
+	{
+		d_sigpos = (uint32_t*)A.d_sigpos.get(rt, seg_total * 4);
+		d_prob = (double*)A.d_prob.get(rt, seg_total * 8);
+	}
+
+	// ---- K1: kmer encoding + emission constants ---------------------------------------------------------------
+	EncodeArgs ea;
+	ea.reads = d_desc; ea.n_reads = n; ea.seq = d_seq; ea.seq_off = d_seqoff; ea.k = A.k;
+	ea.table = (const PosConst*)A.d_table.p; ea.pc = d_pc; ea.kmers = d_kmers; ea.bad_pos = d_bad;
+	rt.mark(0);
+	launch_encode(rt, ea);
+	rt.mark(1);
+
+	// ---- scratch: one slot per resident warp, sized for the longest read --------------------------------------
+	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * A.warps_per_sm, order.size());
+	size_t per_slot = 0;
+	uint64_t rec_cap = 0;
+	size_t o_ck = 0, o_ob = 0, o_bits = 0, o_rp = 0, o_rec = 0, o_pn = 0, o_pp = 0;
+	if (mode != 0)
+	{
+		const size_t nck = (size_t)maxT / CFG::CK + 2;
+		rec_cap = (uint64_t)std::min<double>((double)maxT * A.recs_per_row, (double)maxT * (2.0 * (A.band / 2) + 1.0)) + 64;
+		size_t o = 0;
+		o_ck = o; o = align_up(o + nck * CFG::CKF * 4, 256);
+		o_ob = o; o = align_up(o + nck * 32 * 8, 256);
+		o_bits = o; o = align_up(o + ((size_t)maxT + 32) * 64, 256);
+		o_rp = o; o = align_up(o + ((size_t)maxT + 2) * 4, 256);
+		o_rec = o; o = align_up(o + rec_cap * sizeof(PostRec), 256);
+		o_pn = o; o = align_up(o + ((size_t)maxT + 1) * 4, 256);
+		o_pp = o; o = align_up(o + ((size_t)maxT + 1) * 4, 256);
+		per_slot = o;
+		const size_t budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
+		const size_t fit = std::max<size_t>(1, budget / per_slot);
+		grid = (unsigned)std::min<size_t>(grid, fit);
+	}
+	std::vector<SlotScratch> slots(grid);
+	if (mode != 0)
+	{
+		unsigned char* base = (unsigned char*)A.d_scratch.get(rt, per_slot * grid);
+		for (unsigned s = 0; s < grid; ++s)
+		{
+			unsigned char* b = base + per_slot * s;
+			slots[s].ckpt = (float*)(b + o_ck);
+			slots[s].ckpt_ob = (double*)(b + o_ob);
+			slots[s].bits = (uint16_t*)(b + o_bits);
+			slots[s].rowptr = (uint32_t*)(b + o_rp);
+			slots[s].recs = (PostRec*)(b + o_rec);
+			slots[s].pn = (uint32_t*)(b + o_pn);
+			slots[s].pp = (float*)(b + o_pp);
+		}
+	}
+	else
+		memset(slots.data(), 0, slots.size() * sizeof(SlotScratch));
+	SlotScratch* d_slots = (SlotScratch*)A.d_slots.get(rt, (size_t)grid * sizeof(SlotScratch));
+	rt.h2d(d_slots, slots.data(), (size_t)grid * sizeof(SlotScratch));
+
+	BatchArgs ba;
+	memset(&ba, 0, sizeof(ba));
+	ba.reads = d_desc; ba.order = d_order; ba.n_reads = (uint32_t)order.size(); ba.queue = d_queue;
+	ba.signal = d_sig; ba.pc = d_pc; ba.slots = d_slots; ba.rec_cap = rec_cap; ba.out = d_out;
+	ba.out_sigpos = d_sigpos; ba.out_prob = d_prob;
+	ba.m1 = (float)(A.trans[0] * LOG2E);
+	ba.e2 = (float)(A.trans[2] * LOG2E);
+	ba.thr2 = (float)A.thr2;
+	ba.mode = mode;
+	ba.kmers = d_kmers;
+	if (mode == 2)
+	{
+		ba.read_w = (double*)A.d_rw.get(rt, pc_total * 8);
+		ba.read_x = (double*)A.d_rx.get(rt, pc_total * 8);
+		ba.read_xx = (double*)A.d_rxx.get(rt, pc_total * 8);
+		rt.zero(ba.read_w, pc_total * 8);
+		rt.zero(ba.read_x, pc_total * 8);
+		rt.zero(ba.read_xx, pc_total * 8);
+		ba.stat_w = (double*)A.d_sw.get(rt, A.K * 8);
+		ba.stat_x = (double*)A.d_sx.get(rt, A.K * 8);
+		ba.stat_xx = (double*)A.d_sxx.get(rt, A.K * 8);
+		rt.zero(ba.stat_w, A.K * 8);
+		rt.zero(ba.stat_x, A.K * 8);
+		rt.zero(ba.stat_xx, A.K * 8);
+	}
+
+	// ---- K2..K5: the DP kernel ------------------------------------------------------------------------------------
+	rt.mark(2);
+	launch_align<CFG>(rt, ba, grid, mode);
+	rt.mark(3);
+	int launches = 2;
+	if (mode == 2)
+	{
+		FoldArgs fa;
+		fa.reads = d_desc; fa.out = d_out; fa.n_reads = n; fa.kmers = d_kmers;
+		fa.read_w = ba.read_w; fa.read_x = ba.read_x; fa.read_xx = ba.read_xx;
+		fa.stat_w = ba.stat_w; fa.stat_x = ba.stat_x; fa.stat_xx = ba.stat_xx;
+		launch_fold(rt, fa);
+		++launches;
+	}
+
+	// ---- results ---------------------------------------------------------------------------------------------------
+	rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
+	rt.d2h(res.bad_pos.data(), d_bad, (size_t)n * 4);
+	if (mode == 1 && seg_total)
+	{
+		rt.d2h(sigpos_h, d_sigpos, seg_total * 4);
+		rt.d2h(prob_h, d_prob, seg_total * 8);
+	}
+	if (mode == 2 && pooled)
+	{
+		rt.d2h(pooled, ba.stat_w, A.K * 8);
+		rt.d2h(pooled + A.K, ba.stat_x, A.K * 8);
+		rt.d2h(pooled + 2 * A.K, ba.stat_xx, A.K * 8);
+	}
+	if (mode == 2 && per_read_w)
+	{
+		rt.d2h(per_read_w, ba.read_w, pc_total * 8);
+		rt.d2h(per_read_w + pc_total, ba.read_x, pc_total * 8);
+		rt.d2h(per_read_w + 2 * pc_total, ba.read_xx, pc_total * 8);
+	}
+	rt.sync();
+	A.timing[0] = rt.elapsed(0, 1);
+	A.timing[1] = rt.elapsed(2, 3);
+	A.timing[2] = launches;
+	for (uint32_t r = 0; r < n; ++r)
+	{
+		if (res.desc[r].status != ST_OK && res.desc[r].status != ST_INVALID_NT) res.out[r].status = res.desc[r].status;
+		if (res.bad_pos[r] != 0xffffffffu) res.out[r].status = ST_INVALID_NT;
+	}
+}
+
+// Re-run reads whose sparse-record buffer overflowed, with a buffer that can hold every in-band cell.
+struct SubsetBatch
+{
+	std::vector<uint64_t> sig_off, seq_off;
+	std::vector<float> sig;
+	std::vector<double> sig64;
+	std::string seq;
+};
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C"
+{
+
+dyn_aligner* dyn_create(const char* model_path, const char* pore, const char* mode, int threads, int band,
+	int device, char* err, size_t errlen, int* err_kind)
+{
+	(void)threads;  // accepted and unused, like the reference
+	if (err_kind) *err_kind = 0;
+	dyn_aligner* A = nullptr;
+	try
+	{
+		const PoreInfo* pi = nullptr;
+		for (const PoreInfo& p : PORES)
+			if (std::string(p.name) == pore) pi = &p;
+		if (!pi)
+		{
+			if (err_kind) *err_kind = 1;
+			throw std::invalid_argument(std::string("Unknown pore type: ") + pore);  // aligner_bindings.cpp:31
+		}
+		const std::string m(mode ? mode : "basic");
+		if (m == "resquiggle" || m == "ntk")
+			throw std::runtime_error("dynamont_b200: resquiggle (NTK) mode is not built yet; use mode='basic'");
+		if (m != "basic" && m != "nt")
+		{
+			if (err_kind) *err_kind = 1;
+			throw std::invalid_argument("Unknown aligner mode: " + m);  // aligner_bindings.cpp:50
+		}
+		A = new dyn_aligner();
+		A->rna = pi->rna;
+		A->k = pi->k;
+		A->band = band;
+		A->trans[0] = std::log(pi->m1);
+		A->trans[1] = std::log(pi->e1);
+		A->trans[2] = std::log(pi->e2);
+		load_model(*A, model_path);
+		A->rt.init(device);
+		A->upload_table();
+		return A;
+	}
+	catch (const std::exception& e)
+	{
+		if (err && errlen)
+		{
+			std::strncpy(err, e.what(), errlen - 1);
+			err[errlen - 1] = 0;
+		}
+		delete A;
+		return nullptr;
+	}
+}
+
+void dyn_destroy(dyn_aligner* A)
+{
+	if (!A) return;
+	try
+	{
+		A->rt.bind();
+		for (DevBuf* b : {&A->d_table, &A->d_sig, &A->d_seq, &A->d_seqoff, &A->d_desc, &A->d_order, &A->d_pc, &A->d_kmers,
+				 &A->d_bad, &A->d_out, &A->d_sigpos, &A->d_prob, &A->d_scratch, &A->d_slots, &A->d_queue, &A->d_rw,
+				 &A->d_rx, &A->d_rxx, &A->d_sw, &A->d_sx, &A->d_sxx})
+			b->release(A->rt);
+		A->rt.fini();
+	}
+	catch (...)
+	{
+	}
+	delete A;
+}
+
+int dyn_kmer_size(const dyn_aligner* A) { return A->k; }
+uint64_t dyn_num_kmers(const dyn_aligner* A) { return A->K; }
+int dyn_is_rna(const dyn_aligner* A) { return A->rna ? 1 : 0; }
+
+void dyn_model(const dyn_aligner* A, double* mean, double* stdev)
+{
+	std::memcpy(mean, A->mean.data(), A->K * 8);
+	std::memcpy(stdev, A->stdev.data(), A->K * 8);
+}
+
+int dyn_set_model(dyn_aligner* A, const double* mean, const double* stdev)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	A->mean.assign(mean, mean + A->K);
+	A->stdev.assign(stdev, stdev + A->K);
+	A->table_dirty = true;
+	return 0;
+}
+
+void dyn_transitions(const dyn_aligner* A, double* log3)
+{
+	log3[0] = A->trans[0];
+	log3[1] = A->trans[1];
+	log3[2] = A->trans[2];
+}
+
+uint64_t dyn_count_segments(const dyn_aligner* A, const uint64_t* seq_off, uint32_t n_reads)
+{
+	uint64_t s = 0;
+	for (uint32_t r = 0; r < n_reads; ++r)
+	{
+		const uint64_t L = seq_off[r + 1] - seq_off[r];
+		if (L >= (uint64_t)A->k) s += L - A->k + 1;
+	}
+	return s;
+}
+
+uint64_t dyn_read_cells(const dyn_aligner* A, uint64_t S, uint64_t L)
+{
+	if (S < 1 || L < (uint64_t)A->k) return 0;
+	const uint64_t T = S + 1, N = L - A->k + 2;
+	const uint64_t bw = std::min<uint64_t>((uint64_t)A->band / 2, N / 2);
+	const double ratio = (double)N / (double)T;
+	uint64_t cells = 0;
+	for (uint64_t t = 1; t < T; ++t)
+	{
+		const uint64_t mid = (uint64_t)((double)t * ratio);
+		const uint64_t lo = std::max<uint64_t>(mid >= bw ? mid - bw : 0, 1);
+		const uint64_t hi = std::min<uint64_t>(mid + bw + 1, N);
+		if (hi > lo) cells += hi - lo;
+	}
+	return cells;
+}
+
+static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilities, dyn_read_result* results,
+	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	try
+	{
+		BatchResult res;
+		const uint64_t seg_total = dyn_count_segments(A, io.seq_off, io.n);
+		std::vector<uint32_t> sigpos(calc_probabilities ? seg_total : 0);
+		run_batch(*A, io, calc_probabilities ? 1 : 0, res, sigpos.data(), probabilities, nullptr, nullptr);
+
+		// retry reads whose sparse posterior buffer overflowed, one by one with a full-size buffer
+		std::vector<uint32_t> retry;
+		for (uint32_t r = 0; r < io.n; ++r)
+			if (res.out[r].status == ST_REC_OVERFLOW) retry.push_back(r);
+		if (!retry.empty())
+		{
+			const double saved = A->recs_per_row;
+			A->recs_per_row = 1e9;  // clamped to the band width inside run_batch
+			for (uint32_t r : retry)
+			{
+				BatchIO one = io;
+				one.n = 1;
+				uint64_t so[2] = {io.sig_off[r], io.sig_off[r + 1]};
+				uint64_t qo[2] = {io.seq_off[r], io.seq_off[r + 1]};
+				// offsets are absolute into the caller's arrays, which run_batch indexes from sig_off[0]
+				one.sig_off = so;
+				one.seq_off = qo;
+				BatchResult r1;
+				const uint64_t kc = res.seg_off[r + 1] - res.seg_off[r];
+				std::vector<uint32_t> sp(kc);
+				std::vector<double> pr(kc);
+				// single-read batches upload [0, sig_off[1]) — shift the base pointers instead
+				BatchIO sh = one;
+				uint64_t so0[2] = {0, so[1] - so[0]};
+				uint64_t qo0[2] = {0, qo[1] - qo[0]};
+				sh.sig_off = so0;
+				sh.seq_off = qo0;
+				if (io.sig_host) sh.sig_host = io.sig_host + so[0];
+				if (io.sig_host64) sh.sig_host64 = io.sig_host64 + so[0];
+				if (io.sig_dev) sh.sig_dev = io.sig_dev + so[0];
+				if (io.seq_host) sh.seq_host = io.seq_host + qo[0];
+				if (io.seq_dev) sh.seq_dev = io.seq_dev + qo[0];
+				run_batch(*A, sh, 1, r1, sp.data(), pr.data(), nullptr, nullptr);
+				res.out[r] = r1.out[0];
+				std::copy(sp.begin(), sp.end(), sigpos.begin() + res.seg_off[r]);
+				std::copy(pr.begin(), pr.end(), probabilities + res.seg_off[r]);
+			}
+			A->recs_per_row = saved;
+		}
+
+		for (uint32_t r = 0; r < io.n; ++r)
+		{
+			dyn_read_result& o = results[r];
+			std::memset(&o, 0, sizeof(o));
+			o.status = res.out[r].status == ST_REC_OVERFLOW ? (int32_t)ST_INTERNAL : res.out[r].status;
+			o.seg_offset = res.seg_off[r];
+			o.Z = res.out[r].Z;
+			if (o.status == ST_INVALID_NT)
+			{
+				const uint64_t pos = io.seq_off[r] + res.bad_pos[r];
+				if (io.seq_host) o.bad_char = io.seq_host[pos];
+				else
+				{
+					A->rt.d2h(&o.bad_char, io.seq_dev + pos, 1);
+					A->rt.sync();
+				}
+			}
+			if (o.status == ST_OK && calc_probabilities)
+			{
+				const uint64_t kc = res.seg_off[r + 1] - res.seg_off[r];
+				o.n_segments = kc;
+				for (uint64_t i = 0; i < kc; ++i)
+				{
+					sequence_positions[o.seg_offset + i] = i + (uint64_t)A->k / 2;  // n - 1 + k/2 (NT:421)
+					signal_positions[o.seg_offset + i] = sigpos[o.seg_offset + i];
+				}
+			}
+		}
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		A->last_error = e.what();
+		return -1;
+	}
+}
+
+int dyn_align_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results,
+	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities)
+{
+	BatchIO io;
+	io.sig_host = signal; io.seq_host = seq; io.sig_off = sig_off; io.seq_off = seq_off; io.n = n_reads;
+	return align_common(A, io, calc_probabilities, results, sequence_positions, signal_positions, probabilities);
+}
+
+int dyn_align_batch_f64(dyn_aligner* A, const double* signal, const uint64_t* sig_off, const char* seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results,
+	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities)
+{
+	BatchIO io;
+	io.sig_host64 = signal; io.seq_host = seq; io.sig_off = sig_off; io.seq_off = seq_off; io.n = n_reads;
+	return align_common(A, io, calc_probabilities, results, sequence_positions, signal_positions, probabilities);
+}
+
+int dyn_align_batch_device(dyn_aligner* A, const float* d_signal, const uint64_t* sig_off, const char* d_seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results,
+	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities)
+{
+	BatchIO io;
+	io.sig_dev = d_signal; io.seq_dev = d_seq; io.sig_off = sig_off; io.seq_off = seq_off; io.n = n_reads;
+	return align_common(A, io, calc_probabilities, results, sequence_positions, signal_positions, probabilities);
+}
+
+int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq,
+	const uint64_t* seq_off, uint32_t n_reads, dyn_train_result* results, double* pooled_w, double* pooled_x,
+	double* pooled_xx, double* pooled_xi, double* per_read_mean, double* per_read_stdev)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	try
+	{
+		BatchIO io;
+		io.sig_host = signal; io.seq_host = seq; io.sig_off = sig_off; io.seq_off = seq_off; io.n = n_reads;
+		BatchResult res;
+		const uint64_t K = A->K;
+		std::vector<double> pooled(3 * K, 0.0);
+		uint64_t pc_total = 0;
+		for (uint32_t r = 0; r < n_reads; ++r)
+		{
+			const uint64_t S = sig_off[r + 1] - sig_off[r], L = seq_off[r + 1] - seq_off[r];
+			if (S >= 1 && L >= (uint64_t)A->k && S >= 2 * (L - A->k + 1)) pc_total += L - A->k + 2;
+		}
+		std::vector<double> cols;
+		const bool want_cols = per_read_mean && per_read_stdev;
+		if (want_cols) cols.assign(3 * pc_total, 0.0);
+		const double saved = A->recs_per_row;
+		A->recs_per_row = 1e9;  // training keeps every significant cell; no overflow retry path
+		try
+		{
+			run_batch(*A, io, 2, res, nullptr, nullptr, pooled.data(), want_cols ? cols.data() : nullptr);
+		}
+		catch (...)
+		{
+			A->recs_per_row = saved;
+			throw;
+		}
+		A->recs_per_row = saved;
+		for (uint64_t q = 0; q < K; ++q)
+		{
+			if (pooled_w) pooled_w[q] += pooled[q];
+			if (pooled_x) pooled_x[q] += pooled[K + q];
+			if (pooled_xx) pooled_xx[q] += pooled[2 * K + q];
+		}
+		// kmer ids of every column are needed for the per-read M-step: recompute on the host (cheap, L ints)
+		for (uint32_t r = 0; r < n_reads; ++r)
+		{
+			dyn_train_result& o = results[r];
+			std::memset(&o, 0, sizeof(o));
+			o.status = res.out[r].status;
+			o.Z = res.out[r].Z;
+			if (o.status == ST_INVALID_NT) o.bad_char = seq[seq_off[r] + res.bad_pos[r]];
+			if (o.status != ST_OK) continue;
+			// NT:703-722: normalised re-estimates of m1 and e2; e1 = exp(log 1)
+			const double xm = res.out[r].xi_m, xe = res.out[r].xi_e;
+			const double norm = xm + xe;
+			o.m1 = norm > 0 ? xm / norm : 0.0;
+			o.e2 = norm > 0 ? xe / norm : 0.0;
+			o.e1 = std::exp(A->trans[1]);
+			if (pooled_xi)
+			{
+				pooled_xi[0] += xm;
+				pooled_xi[1] += xe;
+			}
+			if (want_cols)
+			{
+				// NT:519-535 per-read M-step
+				double* pm = per_read_mean + (uint64_t)r * K;
+				double* ps = per_read_stdev + (uint64_t)r * K;
+				std::vector<double> w(K, 0.0), sx(K, 0.0), sxx(K, 0.0);
+				const ReadDesc& d = res.desc[r];
+				const char* s = seq + seq_off[r];
+				for (uint32_t n = 1; n < d.N; ++n)
+				{
+					uint64_t id = 0;
+					for (int i = 0; i < A->k; ++i) id = id * 4 + (uint64_t)host_digit((unsigned char)s[n - 1 + i]);
+					w[id] += cols[d.pc_off + n];
+					sx[id] += cols[pc_total + d.pc_off + n];
+					sxx[id] += cols[2 * pc_total + d.pc_off + n];
+				}
+				for (uint64_t q = 0; q < K; ++q)
+				{
+					if (w[q] > 0.0)
+					{
+						const double mu = sx[q] / w[q];
+						double var = sxx[q] / w[q] - mu * mu;
+						if (var < 1e-12) var = 1e-12;
+						pm[q] = mu;
+						ps[q] = std::sqrt(var);
+					}
+					else
+					{
+						pm[q] = A->mean[q];
+						ps[q] = A->stdev[q];
+					}
+				}
+			}
+		}
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		A->last_error = e.what();
+		return -1;
+	}
+}
+
+const char* dyn_status_message(int status)
+{
+	switch (status)
+	{
+	case DYN_OK: return "";
+	case DYN_SIGNAL_EMPTY: return "Signal is empty";
+	case DYN_SEQ_SHORT: return "Sequence shorter than model kmer size";
+	case DYN_SIGNAL_SHORT: return "Signal too short compared to sequence";
+	case DYN_INVALID_NT: return "Invalid nucleotide: ";
+	case DYN_ALIGN_FAILED: return "Alignment failed: alignment scores do not match";
+	case DYN_TRAIN_FAILED: return "Training failed: alignment scores do not match";
+	case DYN_BAND_UNSUPPORTED: return "dynamont_b200: band too wide for this build (band/2 must be <= 207)";
+	default: return "dynamont_b200: internal error";
+	}
+}
+
+const char* dyn_last_error(const dyn_aligner* A) { return A->last_error.c_str(); }
+
+void dyn_last_timing(const dyn_aligner* A, double* out3)
+{
+	out3[0] = A->timing[0];
+	out3[1] = A->timing[1];
+	out3[2] = A->timing[2];
+}
+
+int dyn_set_option(dyn_aligner* A, const char* key, double value)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	const std::string k(key);
+	if (k == "warps_per_sm") A->warps_per_sm = std::max(1, (int)value);
+	else if (k == "thr2") A->thr2 = value;
+	else if (k == "recs_per_row") A->recs_per_row = value;
+	else if (k == "mem_fraction") A->mem_fraction = value;
+	else if (k == "sms") A->rt.sms = std::max(1, (int)value);
+	else return -1;
+	return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,129 @@
+/* dynamont_b200 — C ABI of the B200-native Dynamont segmentation hot path.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI: its native boundary is the pybind11 class
+ * `dynamont._dynamont.Aligner` (reference src/cpp/aligner_bindings.cpp:111-167, 180-219) over
+ * `dynamont::Aligner::align / train` (reference include/dynamont/aligner.hpp:56-85).  Each entry point
+ * below names the reference interface it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * All functions are thread-safe per handle (calls on one handle are serialised internally).
+ * There is no CPU fallback: creating a handle fails when no CUDA device is usable.
+ */
+#ifndef DYNAMONT_B200_H
+#define DYNAMONT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dyn_aligner dyn_aligner;
+
+/* Per-read status.  Values 1..6 correspond one-to-one to the exceptions the reference throws for that
+ * read (message text via dyn_status_message, identical to the reference's strings). */
+enum
+{
+	DYN_OK = 0,
+	DYN_SIGNAL_EMPTY = 1,   /* aligner.cpp:151  "Signal is empty" */
+	DYN_SEQ_SHORT = 2,      /* aligner.cpp:156  "Sequence shorter than model kmer size" */
+	DYN_SIGNAL_SHORT = 3,   /* aligner.cpp:162  "Signal too short compared to sequence" */
+	DYN_INVALID_NT = 4,     /* aligner.cpp:182,194  "Invalid nucleotide: X" (X in dyn_read_result.bad_char) */
+	DYN_ALIGN_FAILED = 5,   /* NT_aligner_api.cpp:291  "Alignment failed: alignment scores do not match" */
+	DYN_TRAIN_FAILED = 6,   /* NT_aligner_api.cpp:625  "Training failed: alignment scores do not match" */
+	DYN_REC_OVERFLOW = 7,   /* internal, never returned: resolved by an automatic retry */
+	DYN_INTERNAL = 8,
+	DYN_BAND_UNSUPPORTED = 9 /* band wider than this build's ring capacity */
+};
+
+typedef struct
+{
+	int32_t status;        /* DYN_* */
+	char bad_char;         /* offending character for DYN_INVALID_NT */
+	char pad[3];
+	double Z;              /* Result.Z (aligner.hpp:44-48): natural-log partition function (backward) */
+	uint64_t seg_offset;   /* first entry of this read in the segment output arrays */
+	uint64_t n_segments;   /* Kc = L - k + 1 on success with calc_probabilities, else 0 */
+} dyn_read_result;
+
+typedef struct
+{
+	int32_t status;
+	char bad_char;
+	char pad[3];
+	double Z;              /* TrainingResult.Z (aligner.hpp:50-55) */
+	double m1, e1, e2;     /* TrainingResult.transitions: re-estimated probabilities (NT:703-722) */
+} dyn_train_result;
+
+/* Replaces PyAligner's constructor / makeAligner (aligner_bindings.cpp:34-51,111-130) and
+ * Aligner::Aligner (aligner.cpp:13-36).  pore: "rna002" | "rna004" | "dna_r9" | "dna_r10_260bps" |
+ * "dna_r10_400bps"; mode: "basic" | "nt" (resquiggle/ntk: not built yet -> error); threads is accepted and
+ * ignored exactly like the reference; band as in the reference (default 400);
+ * device = CUDA ordinal or -1 for the current device.  Returns NULL and fills err on failure; err_kind is
+ * set to 1 for the reference's std::invalid_argument cases (-> ValueError), 0 for runtime_error. */
+dyn_aligner* dyn_create(const char* model_path, const char* pore, const char* mode, int threads, int band,
+	int device, char* err, size_t errlen, int* err_kind);
+void dyn_destroy(dyn_aligner*);
+
+int dyn_kmer_size(const dyn_aligner*);
+uint64_t dyn_num_kmers(const dyn_aligner*);
+int dyn_is_rna(const dyn_aligner*);
+/* model table in native index order (aligner.cpp:136-141): mean[K], stdev[K] */
+void dyn_model(const dyn_aligner*, double* mean, double* stdev);
+/* replace the emission table (native order); used by the training driver between iterations */
+int dyn_set_model(dyn_aligner*, const double* mean, const double* stdev);
+/* log transition parameters {m1, e1, e2} (NT_aligner_api.cpp:84-86) */
+void dyn_transitions(const dyn_aligner*, double* log3);
+
+/* number of output segments a batch needs: sum over reads of max(L - k + 1, 0) */
+uint64_t dyn_count_segments(const dyn_aligner*, const uint64_t* seq_off, uint32_t n_reads);
+/* in-band DP cells of one read (forward's trip count, NT:122-141) — the GCUPS unit */
+uint64_t dyn_read_cells(const dyn_aligner*, uint64_t S, uint64_t L);
+
+/* Batched Aligner::align (NT_aligner_api.cpp:230-312).  Read r has samples
+ * signal[sig_off[r] .. sig_off[r+1]) and bases seq[seq_off[r] .. seq_off[r+1]) (no terminators).
+ * results[n_reads]; the three segment arrays hold dyn_count_segments() entries and are filled at
+ * results[r].seg_offset: Segment.sequencePosition, Segment.signalPosition, Segment.probability
+ * (aligner.hpp:35-42; state is always 'M' and polish empty in basic mode).  calc_probabilities = 0 computes
+ * Z only.  Returns 0, or -1 on a CUDA/runtime error (message via dyn_last_error). One bad read never fails the
+ * batch (reference front end: segment.py:160-176). */
+int dyn_align_batch(dyn_aligner*, const float* signal, const uint64_t* sig_off, const char* seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results,
+	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities);
+
+/* Same, float64 samples as in the reference signature (converted to FP32 with round-to-nearest). */
+int dyn_align_batch_f64(dyn_aligner*, const double* signal, const uint64_t* sig_off, const char* seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results,
+	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities);
+
+/* Same, with the samples and bases already resident in device memory (d_signal, d_seq are device pointers;
+ * offsets and outputs are host pointers). */
+int dyn_align_batch_device(dyn_aligner*, const float* d_signal, const uint64_t* sig_off, const char* d_seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results,
+	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities);
+
+/* Batched Aligner::train (NT_aligner_api.cpp:567-639 + runTraining :462-561 + trainTransition :641-725).
+ * results[n_reads] receives per-read Z and re-estimated transitions.  Pooled sufficient statistics over all
+ * successful reads of the batch are ADDED to pooled_w / pooled_x / pooled_xx (K doubles each, native kmer
+ * order; NT:510-512) and to pooled_xi[2] = expected {E->M, E->E} transition counts — these are what a
+ * data-parallel trainer all-reduces.  If per_read_mean/per_read_stdev are non-NULL they receive the
+ * reference's per-read M-step (n_reads x K doubles each, NT:519-535: kmers without weight keep the model). */
+int dyn_train_batch(dyn_aligner*, const float* signal, const uint64_t* sig_off, const char* seq,
+	const uint64_t* seq_off, uint32_t n_reads, dyn_train_result* results, double* pooled_w, double* pooled_x,
+	double* pooled_xx, double* pooled_xi, double* per_read_mean, double* per_read_stdev);
+
+/* the reference's exact message for a status; "Invalid nucleotide: " lacks the char */
+const char* dyn_status_message(int status);
+/* message of the last runtime failure on this handle */
+const char* dyn_last_error(const dyn_aligner*);
+
+/* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
+ * last batch call: [0] encode/emission-constant kernel, [1] main DP kernel, [2] number of kernel launches */
+void dyn_last_timing(const dyn_aligner*, double* out3);
+/* tuning: resident warps per SM for the DP kernel (default chosen by the build), sparse threshold etc. */
+int dyn_set_option(dyn_aligner*, const char* key, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
