@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""Benchmark of the segmentation hot path (BASELINE.json metric: DP GCUPS and reads/s vs the reference CPU path).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R] [--config c2|c1]
+
+One "step" = one pass of the hot path (Aligner.align with calc_probabilities=True: backward, forward,
+posterior, posterior-Viterbi, traceback, medians) over one batch of R synthetic reads per GPU.
+N > 1 is launched with torchrun, one rank per GPU; reads shard across ranks with no communication (weak scaling).
+
+Workload c2 (default, the configuration the metric is quoted on for one GPU): rna004 pore, synthetic 9-mer
+model, basic mode, reads uniform 0.5-5 kb at ~30 samples/base, band 400.
+GCUPS = in-band lattice cells (each counted once, whatever number of passes touches it) / second / 1e9.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (pore, model, min_len, max_len, samples/base, dwell, default reads per step per GPU)
+    "c1": ("rna002", "rna002_5mer", 1000, 1000, 30.0, "geometric", 1000),
+    "c2": ("rna004", "synthetic_rna004_9mer", 500, 5000, 30.0, "geometric", 16384),
+}
+MODELS_DIR = os.path.join(ROOT, "tests", "golden", "_models")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per step per GPU (0 = config default)")
+    ap.add_argument("--seed", type=int, default=20262000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--warps-per-sm", type=int, default=0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ----------------------------------------------------------------------------------------------------------
+def gen_reads_numpy(cfg, n, seed):
+    """CPU generation (numpy) of n reads of the config's distribution — used for the CPU baseline sample."""
+    from dynamont_b200.synth import PORE_INFO, materialize_model, native_model, synth_read
+    pore, model, lo, hi, spb, dwell, _ = cfg
+    path = materialize_model(model, MODELS_DIR)
+    nm, ns = native_model(path, pore)
+    k = PORE_INFO[pore][1]
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        s, q, _ = synth_read(rng, nm, ns, k, L, spb, dwell=dwell)
+        out.append((s, q))
+    return path, out
+
+
+def gen_reads_torch(cfg, n, seed, device):
+    """GPU generation of the same distribution: returns device signal (float32), device bases (uint8 ASCII),
+    host offsets."""
+    import torch
+    from dynamont_b200.synth import PORE_INFO, materialize_model, native_model
+    pore, model, lo, hi, spb, dwell, _ = cfg
+    path = materialize_model(model, MODELS_DIR)
+    nm, ns = native_model(path, pore)
+    k = PORE_INFO[pore][1]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    mu = torch.tensor(nm, dtype=torch.float32, device=device)
+    sd = torch.tensor(ns, dtype=torch.float32, device=device)
+    lens = torch.randint(lo, hi + 1, (n,), generator=g, device=device, dtype=torch.int64)
+    seq_off = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    seq_off[1:] = torch.cumsum(lens, 0)
+    B = int(seq_off[-1].item())
+    digits = torch.randint(0, 4, (B,), generator=g, device=device, dtype=torch.int64)
+    pos = torch.arange(B, device=device) - torch.repeat_interleave(seq_off[:-1], lens)
+    digits[pos < k] = 0  # k x 'A' prefix (front end does this for RNA reads, segment.py:155-158)
+    ids = torch.zeros(B, dtype=torch.int64, device=device)
+    for i in range(k):
+        ids = ids * 4 + torch.roll(digits, -i)
+    valid = pos <= (torch.repeat_interleave(lens, lens) - k)  # kmer start positions
+    if dwell == "geometric":
+        u = torch.rand(B, generator=g, device=device, dtype=torch.float64).clamp_min(1e-300)
+        d = torch.floor(torch.log(u) / np.log1p(-1.0 / spb)).to(torch.int64) + 1
+    else:
+        gam = torch.distributions.Gamma(torch.tensor(4.0, device=device), torch.tensor(4.0 / spb, device=device))
+        d = torch.round(gam.sample((B,))).to(torch.int64)
+    d = torch.clamp(d, min=2) * valid
+    # per-read sample counts
+    csum = torch.zeros(B + 1, dtype=torch.int64, device=device)
+    csum[1:] = torch.cumsum(d, 0)
+    sig_off = csum[seq_off]
+    total = int(csum[-1].item())
+    signal = torch.empty(total, dtype=torch.float32, device=device)
+    chunk = 1 << 22  # kmer positions per chunk keeps repeat_interleave temporaries bounded
+    for a in range(0, B, chunk):
+        b = min(B, a + chunk)
+        per = torch.repeat_interleave(ids[a:b], d[a:b])
+        seg = signal[int(csum[a].item()):int(csum[b].item())]
+        seg.copy_(mu[per] + sd[per] * torch.randn(per.numel(), generator=g, device=device))
+    bases = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)[digits]
+    return path, signal, bases, sig_off.cpu().numpy().astype(np.uint64), seq_off.cpu().numpy().astype(np.uint64)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation, one single-threaded process per host core
+# ----------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(model_path, pore, kind):
+    import oracle
+    _W["al"] = oracle.Reference(model_path, pore) if kind == "reference" else oracle.Oracle(model_path, pore)
+
+
+def _cpu_align(item):
+    sig, seq = item
+    r = _W["al"].align(sig, seq, True)
+    return len(r["signal_positions"])
+
+
+def cpu_pool_plan(cfg, sample):
+    import oracle
+    import psutil
+    pore, model, lo, hi, spb, dwell, _ = cfg
+    kind = "reference" if oracle.have_reference() else "port"
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    # the reference holds 8 T x B double matrices per read: ~64*T*403 bytes
+    worst = 64.0 * (hi * spb + 1) * 403
+    avail = psutil.virtual_memory().available
+    procs = int(max(1, min(cores, (0.5 * avail) // worst)))
+    if sample <= 0:
+        sample = max(procs, 8)
+    return kind, procs, sample
+
+
+def run_cpu_sample(cfg, kind, procs, reads, model_path):
+    """Wall time of aligning `reads` with `procs` single-threaded worker processes (segment.py:304-324 shape)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(model_path, cfg[0], kind)) as pool:
+        pool.map(_cpu_align, reads[:procs], chunksize=1)  # construct aligners / warm caches (untimed)
+        t0 = time.perf_counter()
+        list(pool.imap_unordered(_cpu_align, reads, chunksize=1))
+        dt = time.perf_counter() - t0
+    return dt
+
+
+def cells_of(reads, model_path, pore):
+    import oracle
+    o = oracle.Oracle(model_path, pore)
+    return sum(o.cells(len(s), len(q)) for s, q in reads)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def main():
+    args = parse_args()
+    cfg = CONFIGS[args.config]
+    pore, model, lo, hi, spb, dwell, default_reads = cfg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    reads_per_gpu = args.reads or default_reads
+    workload = f"{args.config}: {pore} {model} basic mode, reads {lo}-{hi} b at ~{spb:g} samples/base ({dwell} dwell), band 400"
+
+    # ------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        kind, procs, sample = cpu_pool_plan(cfg, args.cpu_sample)
+        model_path, reads = gen_reads_numpy(cfg, sample, args.seed + 17)
+        cells = cells_of(reads, model_path, pore)
+        times = []
+        for i in range(args.warmup + args.steps):
+            dt = run_cpu_sample(cfg, kind, procs, reads, model_path)
+            if i >= args.warmup:
+                times.append(dt)
+        dt = float(np.mean(times))
+        gcups = cells / dt / 1e9
+        line = {
+            "impl": "reference", "metric": "dp_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "reads_per_s": len(reads) / dt,
+            "config": {"workload": workload, "reads_per_step": len(reads), "cells_per_step": int(cells)},
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": procs, "kind": kind,
+                             "sample": f"{len(reads)} reads of the workload per step, one single-threaded process per core "
+                                       f"({procs} processes), align(calc_probabilities=True)",
+                             "reads_per_s": len(reads) / dt},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu_baseline = None
+    if world == 1 and args.gpus == 1 and not args.no_cpu_baseline:
+        try:
+            kind, procs, sample = cpu_pool_plan(cfg, args.cpu_sample)
+            model_path, reads = gen_reads_numpy(cfg, sample, args.seed + 17)
+            cells = cells_of(reads, model_path, pore)
+            dt = run_cpu_sample(cfg, kind, procs, reads, model_path)
+            cpu_baseline = {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": procs, "kind": kind,
+                            "sample": f"{len(reads)} reads of the workload, one single-threaded process per core "
+                                      f"({procs} processes), align(calc_probabilities=True), {dt:.1f} s wall",
+                            "reads_per_s": len(reads) / dt}
+        except Exception as e:  # the baseline is context, never fatal
+            cpu_baseline = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+    # ------------------------------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dynamont_b200 import Aligner
+    model_path, d_signal, d_bases, sig_off, seq_off = gen_reads_torch(cfg, reads_per_gpu, args.seed + 1000 * rank, dev)
+    al = Aligner(model_path, pore, device=local_rank)
+    al.set_stream(torch.cuda.current_stream().cuda_stream)
+    if args.warps_per_sm:
+        al.set_option("warps_per_sm", args.warps_per_sm)
+    cells = al.batch_cells(sig_off, seq_off)
+    n_reads = sig_off.size - 1
+    n_samples = int(sig_off[-1])
+    n_bases = int(seq_off[-1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return al.align_packed(d_signal.data_ptr(), sig_off, d_bases.data_ptr(), seq_off, True, device=True)
+
+    dp_ms, launches = [], 0
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        res, _, sigpos, prob = step_device()
+        tm = al.last_timing()
+        dp_ms.append(tm["dp_ms"])
+        launches += tm["launches"]
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    n_ok = sum(1 for i in range(n_reads) if res[i].status == 0)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_signal = torch.empty(n_samples, dtype=torch.float32, pin_memory=True)
+        h_signal.copy_(d_signal)
+        h_bases = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
+        h_bases.copy_(d_bases)
+        torch.cuda.synchronize()
+
+        def step_host():
+            return al.align_packed(h_signal.data_ptr(), sig_off, h_bases.data_ptr(), seq_off, True, device=False)
+        step_host()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.steps):
+            step_host()
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / args.steps
+        e2e_ms = max(e0.elapsed_time(e1) / args.steps, 0.0)
+        nseg = int(al._lib.dyn_count_segments(al._h, seq_off.ctypes.data_as(__import__("ctypes").POINTER(__import__("ctypes").c_uint64)), n_reads))
+        e2e = {"ms": e2e_ms, "wall_ms": wall * 1e3, "h2d": n_samples * 4 + n_bases + (n_reads + 1) * 8 + n_reads * 48,
+               "d2h": nseg * 12 + n_reads * 52}
+
+    # ---- reduce over ranks: time = max, work = sum
+    stats = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(np.mean(dp_ms))], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(cells), float(n_reads), float(n_ok)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_all, e2e_ms_all, dp_ms_all = [float(x) for x in stats.tolist()]
+    cells_all, reads_all, ok_all = [float(x) for x in work.tolist()]
+    gcups = cells_all / (ms_all * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (k_align): SFU/MUFU-bound (north_star), HBM traffic reported beside it
+    props = torch.cuda.get_device_properties(dev)
+    sms = props.multi_processor_count
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    clk_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    mufu_peak = 16.0 * sms * clk_mhz * 1e6 / 1e9           # G MUFU op/s at the clock seen under load
+    mufu_peak_max = 16.0 * sms * (peaks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
+    dp_s = dp_ms_all * 1e-3
+    alg_mufu = 4.0 * cells / dp_s / 1e9                     # forward + backward: 2 MUFU per cell-update each
+    exe_mufu = 6.0 * cells / dp_s / 1e9                     # executed: backward, backward recompute, forward
+    # algorithmic HBM bytes per read: 4*S signal in + 16*N emission constants + 12*Kc out + spill
+    # (checkpoints 3584 B per 16 rows written+read, decision bits 64 B/row written+read, records ~ 12 B * few / row)
+    hbm_bytes = n_samples * 4.0 + n_bases * 17.0 + (n_samples / 16.0) * 3584 * 2 + n_samples * 64.0 * 2 + n_samples * 12.0 * 3 * 2
+    roofline = {
+        "bound": "sfu", "kernel": "k_align<Cfg<13,16,4,8>,1>",
+        "achieved": alg_mufu, "peak": mufu_peak, "unit": "G MUFU op/s", "frac": alg_mufu / mufu_peak,
+        "executed": exe_mufu, "executed_frac": exe_mufu / mufu_peak,
+        "peak_at_max_clock": mufu_peak_max, "peak_source": "16 MUFU/clk/SM x SMs x SM clock sampled by nvidia-smi during the timed region",
+        "cell_updates_per_s": 3.0 * cells / dp_s, "kernel_ms": dp_ms_all,
+        "traffic": None,
+        "hbm": {"achieved": hbm_bytes / dp_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "note": "algorithmic signal + constants + checkpoint/decision-bit/record spill per launch"},
+    }
+    line = {
+        "metric": "dp_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_all, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "reads_per_s": reads_all / (ms_all * 1e-3),
+        "config": {"workload": workload, "reads_per_step_per_gpu": int(n_reads), "cells_per_step": int(cells_all),
+                   "samples_per_step_per_gpu": n_samples, "reads_ok": int(ok_all),
+                   "l2": "inputs larger than L2 (signal %.1f GB per step)" % (n_samples * 4 / 1e9)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    if e2e:
+        line["e2e"] = {"value": cells_all / (e2e_ms_all * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms_all,
+                       "reads_per_s": reads_all / (e2e_ms_all * 1e-3),
+                       "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"])}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

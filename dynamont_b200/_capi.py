@@ -30,9 +30,9 @@ class TrainResult(C.Structure):
 
 EXPORTS = [
     "dyn_create", "dyn_destroy", "dyn_kmer_size", "dyn_num_kmers", "dyn_is_rna", "dyn_model", "dyn_set_model",
-    "dyn_transitions", "dyn_count_segments", "dyn_read_cells", "dyn_align_batch", "dyn_align_batch_f64",
+    "dyn_transitions", "dyn_count_segments", "dyn_read_cells", "dyn_batch_cells", "dyn_align_batch", "dyn_align_batch_f64",
     "dyn_align_batch_device", "dyn_train_batch", "dyn_status_message", "dyn_last_error", "dyn_last_timing",
-    "dyn_set_option",
+    "dyn_set_option", "dyn_set_stream",
 ]
 
 _libs: dict = {}
@@ -63,6 +63,8 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dyn_count_segments.restype = C.c_uint64
     lib.dyn_read_cells.argtypes = [vp, C.c_uint64, C.c_uint64]
     lib.dyn_read_cells.restype = C.c_uint64
+    lib.dyn_batch_cells.argtypes = [vp, u64p, u64p, C.c_uint32, u64p]
+    lib.dyn_batch_cells.restype = C.c_uint64
     common = [u64p, C.c_void_p, u64p, C.c_uint32, C.c_int, C.POINTER(ReadResult), u64p, u64p, f64p]
     lib.dyn_align_batch.argtypes = [vp, C.c_void_p] + common
     lib.dyn_align_batch_f64.argtypes = [vp, C.c_void_p] + common
@@ -75,5 +77,6 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dyn_last_error.restype = C.c_char_p
     lib.dyn_last_timing.argtypes = [vp, f64p]
     lib.dyn_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+    lib.dyn_set_stream.argtypes = [vp, C.c_void_p]
     _libs[path] = lib
     return lib

@@ -89,6 +89,38 @@ class Aligner:
         if self._lib.dyn_set_option(self._h, key.encode(), float(value)) != 0:
             raise KeyError(key)
 
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run this handle's work on the given ``cudaStream_t`` (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
+        self._lib.dyn_set_stream(self._h, C.c_void_p(cuda_stream))
+
+    def batch_cells(self, sig_off, seq_off) -> int:
+        sig_off = np.ascontiguousarray(sig_off, dtype=np.uint64)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        return int(self._lib.dyn_batch_cells(self._h, sig_off.ctypes.data_as(u64p), seq_off.ctypes.data_as(u64p),
+                                             sig_off.size - 1, None))
+
+    def align_packed(self, signal_ptr: int, sig_off, seq_ptr: int, seq_off, calc_probabilities: bool = True,
+                     device: bool = False, f64: bool = False):
+        """Zero-copy batched entry used by bench.py / streaming front ends: ``signal_ptr``/``seq_ptr`` are raw
+        addresses of the concatenated samples / bases (host, or device memory if ``device``).  Returns
+        (results ctypes array, sequence_positions, signal_positions, probabilities)."""
+        sig_off = np.ascontiguousarray(sig_off, dtype=np.uint64)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        n = sig_off.size - 1
+        res = (ReadResult * max(n, 1))()
+        nseg = int(self._lib.dyn_count_segments(self._h, seq_off.ctypes.data_as(u64p), n))
+        seqpos = np.empty(max(nseg, 1), dtype=np.uint64)
+        sigpos = np.empty(max(nseg, 1), dtype=np.uint64)
+        prob = np.empty(max(nseg, 1), dtype=np.float64)
+        fn = self._lib.dyn_align_batch_device if device else (
+            self._lib.dyn_align_batch_f64 if f64 else self._lib.dyn_align_batch)
+        rc = fn(self._h, C.c_void_p(signal_ptr), sig_off.ctypes.data_as(u64p), C.c_void_p(seq_ptr),
+                seq_off.ctypes.data_as(u64p), n, int(calc_probabilities), res, seqpos.ctypes.data_as(u64p),
+                sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p))
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        return res, seqpos, sigpos, prob
+
     def read_cells(self, S: int, L: int) -> int:
         return int(self._lib.dyn_read_cells(self._h, int(S), int(L)))
 

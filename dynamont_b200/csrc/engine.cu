@@ -58,9 +58,16 @@ struct Rt
 		CK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
 		for (auto& v : ev) CK_CUDA(cudaEventCreate(&v));
 	}
+	bool own_stream = true;
+	void use_stream(void* sh)
+	{
+		if (own_stream && stream) cudaStreamDestroy(stream);
+		stream = (cudaStream_t)sh;
+		own_stream = false;
+	}
 	void fini()
 	{
-		if (stream) cudaStreamDestroy(stream);
+		if (stream && own_stream) cudaStreamDestroy(stream);
 		for (auto& v : ev)
 			if (v) cudaEventDestroy(v);
 	}
@@ -100,6 +107,7 @@ struct Rt
 	size_t smem_optin = 227 * 1024;
 	double tm[4] = {0, 0, 0, 0};
 	void init(int) {}
+	void use_stream(void*) {}
 	void fini() {}
 	void bind() {}
 	void* dmalloc(size_t n) { return malloc(n ? n : 1); }
@@ -860,21 +868,50 @@ uint64_t dyn_count_segments(const dyn_aligner* A, const uint64_t* seq_off, uint3
 	return s;
 }
 
+// smallest row t in [0, T] with (size_t)(t * ratio) >= m   (band centre of row t, NT:100)
+static uint64_t first_row_with_mid(uint64_t m, double ratio, uint64_t T)
+{
+	if (m == 0) return 0;
+	uint64_t t = (uint64_t)std::ceil((double)m / ratio);
+	if (t > T) t = T;
+	while (t > 0 && (uint64_t)((double)(t - 1) * ratio) >= m) --t;
+	while (t < T && (uint64_t)((double)t * ratio) < m) ++t;
+	return t;
+}
+
 uint64_t dyn_read_cells(const dyn_aligner* A, uint64_t S, uint64_t L)
 {
 	if (S < 1 || L < (uint64_t)A->k) return 0;
 	const uint64_t T = S + 1, N = L - A->k + 2;
 	const uint64_t bw = std::min<uint64_t>((uint64_t)A->band / 2, N / 2);
 	const double ratio = (double)N / (double)T;
+	// rows 1..T-1 grouped by their band centre m: width(m) = min(m+bw+1, N) - max(m-bw, 1)   (NT:122-141)
 	uint64_t cells = 0;
-	for (uint64_t t = 1; t < T; ++t)
+	uint64_t t0 = std::max<uint64_t>(first_row_with_mid(0, ratio, T), 1);
+	for (uint64_t m = 0; m < N && t0 < T; ++m)
 	{
-		const uint64_t mid = (uint64_t)((double)t * ratio);
-		const uint64_t lo = std::max<uint64_t>(mid >= bw ? mid - bw : 0, 1);
-		const uint64_t hi = std::min<uint64_t>(mid + bw + 1, N);
-		if (hi > lo) cells += hi - lo;
+		const uint64_t t1 = std::max<uint64_t>(first_row_with_mid(m + 1, ratio, T), 1);
+		const uint64_t lo = std::max<uint64_t>(m >= bw ? m - bw : 0, 1);
+		const uint64_t hi = std::min<uint64_t>(m + bw + 1, N);
+		if (t1 > t0 && hi > lo) cells += (t1 - t0) * (hi - lo);
+		t0 = t1;
 	}
 	return cells;
+}
+
+uint64_t dyn_batch_cells(const dyn_aligner* A, const uint64_t* sig_off, const uint64_t* seq_off, uint32_t n_reads,
+	uint64_t* per_read)
+{
+	uint64_t total = 0;
+	for (uint32_t r = 0; r < n_reads; ++r)
+	{
+		const uint64_t S = sig_off[r + 1] - sig_off[r], L = seq_off[r + 1] - seq_off[r];
+		uint64_t c = 0;
+		if (S >= 1 && L >= (uint64_t)A->k && S >= 2 * (L - A->k + 1)) c = dyn_read_cells(A, S, L);
+		if (per_read) per_read[r] = c;
+		total += c;
+	}
+	return total;
 }
 
 static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilities, dyn_read_result* results,
@@ -1117,6 +1154,13 @@ void dyn_last_timing(const dyn_aligner* A, double* out3)
 	out3[0] = A->timing[0];
 	out3[1] = A->timing[1];
 	out3[2] = A->timing[2];
+}
+
+int dyn_set_stream(dyn_aligner* A, void* cuda_stream)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	A->rt.use_stream(cuda_stream);
+	return 0;
 }
 
 int dyn_set_option(dyn_aligner* A, const char* key, double value)

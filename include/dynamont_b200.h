@@ -79,6 +79,9 @@ void dyn_transitions(const dyn_aligner*, double* log3);
 uint64_t dyn_count_segments(const dyn_aligner*, const uint64_t* seq_off, uint32_t n_reads);
 /* in-band DP cells of one read (forward's trip count, NT:122-141) — the GCUPS unit */
 uint64_t dyn_read_cells(const dyn_aligner*, uint64_t S, uint64_t L);
+/* same for a whole batch (invalid reads count 0); per_read may be NULL; returns the total */
+uint64_t dyn_batch_cells(const dyn_aligner*, const uint64_t* sig_off, const uint64_t* seq_off, uint32_t n_reads,
+	uint64_t* per_read);
 
 /* Batched Aligner::align (NT_aligner_api.cpp:230-312).  Read r has samples
  * signal[sig_off[r] .. sig_off[r+1]) and bases seq[seq_off[r] .. seq_off[r+1]) (no terminators).
@@ -120,6 +123,9 @@ const char* dyn_last_error(const dyn_aligner*);
 /* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
  * last batch call: [0] encode/emission-constant kernel, [1] main DP kernel, [2] number of kernel launches */
 void dyn_last_timing(const dyn_aligner*, double* out3);
+/* run all work of this handle on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
+ * of the handle's own stream, so that the caller's CUDA events bracket it */
+int dyn_set_stream(dyn_aligner*, void* cuda_stream);
 /* tuning: resident warps per SM for the DP kernel (default chosen by the build), sparse threshold etc. */
 int dyn_set_option(dyn_aligner*, const char* key, double value);
 

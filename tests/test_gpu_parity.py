@@ -1,0 +1,147 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (dynamont_b200.Aligner -> ctypes ->
+libdynamont_b200.so), against (i) the golden vectors produced by the unmodified reference C++, (ii) the CPU
+oracle on seeded reads, (iii) size-independent properties at BASELINE.json's read sizes."""
+import numpy as np
+import pytest
+
+from conftest import PROB_ATOL, TRAIN_RTOL, check_alignment, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def aligners():
+    from dynamont_b200 import Aligner
+    cache = {}
+
+    def get(model_path, pore, band=400):
+        key = (model_path, pore, band)
+        if key not in cache:
+            cache[key] = Aligner(model_path, pore, band=band)
+        return cache[key]
+    return get
+
+
+@pytest.mark.parametrize("case", load_golden(), ids=lambda c: c.name)
+def test_align_matches_reference_golden(case, aligners):
+    al = aligners(case.model_path, case.pore)
+    r = al.align(case.signal, case.sequence, True)
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    assert r["states"] == ["M"] * len(r["signal_positions"]) and r["polishes"] == [""] * len(r["states"])
+    z_only = al.align(case.signal, case.sequence, False)
+    assert z_only["Z"] == r["Z"] and len(z_only["signal_positions"]) == 0
+
+
+@pytest.mark.parametrize("case", load_golden(), ids=lambda c: c.name)
+def test_train_matches_reference_golden(case, aligners):
+    al = aligners(case.model_path, case.pore)
+    per_read, pooled = al.train_batch([case.signal], [case.sequence], per_read_model=True)
+    r = per_read[0]
+    assert abs(r["Z"] - case.train_Z) <= 1e-6 * max(1.0, abs(case.train_Z))
+    tp = r["transition_params"]
+    np.testing.assert_allclose([tp["m1"], tp["e1"], tp["e2"]], case.train_trans, rtol=TRAIN_RTOL)
+    km = case.train_kmers
+    # raw sufficient statistics (what a data-parallel trainer all-reduces)
+    heavy = case.stat_w > 1e-3  # parity is only meaningful above a weight threshold
+    np.testing.assert_allclose(pooled["w"][km][heavy], case.stat_w[heavy], rtol=TRAIN_RTOL)
+    np.testing.assert_allclose(pooled["x"][km][heavy], case.stat_x[heavy], rtol=TRAIN_RTOL, atol=1e-6)
+    np.testing.assert_allclose(pooled["xx"][km][heavy], case.stat_xx[heavy], rtol=TRAIN_RTOL)
+    # per-read M-step (reference semantics)
+    np.testing.assert_allclose(r["emission_model"]["mean"][km][heavy], case.train_mean[heavy], rtol=TRAIN_RTOL, atol=1e-5)
+    np.testing.assert_allclose(r["emission_model"]["stdev"][km][heavy], case.train_stdev[heavy], rtol=2e-3, atol=1e-5)
+    # untouched kmers keep the model (NT:531-534)
+    mean0, sd0 = al.model()
+    untouched = np.ones(al.num_kmers, bool)
+    untouched[km] = False
+    idx = np.nonzero(untouched & (pooled["w"] == 0))[0][:1000]
+    assert np.array_equal(r["emission_model"]["mean"][idx], mean0[idx])
+
+
+def _synth_batch(model_path, pore, n, lo, hi, spb, seed, dwell="geometric"):
+    from dynamont_b200.synth import PORE_INFO, native_model, synth_read
+    nm, ns = native_model(model_path, pore)
+    k = PORE_INFO[pore][1]
+    rng = np.random.default_rng(seed)
+    sigs, seqs = [], []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        s, q, _ = synth_read(rng, nm, ns, k, L, spb, dwell=dwell)
+        sigs.append(s.astype(np.float32))
+        seqs.append(q)
+    return sigs, seqs
+
+
+def test_batch_vs_oracle_seeded(aligners, models_dir):
+    """A ragged batch (incl. reads the reference throws on) against the CPU oracle, read by read."""
+    from dynamont_b200.synth import materialize_model
+    from oracle import Oracle
+    path = materialize_model("rna002_5mer", models_dir)
+    al = aligners(path, "rna002")
+    orc = Oracle(path, "rna002")
+    sigs, seqs = _synth_batch(path, "rna002", 24, 30, 900, 9, seed=20260001)
+    sigs += [np.zeros(0, np.float32), sigs[0][:50], sigs[1]]
+    seqs += ["ACGTACGTAC", seqs[0], seqs[1][:20] + "N" + seqs[1][21:]]
+    res = al.align_batch(sigs, seqs, True)
+    n_seg = n_same = 0
+    for s, q, r in zip(sigs, seqs, res):
+        try:
+            o = orc.align(s.astype(np.float64), q, True)
+        except RuntimeError as e:
+            assert isinstance(r, RuntimeError) and str(r) == str(e)
+            continue
+        check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
+        n_seg += o["signal_positions"].size
+        n_same += int((r["signal_positions"] == o["signal_positions"]).sum())
+    assert n_same >= 0.999 * n_seg
+
+
+def test_batch_order_and_idempotence(aligners, models_dir):
+    from dynamont_b200.synth import materialize_model
+    path = materialize_model("rna002_5mer", models_dir)
+    al = aligners(path, "rna002")
+    sigs, seqs = _synth_batch(path, "rna002", 40, 100, 1200, 12, seed=7)
+    a = al.align_batch(sigs, seqs, True)
+    perm = np.random.default_rng(0).permutation(len(sigs))
+    b = al.align_batch([sigs[i] for i in perm], [seqs[i] for i in perm], True)
+    for j, i in enumerate(perm):
+        assert a[i]["Z"] == b[j]["Z"]
+        assert np.array_equal(a[i]["signal_positions"], b[j]["signal_positions"])
+        assert np.array_equal(a[i]["probabilities"], b[j]["probabilities"])
+
+
+def test_full_size_properties(aligners, models_dir):
+    """BASELINE config sizes (1 kb .. 5 kb reads, 30 samples/base, 9-mer model): properties that need no oracle."""
+    from dynamont_b200.synth import materialize_model
+    path = materialize_model("synthetic_rna004_9mer", models_dir)
+    al = aligners(path, "rna004")
+    sigs, seqs = _synth_batch(path, "rna004", 6, 1000, 5000, 30, seed=20262000)
+    res = al.align_batch(sigs, seqs, True)
+    k = al.kmer_size
+    for s, q, r in zip(sigs, seqs, res):
+        Kc = len(q) - k + 1
+        sp = r["signal_positions"].astype(np.int64)
+        assert sp.size == Kc and sp[0] == 0                      # exactly Kc segments, first starts at sample 0
+        assert np.all(np.diff(sp) >= 2)                          # every kmer emits >= 2 samples (M then E)
+        assert sp[-1] <= s.size - 2
+        assert np.array_equal(r["sequence_positions"], np.arange(Kc, dtype=np.uint64) + k // 2)
+        assert np.all(r["probabilities"] >= 0) and np.all(r["probabilities"] <= 1 + 1e-6)
+        assert np.isfinite(r["Z"])
+    # synthetic reads are easy: borders land close to the truth and are confident
+    assert np.median(np.concatenate([r["probabilities"] for r in res])) > 0.5
+
+
+def test_band_cutoff_fails_like_reference(aligners, models_dir):
+    """A read whose true path leaves the band: Z is -inf and the reference throws 'Alignment failed'."""
+    from dynamont_b200.synth import materialize_model
+    from oracle import Oracle
+    path = materialize_model("rna002_5mer", models_dir)
+    al = aligners(path, "rna002", band=6)
+    orc = Oracle(path, "rna002", band=6)
+    sigs, seqs = _synth_batch(path, "rna002", 3, 200, 300, 10, seed=3)
+    res = al.align_batch(sigs, seqs, True)
+    for s, q, r in zip(sigs, seqs, res):
+        try:
+            o = orc.align(s.astype(np.float64), q, True)
+            check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
+        except RuntimeError as e:
+            assert isinstance(r, RuntimeError) and str(r) == str(e)
