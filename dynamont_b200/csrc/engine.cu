@@ -1156,6 +1156,10 @@ void dyn_last_timing(const dyn_aligner* A, double* out3)
 	out3[2] = A->timing[2];
 }
 
+#ifdef DYN_DEBUG_ROWS
+void dyn_debug_rows(double* p) { dyn::g_dbg_rows = p; }
+#endif
+
 int dyn_set_stream(dyn_aligner* A, void* cuda_stream)
 {
 	std::lock_guard<std::mutex> g(A->mu);
