@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--warps-per-sm", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=-1, help="kernel build variant (see csrc/engine.cu); -1 = library default")
     return ap.parse_args()
 
 
@@ -290,6 +291,8 @@ def main():
     al.set_stream(torch.cuda.current_stream().cuda_stream)
     if args.warps_per_sm:
         al.set_option("warps_per_sm", args.warps_per_sm)
+    if args.variant >= 0:
+        al.set_option("variant", args.variant)
     cells = al.batch_cells(sig_off, seq_off)
     n_reads = sig_off.size - 1
     n_samples = int(sig_off[-1])

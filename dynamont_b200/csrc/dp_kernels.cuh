@@ -30,22 +30,23 @@ struct Cfg
 {
 	static constexpr int CPL = CPL_;         // lattice columns per lane
 	static constexpr int SLOTS = 32 * CPL_;  // ring capacity; needs 2*bw + 2 <= SLOTS
-	static constexpr int CK = CK_;           // checkpoint spacing (rows); multiple of RN
-	static constexpr int RN = RN_;           // renormalisation period of the backward pass (rows)
-	static constexpr int RV = RV_;           // renormalisation period of the posterior-Viterbi scores
+	static constexpr int CK = CK_;           // checkpoint spacing (rows); divides 32, multiple of RN
+	static constexpr int RN = RN_;           // renormalisation period of the backward pass (rows), power of two
+	static constexpr int RV = RV_;           // renormalisation period of the posterior-Viterbi scores, power of two
 	static constexpr int NRN = CK_ / RN_ + 1;
 	static constexpr int CKF = 2 * CPL_ * 32;  // floats per checkpoint
-	static constexpr size_t CK_BYTES = CKF * 4 + 32 * 8;
-	static constexpr size_t SMEM_BYTES = (size_t)(CK_ + 1) * CPL_ * 32 * 4 + (size_t)NRN * 32 * (8 + 4);
-	static_assert(CK_ % RN_ == 0, "CK must be a multiple of RN");
+	static constexpr int ROWF = CPL_ * 32;     // floats per shared-memory row
+	static constexpr size_t SMEM_BYTES = (size_t)(CK_ + 1) * ROWF * 4 + (size_t)NRN * 32 * (8 + 4);
+	static_assert(CK_ % RN_ == 0 && 32 % CK_ == 0, "CK must divide 32 and be a multiple of RN");
+	static_assert((RN_ & (RN_ - 1)) == 0 && (RV_ & (RV_ - 1)) == 0, "RN, RV: powers of two");
 };
 
 // Scratch memory of one resident warp ("slot"), sized by the host for the longest read of the batch.
 struct SlotScratch
 {
-	float* ckpt;        // [nck][CKF] floats followed by ... (see ck_f / ck_ob)
+	float* ckpt;        // [nck][CKF]
 	double* ckpt_ob;    // [nck][32]
-	uint16_t* bits;     // [T][32]   decision bits: bit j of word (t, lane) = cell in slot lane*CPL+j came from M
+	uint16_t* bits;     // [T][32]   decision bits: bit j of word (t, lane) set <=> cell in slot lane*CPL+j came from E
 	uint32_t* rowptr;   // [T+1]     first sparse record of row t
 	PostRec* recs;      // [rec_cap]
 	uint32_t* pn;       // [T]       path column of row t (bit 31: match state)
@@ -73,7 +74,7 @@ struct BatchArgs
 	double* stat_x;             // [K] pooled sum of gamma * x          (NT:511)
 	double* stat_xx;            // [K] pooled sum of gamma * x^2        (NT:512)
 	const int32_t* kmers;       // [sum N] kmer id of column n (kmer[n-1]; entry 0 unused), parallel to pc
-	double* read_w;             // optional per-read per-column statistics [sum N] (reference per-read M-step)
+	double* read_w;             // per-read per-column statistics [sum N]
 	double* read_x;
 	double* read_xx;
 };
@@ -120,7 +121,7 @@ DYN_DEV void with_slot(int lane, int q, F body)
 }
 #undef DYN_SLOT_CASE
 
-// A small functor helper because device lambdas with constant-index register access need a template arg.
+// slot functors (compile-time slot index keeps the arrays in registers)
 template <int CPL>
 struct SetEmis
 {
@@ -139,9 +140,12 @@ struct SetEmis
 	}
 };
 
+// set the emission constants of a slot and force its two state values
 template <int CPL>
-struct SetTwo
+struct SetEmisState
 {
+	Emis<CPL>& e;
+	float va, vb, vc;
 	float (&p)[CPL];
 	float (&q)[CPL];
 	float v;
@@ -151,6 +155,9 @@ struct SetTwo
 		for (int jj = 0; jj < CPL; ++jj)
 			if (jj == j)
 			{
+				e.a[jj] = va;
+				e.b[jj] = vb;
+				e.c[jj] = vc;
 				p[jj] = v;
 				q[jj] = v;
 			}
@@ -199,15 +206,17 @@ struct Warp
 	float m1, e2;
 	Emis<CPL> em;
 
+	DYN_DEV bool valid_col(int n) const { return n >= 0 && n < (int)N; }
+
 	DYN_DEV void activate(int n)
 	{
-		if (n < 0 || n >= (int)N) return;
+		if (!valid_col(n)) return;
 		const PosConst v = pc[n];  // uniform address: one broadcast transaction
 		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, v.a, v.b, v.c});
 	}
 	DYN_DEV void deactivate(int n)
 	{
-		if (n < 0 || n >= (int)N) return;
+		if (!valid_col(n)) return;
 		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, 0.0f, 0.0f, CNEG});
 	}
 	// lattice column held by ring slot q when the window starts at column n0 (may be negative)
@@ -240,6 +249,7 @@ struct Warp
 	// move the emission window from centre mid_from up to centre mid_to (mid_to >= mid_from)
 	DYN_DEV void slide_window_up(int mid_from, int mid_to)
 	{
+#pragma unroll 1
 		for (int m = mid_from + 1; m <= mid_to; ++m)
 		{
 			deactivate(m - 1 - bw);
@@ -248,8 +258,26 @@ struct Warp
 	}
 };
 
+// per 32-row chunk: the lane's sample and the band-slide mask (bit i <=> centre(base+i) != centre(base+i+1))
+struct Chunk
+{
+	float xv;
+	unsigned smask;
+};
+
+template <class CFG>
+DYN_DEV Chunk chunk_load(const Warp<CFG>& w, uint32_t base)
+{
+	Chunk c;
+	const uint32_t r = base + w.lane;
+	const uint32_t c0 = band_mid(r, w.ratio), c1 = band_mid(r + 1, w.ratio);
+	c.smask = __ballot_sync(FULL, c0 != c1);
+	c.xv = (r < w.S) ? w.sig[r] : 0.0f;
+	return c;
+}
+
 // ------------------------------------------------------------------------------------------------------
-// backward recurrence (NT_aligner_api.cpp:158-207), one row
+// backward recurrence (NT_aligner_api.cpp:158-207)
 // ------------------------------------------------------------------------------------------------------
 template <int CPL>
 struct Bwd
@@ -275,7 +303,7 @@ DYN_DEV void bwd_row(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x)
 	for (int j = 0; j < CPL; ++j)
 	{
 		const float ext1 = (j + 1 < CPL) ? A[j + 1] : Ar;
-		const float nm = b.bE[j] + s[j];  // bM[t][n] = bE[t+1][n] + score      (NT:200)
+		const float nm = b.bE[j] + s[j];      // bM[t][n] = bE[t+1][n] + score      (NT:200)
 		b.bE[j] = logplus2(ext1, nm + w.e2);  //                                    (NT:194,201,204)
 		b.bM[j] = nm;
 	}
@@ -321,8 +349,8 @@ DYN_DEV void bwd_step(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x, bool slide, int& 
 		const int nb = mid - 1 - w.bw;
 		if (nb >= 0)
 		{
-			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetTwo<CPL>{b.bM, b.bE, NEG});
-			w.activate(nb);
+			const PosConst v = w.pc[nb];
+			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetEmisState<CPL>{w.em, v.a, v.b, v.c, b.bM, b.bE, NEG});
 		}
 	}
 	bwd_row<CFG>(w, b, x);
@@ -330,10 +358,7 @@ DYN_DEV void bwd_step(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x, bool slide, int& 
 	{
 		const int ntop = mid + w.bw;  // column that was in band(t+1) but is not in band(t)
 		if (ntop < (int)w.N)
-		{
-			with_slot<CPL>(w.lane, pmod(ntop, CFG::SLOTS), SetTwo<CPL>{b.bM, b.bE, NEG});
-			w.deactivate(ntop);
-		}
+			with_slot<CPL>(w.lane, pmod(ntop, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, b.bM, b.bE, NEG});
 		--mid;
 	}
 }
@@ -383,16 +408,6 @@ DYN_DEV void ckpt_load(const SlotScratch& sc, uint32_t idx, int lane, Bwd<CFG::C
 	b.dR = (float)(obr - b.OB);
 }
 
-// per 32-row chunk: the lane's sample and the band-slide mask (bit i <=> centre(base+i) != centre(base+i+1))
-template <class CFG>
-DYN_DEV void chunk_prefetch(const Warp<CFG>& w, uint32_t base, float& xv, unsigned& smask)
-{
-	const uint32_t r = base + w.lane;
-	const uint32_t c0 = band_mid(r, w.ratio), c1 = band_mid(r + 1, w.ratio);
-	smask = __ballot_sync(FULL, c0 != c1);
-	xv = (r < w.S) ? w.sig[r] : 0.0f;
-}
-
 #ifdef DYN_DEBUG_ROWS
 static double* g_dbg_rows = nullptr;  // emulator-only debugging aid: [T][N][2] true log2 values of bM, bE
 #endif
@@ -408,22 +423,27 @@ DYN_DEV double backward_pass(Warp<CFG>& w, const SlotScratch& sc)
 	int mid = (int)band_mid(w.T - 1, w.ratio);
 	w.load_window(mid);
 	bwd_init_terminal<CFG>(w, b);
-	if (STORE && (w.T - 1) % CFG::CK == 0) ckpt_store<CFG>(sc, (w.T - 1) / CFG::CK, w.lane, b);
+	if (STORE && ((w.T - 1) & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, (w.T - 1) / CFG::CK, w.lane, b);
 
 	int t = (int)w.T - 2;
+	// the next chunk's samples are requested one chunk ahead so their latency hides behind 32 rows of work
+	Chunk nxt = chunk_load<CFG>(w, (uint32_t)t & ~31u);
 	while (t >= 0)
 	{
 		const uint32_t base = (uint32_t)t & ~31u;
-		float xv;
-		unsigned smask;
-		chunk_prefetch<CFG>(w, base, xv, smask);
+		const Chunk cur = nxt;
+		if (base >= 32) nxt = chunk_load<CFG>(w, base - 32);
+#pragma unroll 1
 		for (int i = t - (int)base; i >= 0; --i)
 		{
 			const uint32_t tt = base + i;
-			const float x = __shfl_sync(FULL, xv, i);
-			bwd_step<CFG>(w, b, x, (smask >> i) & 1u, mid);
-			if (tt % CFG::RN == 0) bwd_renorm<CFG>(w, b);
-			if (STORE && tt % CFG::CK == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
+			const float x = __shfl_sync(FULL, cur.xv, i);
+			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid);
+			if ((tt & (CFG::RN - 1)) == 0)
+			{
+				bwd_renorm<CFG>(w, b);
+				if (STORE && (tt & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
+			}
 #ifdef DYN_DEBUG_ROWS
 			if (g_dbg_rows)
 			{
@@ -471,7 +491,7 @@ struct Smem
 	{
 		OB = reinterpret_cast<double*>(p);
 		bE = reinterpret_cast<float*>(p + (size_t)CFG::NRN * 32 * 8);
-		inc = bE + (size_t)(CFG::CK + 1) * CFG::CPL * 32;
+		inc = bE + (size_t)(CFG::CK + 1) * CFG::ROWF;
 	}
 };
 
@@ -482,16 +502,13 @@ DYN_DEV void fwd_shift_to(Warp<CFG>& w, Fwd<CFG::CPL>& f, double target)
 {
 	constexpr int CPL = CFG::CPL;
 	const float sh = (float)(f.OF - target);
-	if (sh != 0.0f)
-	{
 #pragma unroll
-		for (int j = 0; j < CPL; ++j)
-		{
-			f.fM[j] += sh;
-			f.fE[j] += sh;
-		}
-		f.OF -= (double)sh;
+	for (int j = 0; j < CPL; ++j)
+	{
+		f.fM[j] += sh;
+		f.fE[j] += sh;
 	}
+	f.OF -= (double)sh;
 	const double ofl = shfl_f64(f.OF, (w.lane + 31) & 31);
 	f.dL = (float)(ofl - f.OF);
 }
@@ -518,6 +535,125 @@ DYN_DEV void vit_renorm(Warp<CFG>& w, Fwd<CFG::CPL>& f)
 	f.dVL = (float)(ovl - f.OV);
 }
 
+struct RecSink
+{
+	PostRec* recs;
+	uint64_t cap;
+	uint32_t n;
+	bool overflow;
+};
+
+// One row of pass 2.  On entry f holds the forward values of row t and the Viterbi values of row t-1.
+//   DO_V:    posteriors of row t, posterior-Viterbi update (NT:357-362), decision bits, sparse records
+//   DO_STEP: forward recurrence to row t+1 (NT:141-150) incl. the band slide between t and t+1
+// cur/nxt: shared-memory rows bE(t) / bE(t+1) of the recomputed backward block.
+template <class CFG, bool DO_V, bool DO_STEP>
+DYN_DEV void fwd_row(Warp<CFG>& w, Fwd<CFG::CPL>& f, const SlotScratch& sc, RecSink& rs, float thr2, uint32_t t,
+	float x, bool slide, int& mid_f, const float* cur, const float* nxt, bool rn_row, float inc_t)
+{
+	constexpr int CPL = CFG::CPL;
+	const int lane = w.lane;
+	if (DO_STEP && slide) w.activate(mid_f + 1 + w.bw);  // column entering band(t+1)
+
+	float s[CPL], LPM[CPL], LPE[CPL];
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		s[j] = emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]);
+		if (DO_V)
+		{
+			LPE[j] = f.fE[j] + cur[j * 32 + lane];
+			// bM[t][n] = bE[t+1][n] + score(x[t], kmer[n-1]) (NT:200); the last row has no match state (-inf)
+			LPM[j] = DO_STEP ? f.fM[j] + (nxt[j * 32 + lane] + s[j]) : NEG;
+		}
+	}
+	if (DO_V)
+	{
+		if (DO_STEP && rn_row)
+		{
+			// the backward pass renormalised row t after forming bM[t]: apply the same increment
+#pragma unroll
+			for (int j = 0; j < CPL; ++j) LPM[j] -= inc_t;
+		}
+		if (DO_STEP && slide && mid_f - w.bw >= 0)
+		{
+			// column lo_t leaves the band at row t+1, so bE[t+1][lo_t] is out of band (-inf in the reference) and
+			// with it bM[t][lo_t]; the recomputed row holds the ungated neighbour term there (see bwd_step)
+			with_slot<CPL>(lane, pmod(mid_f - w.bw, CFG::SLOTS), SetOne<CPL>{LPM, NEG});
+		}
+		// posterior-Viterbi fill, in place from the highest slot down so that slot j-1 still holds row t-1;
+		// decision bit = sign(VM - VE): set <=> the E state of this cell is entered from E (test of NT:448)
+		const float vl = __shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31) + f.dVL;
+		unsigned acc = 0;
+		float lmax = NEG;
+#pragma unroll
+		for (int j = CPL - 1; j >= 0; --j)
+		{
+			const float vmx = fmaxf(f.VM[j], f.VE[j]);
+			acc = __funnelshift_l(__float_as_uint(f.VM[j] - f.VE[j]), acc, 1);
+			const float left = (j > 0) ? f.VE[j - 1] : vl;
+			f.VM[j] = left + LPM[j];
+			f.VE[j] = vmx + LPE[j];
+			lmax = fmaxf(lmax, fmaxf(LPM[j], LPE[j]));
+		}
+		if ((t & (CFG::RV - 1)) == 0) vit_renorm<CFG>(w, f);
+		sc.bits[(size_t)t * 32 + lane] = (uint16_t)acc;
+
+		// sparse posterior records: the few cells per row with a non-negligible posterior
+		if (lane == 0) sc.rowptr[t] = rs.n;
+		if (__any_sync(FULL, lmax > thr2))
+		{
+			const int n0 = mid_f - w.bw;
+#pragma unroll
+			for (int j = 0; j < CPL; ++j)
+			{
+				const bool hit = fmaxf(LPM[j], LPE[j]) > thr2;
+				const unsigned hm = __ballot_sync(FULL, hit);
+				if (hm)
+				{
+					if (hit)
+					{
+						const uint32_t pos = rs.n + __popc(hm & ((1u << lane) - 1u));
+						if (pos < rs.cap)
+						{
+							PostRec r;
+							r.n = (uint32_t)w.col_of_slot(lane * CPL + j, n0);
+							r.lpm = LPM[j];
+							r.lpe = LPE[j];
+							rs.recs[pos] = r;
+						}
+					}
+					rs.n += __popc(hm);
+				}
+			}
+			if (rs.n > rs.cap)
+			{
+				rs.overflow = true;
+				rs.n = (uint32_t)rs.cap;
+			}
+		}
+	}
+	if (DO_STEP)
+	{
+		const float fl = __shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) + f.dL;
+#pragma unroll
+		for (int j = CPL - 1; j >= 0; --j)
+		{
+			const float left = (j > 0) ? f.fE[j - 1] : fl;
+			const float ne = logplus2(f.fM[j], f.fE[j] + w.e2) + s[j];
+			f.fM[j] = left + (s[j] + w.m1);
+			f.fE[j] = ne;
+		}
+		if (slide)
+		{
+			const int nold = mid_f - w.bw;  // column of band(t) that is not in band(t+1)
+			if (nold >= 0)
+				with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, f.fM, f.fE, NEG});
+			++mid_f;
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------
 // pass 2: forward + posterior + posterior-Viterbi fill.  Returns (Zf - Zb) in log2 units.
 // ------------------------------------------------------------------------------------------------------
@@ -528,83 +664,71 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 	constexpr int CPL = CFG::CPL;
 	constexpr int CK = CFG::CK;
 	constexpr int RN = CFG::RN;
+	constexpr int ROWF = CFG::ROWF;
 	Smem<CFG> sm(smem_raw);
 	Fwd<CPL> f;
 	Bwd<CPL> b;
 	const int lane = w.lane;
 	const uint32_t T = w.T;
-	uint32_t nrec = 0;
-	overflow = false;
-	float lpe_end = 0.0f;
+	RecSink rs;
+	rs.recs = sc.recs;
+	rs.cap = args.rec_cap;
+	rs.n = 0;
+	rs.overflow = false;
 
 	int mid_f = 0;  // band centre of the forward row
 	w.load_window(0);
 	const uint32_t kb = (T - 1) / CK;
-	float bEcur[CPL];  // bE of the current forward row
+	// samples/slide masks per 32-row chunk: a block (CK | 32) lies inside one chunk; both the backward
+	// recomputation and the forward rows of the block use it; the next chunk is requested a chunk ahead
+	Chunk cur = chunk_load<CFG>(w, 0);
+	Chunk nxtc = chunk_load<CFG>(w, 32);
 
 	for (uint32_t k = 0; k <= kb; ++k)
 	{
 		const uint32_t t_lo = k * CK;
 		const uint32_t t_hi = t_lo + CK;
+		if (k > 0 && (t_lo & 31u) == 0)
+		{
+			cur = nxtc;
+			nxtc = chunk_load<CFG>(w, t_lo + 32);
+		}
 		// ---- step a: recompute the backward rows of this block into shared memory -----------------------
-		uint32_t src_row;
-		if (t_hi <= T - 1)
-		{
-			src_row = t_hi;
-			const int mid_src = (int)band_mid(src_row, w.ratio);
-			w.slide_window_up(mid_f, mid_src);
-			ckpt_load<CFG>(sc, k + 1, lane, b);
-		}
-		else
-		{
-			src_row = T - 1;
-			const int mid_src = (int)band_mid(src_row, w.ratio);
-			w.slide_window_up(mid_f, mid_src);
-			bwd_init_terminal<CFG>(w, b);
-		}
+		const bool from_ckpt = (t_hi <= T - 1);
+		const uint32_t src_row = from_ckpt ? t_hi : T - 1;
 		int mid_b = (int)band_mid(src_row, w.ratio);
+		w.slide_window_up(mid_f, mid_b);
+		if (from_ckpt) ckpt_load<CFG>(sc, k + 1, lane, b);
+		else bwd_init_terminal<CFG>(w, b);
 		{
-			float* dst = sm.bE + (size_t)(src_row - t_lo) * CPL * 32;
+			float* dst = sm.bE + (size_t)(src_row - t_lo) * ROWF;
 #pragma unroll
 			for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
 			// offsets in force for the rows above the last renormalisation row of this block
 			sm.OB[((src_row - t_lo + RN - 1) / RN) * 32 + lane] = b.OB;
-			sm.inc[((src_row - t_lo + RN - 1) / RN) * 32 + lane] = 0.0f;
 		}
+		// the slide between src_row-1 and src_row may belong to the next chunk when src_row is 32-aligned
+#pragma unroll 1
+		for (int tt = (int)src_row - 1; tt >= (int)t_lo; --tt)
 		{
-			int t = (int)src_row - 1;
-			while (t >= (int)t_lo)
+			const int i = tt & 31;
+			const float x = __shfl_sync(FULL, cur.xv, i);
+			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid_b);
+			float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
+			if ((tt & (RN - 1)) == 0)
 			{
-				const uint32_t base = max((uint32_t)t & ~31u, t_lo);
-				// chunk_prefetch works on 32-aligned bases; blocks are CK-aligned with CK <= 32 dividing 32 or not,
-				// so prefetch relative to the aligned base and index with (row - abase)
-				const uint32_t abase = (uint32_t)t & ~31u;
-				float xv;
-				unsigned smask;
-				chunk_prefetch<CFG>(w, abase, xv, smask);
-				for (int tt = t; tt >= (int)base; --tt)
-				{
-					const int i = tt - (int)abase;
-					const float x = __shfl_sync(FULL, xv, i);
-					bwd_step<CFG>(w, b, x, (smask >> i) & 1u, mid_b);
-					float inc = 0.0f;
-					if (tt % RN == 0) inc = bwd_renorm<CFG>(w, b);
-					float* dst = sm.bE + (size_t)(tt - t_lo) * CPL * 32;
-#pragma unroll
-					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
-					if (tt % RN == 0)
-					{
-						sm.OB[((tt - t_lo) / RN) * 32 + lane] = b.OB;
-						sm.inc[((tt - t_lo) / RN) * 32 + lane] = inc;
-					}
-				}
-				t = (int)base - 1;
+				const float inc = bwd_renorm<CFG>(w, b);
+				sm.OB[((tt - (int)t_lo) / RN) * 32 + lane] = b.OB;
+				sm.inc[((tt - (int)t_lo) / RN) * 32 + lane] = inc;
 			}
+#pragma unroll
+			for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
 		}
 		__syncwarp();
-		// emission window is now band(t_lo) again (mid_b == mid_f)
+		// the emission window is band(t_lo) again (mid_b == mid_f)
 
 		// ---- step b: forward rows t_lo .. min(t_hi, T) - 1 ----------------------------------------------
+		uint32_t t = t_lo;
 		if (k == 0)
 		{
 			// row 0: fE[0][0] = 0 (NT:120) expressed relative to OF = Z2 - OB(0); VE[0][0] = 0 (NT:336)
@@ -626,156 +750,39 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 			}
 			const double ofl = shfl_f64(f.OF, (lane + 31) & 31);
 			f.dL = (float)(ofl - f.OF);
+			// row 0 only steps the forward recurrence (T >= 2, so row 0 is never the last row)
+			fwd_row<CFG, false, true>(w, f, sc, rs, args.thr2, 0, __shfl_sync(FULL, cur.xv, 0), cur.smask & 1u, mid_f,
+				sm.bE, sm.bE + ROWF, false, 0.0f);
+			if (RN == 1 || true) fwd_shift_to<CFG>(w, f, Z2 - sm.OB[32 + lane]);  // row 0 is a renormalisation row
+			t = 1;
 		}
+		const uint32_t t_end = min(t_hi, T - 1);  // regular rows: 1 <= t <= T-2
+#pragma unroll 1
+		for (; t < t_end; ++t)
 		{
-			const float* src = sm.bE;
-#pragma unroll
-			for (int j = 0; j < CPL; ++j) bEcur[j] = src[j * 32 + lane];
-		}
-		const uint32_t t_end = min(t_hi, T);
-		uint32_t t = t_lo;
-		while (t < t_end)
-		{
-			const uint32_t abase = t & ~31u;
-			const uint32_t cend = min(abase + 32, t_end);
-			float xv;
-			unsigned smask;
-			chunk_prefetch<CFG>(w, abase, xv, smask);
-			for (; t < cend; ++t)
-			{
-				const int i = (int)(t - abase);
-				const bool last = (t == T - 1);
-				const float x = __shfl_sync(FULL, xv, i);
-				const bool slide = !last && ((smask >> i) & 1u);
-				if (slide) w.activate(mid_f + 1 + w.bw);  // column entering band(t+1)
-
-				// backward values of this row: bE(t) is in bEcur; bM(t) = bE(t+1) + s(x[t]) - inc(t) (NT:200)
-				float s[CPL], bEn[CPL], LPM[CPL], LPE[CPL];
-				const float* nxt = sm.bE + (size_t)(t + 1 - t_lo) * CPL * 32;
-				const bool rn_row = (t % RN == 0);
-				const float inc_t = rn_row ? sm.inc[((t - t_lo) / RN) * 32 + lane] : 0.0f;
-#pragma unroll
-				for (int j = 0; j < CPL; ++j)
-				{
-					s[j] = emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]);
-					bEn[j] = last ? NEG : nxt[j * 32 + lane];
-					float bMj = last ? NEG : (bEn[j] + s[j]);
-					if (rn_row) bMj -= inc_t;
-					LPM[j] = f.fM[j] + bMj;
-					LPE[j] = f.fE[j] + bEcur[j];
-				}
-				if (slide && mid_f - w.bw >= 0)
-				{
-					// column lo_t leaves the band at row t+1, so bE[t+1][lo_t] is out of band (-inf in the
-					// reference) and with it bM[t][lo_t] = bE[t+1][lo_t] + s (NT:200); the recomputed row holds the
-					// ungated neighbour term there (see bwd_step), so the match posterior is forced instead
-					with_slot<CPL>(lane, pmod(mid_f - w.bw, CFG::SLOTS), SetOne<CPL>{LPM, NEG});
-				}
-				if (last)
-				{
-					// (Zf - Zb) in log2 units = log2-posterior of E(T-1, N-1)
-					float v = 0.0f;
-					with_slot<CPL>(lane, pmod((int)w.N - 1, CFG::SLOTS), GetOne<CPL>{LPE, v});
-					lpe_end = __shfl_sync(FULL, v, pmod((int)w.N - 1, CFG::SLOTS) / CPL);
-				}
-
-				if (t >= 1)
-				{
-					// posterior-Viterbi fill (NT:357-362) + decision bits (the test of NT:448 evaluated at fill time)
-					const float vl = __shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31) + f.dVL;
-					unsigned bitsw = 0;
-					float lmax = NEG;
-					float nVM[CPL];
-#pragma unroll
-					for (int j = 0; j < CPL; ++j)
-					{
-						const float left = (j > 0) ? f.VE[j - 1] : vl;
-						nVM[j] = left + LPM[j];
-					}
-#pragma unroll
-					for (int j = 0; j < CPL; ++j)
-					{
-						const float av = f.VM[j] + LPE[j];
-						const float bv = f.VE[j] + LPE[j];
-						f.VE[j] = fmaxf(av, bv);
-						bitsw |= (av >= bv) ? (1u << j) : 0u;
-						f.VM[j] = nVM[j];
-						lmax = fmaxf(lmax, fmaxf(LPM[j], LPE[j]));
-					}
-					if (t % CFG::RV == 0) vit_renorm<CFG>(w, f);
-					sc.bits[(size_t)t * 32 + lane] = (uint16_t)bitsw;
-
-					// sparse posterior records: the few cells per row with a non-negligible posterior
-					if (lane == 0) sc.rowptr[t] = nrec;
-					if (__any_sync(FULL, lmax > args.thr2))
-					{
-						const int n0 = mid_f - w.bw;
-#pragma unroll
-						for (int j = 0; j < CPL; ++j)
-						{
-							const bool hit = fmaxf(LPM[j], LPE[j]) > args.thr2;
-							const unsigned hm = __ballot_sync(FULL, hit);
-							if (hm)
-							{
-								if (hit)
-								{
-									const uint32_t pos = nrec + __popc(hm & ((1u << lane) - 1u));
-									if (pos < args.rec_cap)
-									{
-										PostRec r;
-										r.n = (uint32_t)w.col_of_slot(lane * CPL + j, n0);
-										r.lpm = LPM[j];
-										r.lpe = LPE[j];
-										sc.recs[pos] = r;
-									}
-								}
-								nrec += __popc(hm);
-							}
-						}
-						if (nrec > args.rec_cap)
-						{
-							overflow = true;
-							nrec = (uint32_t)args.rec_cap;
-						}
-					}
-				}
-
-				if (!last)
-				{
-					// forward step to row t+1 (NT:141-150)
-					const float fl = __shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) + f.dL;
-					float nfM[CPL];
-#pragma unroll
-					for (int j = 0; j < CPL; ++j)
-					{
-						const float left = (j > 0) ? f.fE[j - 1] : fl;
-						nfM[j] = left + (s[j] + w.m1);
-					}
-#pragma unroll
-					for (int j = 0; j < CPL; ++j)
-					{
-						f.fE[j] = logplus2(f.fM[j], f.fE[j] + w.e2) + s[j];
-						f.fM[j] = nfM[j];
-						bEcur[j] = bEn[j];
-					}
-					if (slide)
-					{
-						const int nold = mid_f - w.bw;  // column of band(t) that is not in band(t+1)
-						if (nold >= 0)
-						{
-							with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetTwo<CPL>{f.fM, f.fE, NEG});
-							w.deactivate(nold);
-						}
-						++mid_f;
-					}
-					if (rn_row) fwd_shift_to<CFG>(w, f, Z2 - sm.OB[((t - t_lo) / RN + 1) * 32 + lane]);
-				}
-			}
+			const int i = t & 31;
+			const uint32_t r = t - t_lo;
+			const bool rn_row = (t & (RN - 1)) == 0;
+			const float inc_t = rn_row ? sm.inc[(r / RN) * 32 + lane] : 0.0f;
+			fwd_row<CFG, true, true>(w, f, sc, rs, args.thr2, t, __shfl_sync(FULL, cur.xv, i), (cur.smask >> i) & 1u, mid_f,
+				sm.bE + (size_t)r * ROWF, sm.bE + (size_t)(r + 1) * ROWF, rn_row, inc_t);
+			if (rn_row) fwd_shift_to<CFG>(w, f, Z2 - sm.OB[(r / RN + 1) * 32 + lane]);
 		}
 		__syncwarp();
 	}
-	if (lane == 0) sc.rowptr[T] = nrec;
-	nrec_out = nrec;
+	// last row T-1: posteriors, Viterbi, bits, records; no forward step, no match posterior
+	{
+		const uint32_t r = (T - 1) - kb * CK;
+		fwd_row<CFG, true, false>(w, f, sc, rs, args.thr2, T - 1, 0.0f, false, mid_f, sm.bE + (size_t)r * ROWF,
+			sm.bE + (size_t)r * ROWF, false, 0.0f);
+	}
+	// (Zf - Zb) in log2 units = fE[T-1][N-1] + bE[T-1][N-1] with bE = 0 there (NT:170,285-286)
+	float v = 0.0f;
+	with_slot<CPL>(lane, pmod((int)w.N - 1, CFG::SLOTS), GetOne<CPL>{f.fE, v});
+	const float lpe_end = __shfl_sync(FULL, v, pmod((int)w.N - 1, CFG::SLOTS) / CPL);
+	if (lane == 0) sc.rowptr[T] = rs.n;
+	nrec_out = rs.n;
+	overflow = rs.overflow;
 	return lpe_end;
 }
 
@@ -811,7 +818,6 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 	// phase 1: walk the decision bits from (T-1, N-1) in state E
 	uint32_t t = T - 1, n = N - 1;
 	int inM = 0;
-	int ok = 1;
 	while (true)
 	{
 		const uint32_t cbase = t & ~31u;
@@ -844,7 +850,7 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 					sc.pn[t] = n;
 					const int q = (int)(n % SLOTS);
 					const int ql = q / CPL, j = q - ql * CPL;
-					inM = (sbits[(t - cbase) * 32 + ql] >> j) & 1;
+					inM = ((sbits[(t - cbase) * 32 + ql] >> j) & 1) ^ 1;
 					--t;
 				}
 				if (t < cbase) break;
@@ -858,8 +864,7 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 	}
 	// a complete path consumes every column: n == 0 and the first match sits at row 1
 	const uint32_t t_first = t + 1;  // first path row
-	ok = (n == 0) && !inM;
-	if (!ok) return false;
+	if (!((n == 0) && !inM)) return false;
 	__threadfence_block();
 	__syncwarp();
 
@@ -957,7 +962,7 @@ DYN_DEV void train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchAr
 }
 
 // ------------------------------------------------------------------------------------------------------
-// the persistent kernel: one single-warp CTA per resident read slot, reads pulled from an atomic queue
+// one read, all passes
 // ------------------------------------------------------------------------------------------------------
 template <class CFG, int MODE>
 DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx, const SlotScratch& sc,
@@ -996,7 +1001,7 @@ DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx
 		const float dz2 = forward_posterior_pass<CFG>(w, sc, args, smem_raw, Z2, nrec, overflow);
 		out.nrec = nrec;
 		out.dZ = (double)dz2 * LN2;
-		// the reference's consistency check (NT:288-291): |Zf - Zb| / (T*B) > 1e-8, B = 2*bw + 3
+		// the reference's consistency check (NT:288-291): |Zf - Zb| / (T*B) > 1e-8, B = 2*bw + 3.
 		// In the reference's double arithmetic Zf and Zb agree to ~1e-9, so that test only ever fires when a
 		// score is -inf (the band cut every path).  FP32 state carries |Zf - Zb| ~ 1e-4 .. 1e-3, which a narrow
 		// band (small B) would trip, so an FP32 rounding allowance is added to the reference's tolerance.

@@ -129,9 +129,15 @@ struct Rt
 namespace
 {
 
-// Build-time geometry: 13 columns per lane (ring of 416 >= 2*200+2), checkpoints every 16 rows,
-// backward renormalisation every 4 rows, Viterbi renormalisation every 8 rows.
-using CfgDefault = Cfg<13, 16, 4, 8>;
+// Build-time geometry variants: 13 columns per lane (ring of 416 >= 2*200+2), backward renormalisation every
+// 4 rows, Viterbi renormalisation every 8 rows; checkpoint spacing CK and the register budget (resident
+// single-warp CTAs per SM) trade shared memory / HBM scratch against latency hiding:
+//   variant 0: CK = 16, 7 CTAs/SM (<= 255 registers, 30 KB smem)      scratch 224 B/row for checkpoints
+//   variant 1: CK =  8, 10 CTAs/SM (<= 200 registers, 16 KB smem)     scratch 448 B/row
+//   variant 2: CK =  8, 12 CTAs/SM (<= 168 registers, 16 KB smem)     scratch 448 B/row
+using Cfg16 = Cfg<13, 16, 4, 8>;
+using Cfg8 = Cfg<13, 8, 4, 8>;
+constexpr int N_VARIANTS = 3;
 
 struct EncodeArgs
 {
@@ -269,8 +275,8 @@ __global__ void __launch_bounds__(32) k_encode(EncodeArgs a)
 {
 	for (uint32_t r = blockIdx.x; r < a.n_reads; r += gridDim.x) encode_read(a, r, threadIdx.x);
 }
-template <class CFG, int MODE>
-__global__ void __launch_bounds__(32) k_align(BatchArgs args)
+template <class CFG, int MODE, int MINB>
+__global__ void __launch_bounds__(32, MINB) k_align(BatchArgs args)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	align_worker<CFG, MODE>(args, smem_raw, threadIdx.x, blockIdx.x);
@@ -294,7 +300,7 @@ void launch_encode(Rt& rt, const EncodeArgs& a)
 #endif
 }
 
-template <class CFG>
+template <class CFG, int MINB>
 void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 {
 	const size_t smem = CFG::SMEM_BYTES;
@@ -302,14 +308,14 @@ void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 	static bool attr_set = false;
 	if (!attr_set)
 	{
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	if (mode == 0) k_align<CFG, 0><<<grid, 32, smem, rt.stream>>>(args);
-	else if (mode == 1) k_align<CFG, 1><<<grid, 32, smem, rt.stream>>>(args);
-	else k_align<CFG, 2><<<grid, 32, smem, rt.stream>>>(args);
+	if (mode == 0) k_align<CFG, 0, MINB><<<grid, 32, smem, rt.stream>>>(args);
+	else if (mode == 1) k_align<CFG, 1, MINB><<<grid, 32, smem, rt.stream>>>(args);
+	else k_align<CFG, 2, MINB><<<grid, 32, smem, rt.stream>>>(args);
 	CK_CUDA(cudaGetLastError());
 #else
 	(void)rt;
@@ -380,7 +386,8 @@ struct dyn_aligner
 	double trans[3] = {0, 0, 0};  // log m1, e1, e2 (NT:84-86)
 	std::vector<double> mean, stdev;
 	// tuning
-	int warps_per_sm = 8;
+	int warps_per_sm = 0;  // 0 = the variant's own occupancy
+	int variant = 0;
 	double thr2 = -22.0;
 	double recs_per_row = 8.0;
 	double mem_fraction = 0.85;
@@ -516,10 +523,10 @@ struct BatchResult
 };
 
 // mode: 0 Z only, 1 align, 2 train.  sigpos/prob (host) receive the segment arrays for mode 1.
-void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
+template <class CFG, int MINB>
+void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
 	double* pooled, double* per_read_w)
 {
-	using CFG = CfgDefault;
 	Rt& rt = A.rt;
 	rt.bind();
 	if (A.table_dirty) A.upload_table();
@@ -634,7 +641,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 	rt.mark(1);
 
 	// ---- scratch: one slot per resident warp, sized for the longest read --------------------------------------
-	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * A.warps_per_sm, order.size());
+	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * (A.warps_per_sm > 0 ? A.warps_per_sm : MINB), order.size());
 	size_t per_slot = 0;
 	uint64_t rec_cap = 0;
 	size_t o_ck = 0, o_ob = 0, o_bits = 0, o_rp = 0, o_rec = 0, o_pn = 0, o_pp = 0;
@@ -704,7 +711,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 
 	// ---- K2..K5: the DP kernel ------------------------------------------------------------------------------------
 	rt.mark(2);
-	launch_align<CFG>(rt, ba, grid, mode);
+	launch_align<CFG, MINB>(rt, ba, grid, mode);
 	rt.mark(3);
 	int launches = 2;
 	if (mode == 2)
@@ -748,14 +755,16 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 	}
 }
 
-// Re-run reads whose sparse-record buffer overflowed, with a buffer that can hold every in-band cell.
-struct SubsetBatch
+void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
+	double* pooled, double* per_read_w)
 {
-	std::vector<uint64_t> sig_off, seq_off;
-	std::vector<float> sig;
-	std::vector<double> sig64;
-	std::string seq;
-};
+	switch (A.variant)
+	{
+	case 1: run_batch_t<Cfg8, 10>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	case 2: run_batch_t<Cfg8, 12>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	default: run_batch_t<Cfg16, 7>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	}
+}
 
 } // namespace
 
@@ -1171,7 +1180,8 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 {
 	std::lock_guard<std::mutex> g(A->mu);
 	const std::string k(key);
-	if (k == "warps_per_sm") A->warps_per_sm = std::max(1, (int)value);
+	if (k == "warps_per_sm") A->warps_per_sm = std::max(0, (int)value);
+	else if (k == "variant") A->variant = std::min(N_VARIANTS - 1, std::max(0, (int)value));
 	else if (k == "thr2") A->thr2 = value;
 	else if (k == "recs_per_row") A->recs_per_row = value;
 	else if (k == "mem_fraction") A->mem_fraction = value;

@@ -201,6 +201,11 @@ inline void __threadfence() {}
 
 // ---- intrinsics --------------------------------------------------------------------------------------------
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift)
+{
+	shift &= 31;
+	return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
+}
 inline unsigned __float_as_uint(float f)
 {
 	unsigned u;

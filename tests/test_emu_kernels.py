@@ -1,0 +1,94 @@
+"""CPU tests of the CUDA kernels through the SIMT emulator (tests/emu): the very same .cu sources compiled with
+g++ against simt_host.h, driven through the same C ABI and Python binding as the GPU library.  They cover the
+kernel logic (ring slots, band slides, checkpoints, per-lane offsets, traceback, medians, training statistics)
+against the golden vectors of the compiled reference.  The numerical claims that count are the -m gpu tests."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import TRAIN_RTOL, check_alignment, load_golden
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+import build_emu  # noqa: E402
+
+SMALL = ["rna002_short", "rna002_band", "rna002_min_dwell", "rna002_dinuc", "rna004_9mer"]
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    return build_emu.build()
+
+
+def _aligner(lib, case, variant=0, band=400):
+    from dynamont_b200 import Aligner
+    al = Aligner(case.model_path, case.pore, band=band, _lib_path=lib)
+    al.set_option("variant", variant)
+    return al
+
+
+@pytest.mark.parametrize("case", [c for c in load_golden() if c.name in SMALL], ids=lambda c: c.name)
+def test_emulated_align_matches_reference(case, emu_lib):
+    al = _aligner(emu_lib, case)
+    r = al.align(case.signal, case.sequence, True)
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    assert al.align(case.signal, case.sequence, False)["Z"] == r["Z"]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_emulated_variants(variant, emu_lib):
+    case = [c for c in load_golden() if c.name == "rna002_band"][0]
+    al = _aligner(emu_lib, case, variant)
+    r = al.align(case.signal, case.sequence, True)
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+
+
+def test_emulated_training(emu_lib):
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    al = _aligner(emu_lib, case)
+    per_read, pooled = al.train_batch([case.signal], [case.sequence], per_read_model=True)
+    r = per_read[0]
+    tp = r["transition_params"]
+    np.testing.assert_allclose([tp["m1"], tp["e1"], tp["e2"]], case.train_trans, rtol=TRAIN_RTOL)
+    heavy = case.stat_w > 1e-3
+    km = case.train_kmers
+    np.testing.assert_allclose(pooled["w"][km][heavy], case.stat_w[heavy], rtol=TRAIN_RTOL)
+    np.testing.assert_allclose(r["emission_model"]["mean"][km][heavy], case.train_mean[heavy], rtol=TRAIN_RTOL, atol=1e-5)
+
+
+def test_emulated_narrow_band_and_errors(emu_lib):
+    """Narrow bands exercise the band-edge gating; error reads must carry the reference's messages."""
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import materialize_model, native_model, synth_read
+    from conftest import MODELS_DIR
+    from oracle import Oracle
+    path = materialize_model("rna002_5mer", MODELS_DIR)
+    nm, ns = native_model(path, "rna002")
+    rng = np.random.default_rng(3)
+    s, q, _ = synth_read(rng, nm, ns, 5, 150, 8)
+    for band in (6, 10):
+        al = Aligner(path, "rna002", band=band, _lib_path=emu_lib)
+        orc = Oracle(path, "rna002", band=band)
+        try:
+            o = orc.align(s, q, True)
+        except RuntimeError as e:
+            with pytest.raises(RuntimeError, match=str(e)):
+                al.align(s, q, True)
+            continue
+        check_alignment(al.align(s, q, True), o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
+    al = Aligner(path, "rna002", _lib_path=emu_lib)
+    bad = [(np.zeros(0), "ACGTACGT", "Signal is empty"), (s[:50], "ACG", "Sequence shorter than model kmer size"),
+           (s[:20], q[:40], "Signal too short compared to sequence"), (s, q[:30] + "N" + q[31:], "Invalid nucleotide: N")]
+    res = al.align_batch([b[0] for b in bad] + [s], [b[1] for b in bad] + [q], True)
+    for (sig, seq, msg), r in zip(bad, res):
+        assert isinstance(r, RuntimeError) and str(r) == msg
+    assert isinstance(res[-1], dict)
+    with pytest.raises(ValueError, match="Unknown pore type: foo"):
+        Aligner(path, "foo", _lib_path=emu_lib)
+    with pytest.raises(ValueError, match="Unknown aligner mode: bar"):
+        Aligner(path, "rna002", mode="bar", _lib_path=emu_lib)
+    with pytest.raises(RuntimeError, match="Could not open model file"):
+        Aligner(path + ".missing", "rna002", _lib_path=emu_lib)
+    with pytest.raises(RuntimeError, match="Inconsistent kmer size in model"):
+        Aligner(path, "rna004", _lib_path=emu_lib)
