@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--warps-per-sm", type=int, default=0)
+    ap.add_argument("--z-only", action="store_true", help="experiment: backward pass only (calc_probabilities=False)")
+    ap.add_argument("--opt", action="append", default=[], help="experiment: KEY=VALUE passed to dyn_set_option")
     ap.add_argument("--variant", type=int, default=-1, help="kernel build variant (see csrc/engine.cu); -1 = library default")
     return ap.parse_args()
 
@@ -293,6 +295,9 @@ def main():
         al.set_option("warps_per_sm", args.warps_per_sm)
     if args.variant >= 0:
         al.set_option("variant", args.variant)
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        al.set_option(k_, float(v_))
     cells = al.batch_cells(sig_off, seq_off)
     n_reads = sig_off.size - 1
     n_samples = int(sig_off[-1])
@@ -304,7 +309,7 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        return al.align_packed(d_signal.data_ptr(), sig_off, d_bases.data_ptr(), seq_off, True, device=True)
+        return al.align_packed(d_signal.data_ptr(), sig_off, d_bases.data_ptr(), seq_off, not args.z_only, device=True)
 
     dp_ms, launches = [], 0
     for _ in range(args.warmup):

@@ -84,11 +84,14 @@ struct __align__(16) PosConst
 	float a, b, c, pad;
 };
 
-// One sparse posterior record: lattice column and the two log2-posteriors of that cell.
-struct PostRec
+// One sparse posterior record = the log2-posteriors (match, extend) of all CPL cells of ONE lane for one row.
+// A lane is recorded when any of its cells has a non-negligible posterior; per row that is typically one
+// lane (the alignment path crosses a lane boundary every CPL columns).  16-byte aligned for vector stores.
+template <int CPL>
+struct __align__(16) LaneRec
 {
-	uint32_t n;
-	float lpm, lpe;
+	static constexpr int NF = (2 * CPL + 1 + 3) / 4 * 4;  // floats, rounded up to a multiple of 4
+	float v[NF];  // [0, CPL): match, [CPL, 2*CPL): extend, [2*CPL]: lane id (as int bits)
 };
 
 enum Status : int32_t

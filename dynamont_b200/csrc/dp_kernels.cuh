@@ -48,7 +48,7 @@ struct SlotScratch
 	double* ckpt_ob;    // [nck][32]
 	uint16_t* bits;     // [T][32]   decision bits: bit j of word (t, lane) set <=> cell in slot lane*CPL+j came from E
 	uint32_t* rowptr;   // [T+1]     first sparse record of row t
-	PostRec* recs;      // [rec_cap]
+	void* recs;         // [rec_cap] LaneRec<CPL>
 	uint32_t* pn;       // [T]       path column of row t (bit 31: match state)
 	float* pp;          // [T]       posterior of the path cell of row t
 };
@@ -537,7 +537,7 @@ DYN_DEV void vit_renorm(Warp<CFG>& w, Fwd<CFG::CPL>& f)
 
 struct RecSink
 {
-	PostRec* recs;
+	void* recs;
 	uint64_t cap;
 	uint32_t n;
 	bool overflow;
@@ -599,33 +599,32 @@ DYN_DEV void fwd_row(Warp<CFG>& w, Fwd<CFG::CPL>& f, const SlotScratch& sc, RecS
 		if ((t & (CFG::RV - 1)) == 0) vit_renorm<CFG>(w, f);
 		sc.bits[(size_t)t * 32 + lane] = (uint16_t)acc;
 
-		// sparse posterior records: the few cells per row with a non-negligible posterior
+		// sparse posterior records: every lane that holds a cell with a non-negligible posterior dumps its CPL
+		// (match, extend) pairs with vector stores — typically one lane per row
 		if (lane == 0) sc.rowptr[t] = rs.n;
-		if (__any_sync(FULL, lmax > thr2))
+		const bool hot = lmax > thr2;
+		const unsigned hm = __ballot_sync(FULL, hot);
+		if (hm)
 		{
-			const int n0 = mid_f - w.bw;
-#pragma unroll
-			for (int j = 0; j < CPL; ++j)
+			const uint32_t pos = rs.n + __popc(hm & ((1u << lane) - 1u));
+			if (hot && pos < rs.cap)
 			{
-				const bool hit = fmaxf(LPM[j], LPE[j]) > thr2;
-				const unsigned hm = __ballot_sync(FULL, hit);
-				if (hm)
+				typedef LaneRec<CPL> Rec;
+				float4* dst = reinterpret_cast<float4*>(static_cast<Rec*>(rs.recs) + pos);
+				float tmp[Rec::NF];
+#pragma unroll
+				for (int j = 0; j < CPL; ++j)
 				{
-					if (hit)
-					{
-						const uint32_t pos = rs.n + __popc(hm & ((1u << lane) - 1u));
-						if (pos < rs.cap)
-						{
-							PostRec r;
-							r.n = (uint32_t)w.col_of_slot(lane * CPL + j, n0);
-							r.lpm = LPM[j];
-							r.lpe = LPE[j];
-							rs.recs[pos] = r;
-						}
-					}
-					rs.n += __popc(hm);
+					tmp[j] = LPM[j];
+					tmp[CPL + j] = LPE[j];
 				}
+				tmp[2 * CPL] = __int_as_float(lane);
+#pragma unroll
+				for (int q = 2 * CPL + 1; q < Rec::NF; ++q) tmp[q] = 0.0f;
+#pragma unroll
+				for (int q = 0; q < Rec::NF / 4; ++q) dst[q] = make_float4(tmp[4 * q], tmp[4 * q + 1], tmp[4 * q + 2], tmp[4 * q + 3]);
 			}
+			rs.n += __popc(hm);
 			if (rs.n > rs.cap)
 			{
 				rs.overflow = true;
@@ -789,15 +788,33 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 // ------------------------------------------------------------------------------------------------------
 // pass 3: traceback (NT:383-456), path posteriors, per-segment medians (aligner.cpp:247-263)
 // ------------------------------------------------------------------------------------------------------
-DYN_DEV float select_kth(const float* v, uint32_t d, uint32_t kth)
+// median of d <= 32 values (one per lane; lanes >= d hold +inf) by ranking: the lane whose value has rank k owns
+// the k-th smallest.  Returns (k-th smallest, (k-1)-th smallest) broadcast to all lanes.
+DYN_DEV void rank_select(float v, uint32_t d, uint32_t k, int lane, float& kth, float& prev)
 {
-	// kth smallest (0-based) of d non-negative floats by binary search on the bit pattern
-	uint32_t lo = 0u, hi = 0x7f800000u;  // answer in [lo, hi]
+	uint32_t rank = 0;
+	for (uint32_t s = 0; s < d; ++s)
+	{
+		const float o = __shfl_sync(FULL, v, (int)s);
+		rank += (o < v || (o == v && (int)s < lane)) ? 1u : 0u;
+	}
+	const unsigned mk = __ballot_sync(FULL, lane < (int)d && rank == k);
+	const unsigned mp = __ballot_sync(FULL, lane < (int)d && rank + 1 == k);
+	kth = __shfl_sync(FULL, v, __ffs(mk) - 1);
+	prev = mp ? __shfl_sync(FULL, v, __ffs(mp) - 1) : kth;
+}
+
+// k-th smallest (0-based) of d non-negative floats at v[0..d) (global memory), all lanes cooperating: binary
+// search on the bit pattern with a warp-wide count per step
+DYN_DEV float coop_select(const float* v, uint32_t d, uint32_t kth, int lane)
+{
+	uint32_t lo = 0u, hi = 0x7f800000u;
 	while (lo < hi)
 	{
 		const uint32_t midv = lo + (hi - lo) / 2;
-		uint32_t cnt = 0;  // #elements <= midv
-		for (uint32_t i = 0; i < d; ++i) cnt += (__float_as_uint(v[i]) <= midv) ? 1u : 0u;
+		uint32_t cnt = 0;
+		for (uint32_t i = lane; i < d; i += 32) cnt += (__float_as_uint(v[i]) <= midv) ? 1u : 0u;
+		cnt = __reduce_add_sync(FULL, cnt);
 		if (cnt >= kth + 1) hi = midv;
 		else lo = midv + 1;
 	}
@@ -810,20 +827,22 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 {
 	constexpr int CPL = CFG::CPL;
 	constexpr int SLOTS = CFG::SLOTS;
+	typedef LaneRec<CPL> Rec;
 	const int lane = w.lane;
 	const uint32_t T = w.T, N = w.N;
 	uint32_t* border = args.out_sigpos + rd.out_off;  // Kc = N-1 entries
 	uint16_t* sbits = reinterpret_cast<uint16_t*>(smem_raw);  // 32 rows x 32 lanes
 
-	// phase 1: walk the decision bits from (T-1, N-1) in state E
-	uint32_t t = T - 1, n = N - 1;
+	// phase 1: walk the decision bits from (T-1, N-1) in state E (NT:398-452), one 32-row chunk at a time; within a
+	// chunk every lane tests one row, so a whole run of E rows in one column is consumed per step
+	int t = (int)T - 1, n = (int)N - 1;
 	int inM = 0;
-	while (true)
+	bool done = false;
+	while (!done)
 	{
-		const uint32_t cbase = t & ~31u;
-		// all lanes stage rows cbase .. cbase+31
+		const int cbase = t & ~31;
 		{
-			const uint32_t r = cbase + lane;
+			const uint32_t r = (uint32_t)cbase + lane;
 			const uint4* src = reinterpret_cast<const uint4*>(sc.bits + (size_t)r * 32);
 			uint4* dst = reinterpret_cast<uint4*>(sbits + lane * 32);
 			if (r < T)
@@ -833,58 +852,72 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 			}
 		}
 		__syncwarp();
-		if (lane == 0)
+		while (t >= cbase)
 		{
-			while (t >= cbase && t > 0 && n > 0)
+			if (t == 0 || n == 0)
 			{
-				if (inM)
-				{
-					sc.pn[t] = n | 0x80000000u;
-					border[n - 1] = t - 1;  // Segment.signalPosition (NT:424-430)
-					--t;
-					--n;
-					inM = 0;
-				}
-				else
-				{
-					sc.pn[t] = n;
-					const int q = (int)(n % SLOTS);
-					const int ql = q / CPL, j = q - ql * CPL;
-					inM = ((sbits[(t - cbase) * 32 + ql] >> j) & 1) ^ 1;
-					--t;
-				}
-				if (t < cbase) break;
+				done = true;
+				break;
 			}
+			if (inM)
+			{
+				// match state at (t, n): emits the segment border (NT:416-440)
+				if (lane == 0)
+				{
+					sc.pn[t] = (uint32_t)n | 0x80000000u;
+					border[n - 1] = (uint32_t)t - 1;  // Segment.signalPosition (NT:424-430)
+				}
+				--t;
+				--n;
+				inM = 0;
+				continue;
+			}
+			// extension run in column n: rows t, t-1, ... until the row whose E cell was entered from M (NT:443-451)
+			const int q = n % SLOTS;
+			const int ql = q / CPL, j = q - ql * CPL;
+			const int row = cbase + lane;
+			const bool valid = row <= t && row >= 1;
+			const bool from_m = valid && (((sbits[lane * 32 + ql] >> j) & 1) == 0);
+			const unsigned mk = __ballot_sync(FULL, from_m);
+			int tstar;  // lowest row of the run inside this chunk
+			if (mk)
+			{
+				tstar = cbase + (31 - __clz(mk));
+				inM = 1;
+			}
+			else
+				tstar = max(cbase, 1);
+			if (row >= tstar && row <= t) sc.pn[row] = (uint32_t)n;
+			t = tstar - 1;
 		}
 		__syncwarp();
-		t = __shfl_sync(FULL, t, 0);
-		n = __shfl_sync(FULL, n, 0);
-		inM = __shfl_sync(FULL, inM, 0);
-		if (t == 0 || n == 0) break;
 	}
 	// a complete path consumes every column: n == 0 and the first match sits at row 1
-	const uint32_t t_first = t + 1;  // first path row
+	const uint32_t t_first = (uint32_t)t + 1;  // first path row
 	if (!((n == 0) && !inM)) return false;
 	__threadfence_block();
 	__syncwarp();
 
 	// phase 2: posterior of the path cell of every row, normalised by the row's recorded mass
+	const Rec* recs = static_cast<const Rec*>(sc.recs);
 	for (uint32_t r = t_first + lane; r < T; r += 32)
 	{
 		const uint32_t v = sc.pn[r];
 		const uint32_t col = v & 0x7fffffffu;
 		const bool isM = (v >> 31) != 0;
+		const int q = (int)(col % SLOTS);
+		const int ql = q / CPL, j = q - ql * CPL;
 		const uint32_t r0 = sc.rowptr[r], r1 = sc.rowptr[r + 1];
 		float mass = 0.0f, lp = 0.0f;
 		bool found = false;
 		for (uint32_t i = r0; i < r1; ++i)
 		{
-			const PostRec rec = sc.recs[i];
-			mass += exp2f(rec.lpm) + exp2f(rec.lpe);
-			if (rec.n == col)
+			const float* f = recs[i].v;
+			for (int c = 0; c < 2 * CPL; ++c) mass += ex2(f[c]);
+			if (__float_as_int(f[2 * CPL]) == ql)
 			{
 				found = true;
-				lp = isM ? rec.lpm : rec.lpe;
+				lp = f[(isM ? 0 : CPL) + j];
 			}
 		}
 		sc.pp[r] = (found && mass > 0.0f) ? exp2f(lp - log2f(mass)) : 0.0f;
@@ -892,25 +925,28 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 	__threadfence_block();
 	__syncwarp();
 
-	// phase 3: per-segment median of the path posteriors (NT:418-422, aligner.cpp:247-263)
+	// phase 3: per-segment median of the path posteriors (NT:418-422, aligner.cpp:247-263), one segment at a time
 	double* prob = args.out_prob + rd.out_off;
 	const uint32_t Kc = N - 1;
-	for (uint32_t sgm = lane; sgm < Kc; sgm += 32)
+	uint32_t rs_ = border[0] + 1;
+	for (uint32_t sgm = 0; sgm < Kc; ++sgm)
 	{
-		const uint32_t rs = border[sgm] + 1;
 		const uint32_t re = (sgm + 1 < Kc) ? border[sgm + 1] : (T - 1);  // inclusive
-		const uint32_t d = re - rs + 1;
-		const float* v = sc.pp + rs;
-		double med;
-		if (d & 1u)
-			med = (double)select_kth(v, d, d / 2);
+		const uint32_t d = re - rs_ + 1;
+		const float* v = sc.pp + rs_;
+		float up, dn;
+		if (d <= 32)
+		{
+			const float mine = ((uint32_t)lane < d) ? v[lane] : 3.0e38f;
+			rank_select(mine, d, d / 2, lane, up, dn);
+		}
 		else
 		{
-			const float up = select_kth(v, d, d / 2);
-			const float dn = select_kth(v, d, d / 2 - 1);
-			med = ((double)dn + (double)up) / 2.0;
+			up = coop_select(v, d, d / 2, lane);
+			dn = (d & 1u) ? up : coop_select(v, d, d / 2 - 1, lane);
 		}
-		prob[sgm] = med;
+		if (lane == 0) prob[sgm] = (d & 1u) ? (double)up : ((double)dn + (double)up) / 2.0;
+		rs_ = re + 1;
 	}
 	return true;
 }
@@ -926,6 +962,9 @@ template <class CFG>
 DYN_DEV void train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd,
 	double& xi_m, double& xi_e)
 {
+	constexpr int CPL = CFG::CPL;
+	typedef LaneRec<CPL> Rec;
+	const Rec* recs = static_cast<const Rec*>(sc.recs);
 	const int lane = w.lane;
 	double sm_ = 0.0, se_ = 0.0;
 	for (uint32_t r = 1 + lane; r < w.T; r += 32)
@@ -934,22 +973,29 @@ DYN_DEV void train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchAr
 		double mass = 0.0;
 		for (uint32_t i = r0; i < r1; ++i)
 		{
-			const PostRec rec = sc.recs[i];
-			mass += (double)exp2f(rec.lpm) + (double)exp2f(rec.lpe);
+			const float* f = recs[i].v;
+			for (int c = 0; c < 2 * CPL; ++c) mass += (double)exp2f(f[c]);
 		}
 		if (!(mass > 0.0)) continue;
 		const double inv = 1.0 / mass;
 		const double xo = (double)w.sig[r - 1];
+		const int n0 = (int)band_mid(r, w.ratio) - w.bw;
 		for (uint32_t i = r0; i < r1; ++i)
 		{
-			const PostRec rec = sc.recs[i];
-			const double pm = (double)exp2f(rec.lpm) * inv, pe = (double)exp2f(rec.lpe) * inv;
-			const double g = pm + pe;
-			atomicAdd(&args.read_w[rd.pc_off + rec.n], g);
-			atomicAdd(&args.read_x[rd.pc_off + rec.n], g * xo);
-			atomicAdd(&args.read_xx[rd.pc_off + rec.n], g * xo * xo);
-			sm_ += pm;
-			se_ += pe;
+			const float* f = recs[i].v;
+			const int rl = __float_as_int(f[2 * CPL]);
+			for (int j = 0; j < CPL; ++j)
+			{
+				const double pm = (double)exp2f(f[j]) * inv, pe = (double)exp2f(f[CPL + j]) * inv;
+				const double g = pm + pe;
+				if (!(g > 1e-12)) continue;
+				const int col = w.col_of_slot(rl * CPL + j, n0);
+				atomicAdd(&args.read_w[rd.pc_off + col], g);
+				atomicAdd(&args.read_x[rd.pc_off + col], g * xo);
+				atomicAdd(&args.read_xx[rd.pc_off + col], g * xo * xo);
+				sm_ += pm;
+				se_ += pe;
+			}
 		}
 	}
 	for (int o = 16; o; o >>= 1)

@@ -389,7 +389,7 @@ struct dyn_aligner
 	int warps_per_sm = 0;  // 0 = the variant's own occupancy
 	int variant = 0;
 	double thr2 = -22.0;
-	double recs_per_row = 8.0;
+	double recs_per_row = 2.0;  // lane records per row (typical use: ~1.1)
 	double mem_fraction = 0.85;
 	// device state
 	DevBuf d_table, d_sig, d_seq, d_seqoff, d_desc, d_order, d_pc, d_kmers, d_bad, d_out, d_sigpos, d_prob, d_scratch,
@@ -648,13 +648,13 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	if (mode != 0)
 	{
 		const size_t nck = (size_t)maxT / CFG::CK + 2;
-		rec_cap = (uint64_t)std::min<double>((double)maxT * A.recs_per_row, (double)maxT * (2.0 * (A.band / 2) + 1.0)) + 64;
+		rec_cap = (uint64_t)std::min<double>((double)maxT * A.recs_per_row, (double)maxT * 32.0) + 64;
 		size_t o = 0;
 		o_ck = o; o = align_up(o + nck * CFG::CKF * 4, 256);
 		o_ob = o; o = align_up(o + nck * 32 * 8, 256);
 		o_bits = o; o = align_up(o + ((size_t)maxT + 32) * 64, 256);
 		o_rp = o; o = align_up(o + ((size_t)maxT + 2) * 4, 256);
-		o_rec = o; o = align_up(o + rec_cap * sizeof(PostRec), 256);
+		o_rec = o; o = align_up(o + rec_cap * sizeof(LaneRec<CFG::CPL>), 256);
 		o_pn = o; o = align_up(o + ((size_t)maxT + 1) * 4, 256);
 		o_pp = o; o = align_up(o + ((size_t)maxT + 1) * 4, 256);
 		per_slot = o;
@@ -673,7 +673,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			slots[s].ckpt_ob = (double*)(b + o_ob);
 			slots[s].bits = (uint16_t*)(b + o_bits);
 			slots[s].rowptr = (uint32_t*)(b + o_rp);
-			slots[s].recs = (PostRec*)(b + o_rec);
+			slots[s].recs = (void*)(b + o_rec);
 			slots[s].pn = (uint32_t*)(b + o_pn);
 			slots[s].pp = (float*)(b + o_pp);
 		}

@@ -193,6 +193,16 @@ inline unsigned __ballot_sync(unsigned, int pred)
 	return r;
 }
 
+inline unsigned __reduce_add_sync(unsigned, unsigned v)
+{
+	simt::WarpRt* w = simt::rt();
+	w->xch[w->cur] = v;
+	simt::rendezvous();
+	unsigned s = 0;
+	for (int l = 0; l < simt::WARP; ++l) s += (unsigned)w->xch[l];
+	simt::rendezvous();
+	return s;
+}
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline void __syncwarp(unsigned = 0xffffffffu) { simt::rendezvous(); }
 inline void __syncthreads() { simt::rendezvous(); }
@@ -201,6 +211,25 @@ inline void __threadfence() {}
 
 // ---- intrinsics --------------------------------------------------------------------------------------------
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+inline float __int_as_float(int i)
+{
+	float f;
+	memcpy(&f, &i, 4);
+	return f;
+}
+inline int __float_as_int(float f)
+{
+	int i;
+	memcpy(&i, &f, 4);
+	return i;
+}
+struct float4
+{
+	float x, y, z, w;
+};
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift)
 {
 	shift &= 31;
