@@ -433,12 +433,14 @@ DYN_DEV double backward_pass(Warp<CFG>& w, const SlotScratch& sc)
 		const uint32_t base = (uint32_t)t & ~31u;
 		const Chunk cur = nxt;
 		if (base >= 32) nxt = chunk_load<CFG>(w, base - 32);
+		float x = __shfl_sync(FULL, cur.xv, t - (int)base);
 #pragma unroll 1
 		for (int i = t - (int)base; i >= 0; --i)
 		{
 			const uint32_t tt = base + i;
-			const float x = __shfl_sync(FULL, cur.xv, i);
+			const float xn = __shfl_sync(FULL, cur.xv, (i - 1) & 31);  // next row's sample, off the critical path
 			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid);
+			x = xn;
 			if ((tt & (CFG::RN - 1)) == 0)
 			{
 				bwd_renorm<CFG>(w, b);
@@ -546,10 +548,12 @@ struct RecSink
 // One row of pass 2.  On entry f holds the forward values of row t and the Viterbi values of row t-1.
 //   DO_V:    posteriors of row t, posterior-Viterbi update (NT:357-362), decision bits, sparse records
 //   DO_STEP: forward recurrence to row t+1 (NT:141-150) incl. the band slide between t and t+1
-// cur/nxt: shared-memory rows bE(t) / bE(t+1) of the recomputed backward block.
+// bc/bn: this lane's values of the recomputed backward rows bE(t) / bE(t+1), already in registers; pf (or NULL):
+// shared-memory row bE(t+1), from which bc/bn of the NEXT row are fetched before the MUFU-heavy forward step so
+// that their latency is hidden.
 template <class CFG, bool DO_V, bool DO_STEP>
 DYN_DEV void fwd_row(Warp<CFG>& w, Fwd<CFG::CPL>& f, const SlotScratch& sc, RecSink& rs, float thr2, uint32_t t,
-	float x, bool slide, int& mid_f, const float* cur, const float* nxt, bool rn_row, float inc_t)
+	float x, bool slide, int& mid_f, float (&bc)[CFG::CPL], float (&bn)[CFG::CPL], const float* pf, bool rn_row, float inc_t)
 {
 	constexpr int CPL = CFG::CPL;
 	const int lane = w.lane;
@@ -562,9 +566,9 @@ DYN_DEV void fwd_row(Warp<CFG>& w, Fwd<CFG::CPL>& f, const SlotScratch& sc, RecS
 		s[j] = emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]);
 		if (DO_V)
 		{
-			LPE[j] = f.fE[j] + cur[j * 32 + lane];
+			LPE[j] = f.fE[j] + bc[j];
 			// bM[t][n] = bE[t+1][n] + score(x[t], kmer[n-1]) (NT:200); the last row has no match state (-inf)
-			LPM[j] = DO_STEP ? f.fM[j] + (nxt[j * 32 + lane] + s[j]) : NEG;
+			LPM[j] = DO_STEP ? f.fM[j] + (bn[j] + s[j]) : NEG;
 		}
 	}
 	if (DO_V)
@@ -635,6 +639,15 @@ DYN_DEV void fwd_row(Warp<CFG>& w, Fwd<CFG::CPL>& f, const SlotScratch& sc, RecS
 	if (DO_STEP)
 	{
 		const float fl = __shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) + f.dL;
+		if (pf)
+		{
+#pragma unroll
+			for (int j = 0; j < CPL; ++j)
+			{
+				bc[j] = pf[j * 32 + lane];
+				bn[j] = pf[CFG::ROWF + j * 32 + lane];
+			}
+		}
 #pragma unroll
 		for (int j = CPL - 1; j >= 0; --j)
 		{
@@ -676,6 +689,9 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 	rs.overflow = false;
 
 	int mid_f = 0;  // band centre of the forward row
+	float bc[CPL], bn[CPL];  // backward rows bE(t), bE(t+1) of the current forward row
+#pragma unroll
+	for (int j = 0; j < CPL; ++j) bc[j] = bn[j] = NEG;
 	w.load_window(0);
 	const uint32_t kb = (T - 1) / CK;
 	// samples/slide masks per 32-row chunk: a block (CK | 32) lies inside one chunk; both the backward
@@ -707,11 +723,13 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 			sm.OB[((src_row - t_lo + RN - 1) / RN) * 32 + lane] = b.OB;
 		}
 		// the slide between src_row-1 and src_row may belong to the next chunk when src_row is 32-aligned
+		float xb = __shfl_sync(FULL, cur.xv, ((int)src_row - 1) & 31);
 #pragma unroll 1
 		for (int tt = (int)src_row - 1; tt >= (int)t_lo; --tt)
 		{
 			const int i = tt & 31;
-			const float x = __shfl_sync(FULL, cur.xv, i);
+			const float x = xb;
+			xb = __shfl_sync(FULL, cur.xv, (i - 1) & 31);
 			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid_b);
 			float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
 			if ((tt & (RN - 1)) == 0)
@@ -751,11 +769,22 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 			f.dL = (float)(ofl - f.OF);
 			// row 0 only steps the forward recurrence (T >= 2, so row 0 is never the last row)
 			fwd_row<CFG, false, true>(w, f, sc, rs, args.thr2, 0, __shfl_sync(FULL, cur.xv, 0), cur.smask & 1u, mid_f,
-				sm.bE, sm.bE + ROWF, false, 0.0f);
-			if (RN == 1 || true) fwd_shift_to<CFG>(w, f, Z2 - sm.OB[32 + lane]);  // row 0 is a renormalisation row
+				bc, bn, nullptr, false, 0.0f);
+			fwd_shift_to<CFG>(w, f, Z2 - sm.OB[32 + lane]);  // row 0 is a renormalisation row
 			t = 1;
 		}
 		const uint32_t t_end = min(t_hi, T - 1);  // regular rows: 1 <= t <= T-2
+		if (t < t_end)
+		{
+			const float* row = sm.bE + (size_t)(t - t_lo) * ROWF;
+#pragma unroll
+			for (int j = 0; j < CPL; ++j)
+			{
+				bc[j] = row[j * 32 + lane];
+				bn[j] = row[ROWF + j * 32 + lane];
+			}
+		}
+		float x = __shfl_sync(FULL, cur.xv, t & 31);
 #pragma unroll 1
 		for (; t < t_end; ++t)
 		{
@@ -763,17 +792,20 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 			const uint32_t r = t - t_lo;
 			const bool rn_row = (t & (RN - 1)) == 0;
 			const float inc_t = rn_row ? sm.inc[(r / RN) * 32 + lane] : 0.0f;
-			fwd_row<CFG, true, true>(w, f, sc, rs, args.thr2, t, __shfl_sync(FULL, cur.xv, i), (cur.smask >> i) & 1u, mid_f,
-				sm.bE + (size_t)r * ROWF, sm.bE + (size_t)(r + 1) * ROWF, rn_row, inc_t);
+			const float xn = __shfl_sync(FULL, cur.xv, (i + 1) & 31);
+			fwd_row<CFG, true, true>(w, f, sc, rs, args.thr2, t, x, (cur.smask >> i) & 1u, mid_f, bc, bn,
+				(t + 1 < t_end) ? sm.bE + (size_t)(r + 1) * ROWF : nullptr, rn_row, inc_t);
 			if (rn_row) fwd_shift_to<CFG>(w, f, Z2 - sm.OB[(r / RN + 1) * 32 + lane]);
+			x = xn;
 		}
 		__syncwarp();
 	}
 	// last row T-1: posteriors, Viterbi, bits, records; no forward step, no match posterior
 	{
-		const uint32_t r = (T - 1) - kb * CK;
-		fwd_row<CFG, true, false>(w, f, sc, rs, args.thr2, T - 1, 0.0f, false, mid_f, sm.bE + (size_t)r * ROWF,
-			sm.bE + (size_t)r * ROWF, false, 0.0f);
+		const float* row = sm.bE + (size_t)((T - 1) - kb * CK) * ROWF;
+#pragma unroll
+		for (int j = 0; j < CPL; ++j) bc[j] = row[j * 32 + lane];
+		fwd_row<CFG, true, false>(w, f, sc, rs, args.thr2, T - 1, 0.0f, false, mid_f, bc, bn, nullptr, false, 0.0f);
 	}
 	// (Zf - Zb) in log2 units = fE[T-1][N-1] + bE[T-1][N-1] with bE = 0 there (NT:170,285-286)
 	float v = 0.0f;

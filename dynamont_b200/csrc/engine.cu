@@ -135,9 +135,10 @@ namespace
 //   variant 0: CK = 16, 7 CTAs/SM (<= 255 registers, 30 KB smem)      scratch 224 B/row for checkpoints
 //   variant 1: CK =  8, 10 CTAs/SM (<= 200 registers, 16 KB smem)     scratch 448 B/row
 //   variant 2: CK =  8, 12 CTAs/SM (<= 168 registers, 16 KB smem)     scratch 448 B/row
+//   variant 3: CK =  8, 8 CTAs/SM (<= 255 registers, 16 KB smem)      scratch 448 B/row
 using Cfg16 = Cfg<13, 16, 4, 8>;
 using Cfg8 = Cfg<13, 8, 4, 8>;
-constexpr int N_VARIANTS = 3;
+constexpr int N_VARIANTS = 4;
 
 struct EncodeArgs
 {
@@ -762,6 +763,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 	{
 	case 1: run_batch_t<Cfg8, 10>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 	case 2: run_batch_t<Cfg8, 12>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	case 3: run_batch_t<Cfg8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 	default: run_batch_t<Cfg16, 7>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 	}
 }
