@@ -9,6 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdynamont_b200.so")
+STREAM_BIN = os.path.join(CSRC, "dynamont-NT-b200")
+STREAM_SRC = os.path.join(CSRC, "stream_main.cpp")
 SOURCES = [os.path.join(CSRC, "engine.cu")]
 HEADERS = [os.path.join(CSRC, "dp_common.cuh"), os.path.join(CSRC, "dp_kernels.cuh"),
            os.path.join(HERE, "..", "include", "dynamont_b200.h")]
@@ -31,7 +33,7 @@ def up_to_date() -> bool:
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS)
+    return os.path.exists(STREAM_BIN) and all(os.path.getmtime(f) <= t for f in SOURCES + HEADERS + [STREAM_SRC])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -46,7 +48,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(log, file=sys.stderr)
     if r.returncode:
         raise RuntimeError("nvcc failed (see dynamont_b200/csrc/build.log)")
+    build_stream()
     return LIB
+
+
+def build_stream() -> str:
+    """The streaming stdin/stdout front end: plain C++ host code linked against the C ABI library."""
+    cmd = ["g++", "-O2", "-std=c++17", "-o", STREAM_BIN, STREAM_SRC, "-L" + CSRC, "-ldynamont_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return STREAM_BIN
 
 
 if __name__ == "__main__":

@@ -314,7 +314,7 @@ void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	if (mode == 0) k_align<CFG, 0, MINB><<<grid, 32, smem, rt.stream>>>(args);
+	if (mode == 0) k_align<CFG, 0, MINB><<<grid, 32, 0, rt.stream>>>(args);  // the backward pass alone needs no shared memory
 	else if (mode == 1) k_align<CFG, 1, MINB><<<grid, 32, smem, rt.stream>>>(args);
 	else k_align<CFG, 2, MINB><<<grid, 32, smem, rt.stream>>>(args);
 	CK_CUDA(cudaGetLastError());
@@ -642,7 +642,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	rt.mark(1);
 
 	// ---- scratch: one slot per resident warp, sized for the longest read --------------------------------------
-	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * (A.warps_per_sm > 0 ? A.warps_per_sm : MINB), order.size());
+	// Z-only runs the backward pass alone: <= 128 registers and no shared memory, i.e. 16 single-warp CTAs per SM
+	const int resident = (mode == 0) ? 16 : MINB;
+	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * (A.warps_per_sm > 0 ? A.warps_per_sm : resident), order.size());
 	size_t per_slot = 0;
 	uint64_t rec_cap = 0;
 	size_t o_ck = 0, o_ob = 0, o_bits = 0, o_rp = 0, o_rec = 0, o_pn = 0, o_pp = 0;
