@@ -390,7 +390,7 @@ def main():
     # (checkpoints 3584 B per 16 rows written+read, decision bits 64 B/row written+read, records ~ 12 B * few / row)
     hbm_bytes = n_samples * 4.0 + n_bases * 17.0 + (n_samples / 16.0) * 3584 * 2 + n_samples * 64.0 * 2 + n_samples * 12.0 * 3 * 2
     roofline = {
-        "bound": "sfu", "kernel": "k_align<Cfg<13,16,4,8>,1>",
+        "bound": "sfu", "kernel": "k_align<Cfg<13,CK,4,8>,1> (library default variant unless --variant)",
         "achieved": alg_mufu, "peak": mufu_peak, "unit": "G MUFU op/s", "frac": alg_mufu / mufu_peak,
         "executed": exe_mufu, "executed_frac": exe_mufu / mufu_peak,
         "peak_at_max_clock": mufu_peak_max, "peak_source": "16 MUFU/clk/SM x SMs x SM clock sampled by nvidia-smi during the timed region",

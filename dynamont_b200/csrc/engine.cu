@@ -388,7 +388,7 @@ struct dyn_aligner
 	std::vector<double> mean, stdev;
 	// tuning
 	int warps_per_sm = 0;  // 0 = the variant's own occupancy
-	int variant = 0;
+	int variant = 3;  // measured fastest on B200
 	double thr2 = -22.0;
 	double recs_per_row = 2.0;  // lane records per row (typical use: ~1.1)
 	double mem_fraction = 0.85;
