@@ -12,7 +12,7 @@ LIB = os.path.join(CSRC, "libdynamont_b200.so")
 STREAM_BIN = os.path.join(CSRC, "dynamont-NT-b200")
 STREAM_SRC = os.path.join(CSRC, "stream_main.cpp")
 SOURCES = [os.path.join(CSRC, "engine.cu")]
-HEADERS = [os.path.join(CSRC, "dp_common.cuh"), os.path.join(CSRC, "dp_kernels.cuh"),
+HEADERS = [os.path.join(CSRC, "dp_common.cuh"), os.path.join(CSRC, "dp_kernels.cuh"), os.path.join(CSRC, "dp_linear.cuh"),
            os.path.join(HERE, "..", "include", "dynamont_b200.h")]
 
 NVCC_FLAGS = [

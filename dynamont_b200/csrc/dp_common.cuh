@@ -34,7 +34,8 @@ DYN_DEV float ex2(float x)
 	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
 	return y;
 #else
-	return exp2f(x);
+	const float y = exp2f(x);
+	return y < 1.17549435e-38f ? 0.0f : y;  // .ftz
 #endif
 }
 
@@ -106,6 +107,7 @@ enum Status : int32_t
 	ST_REC_OVERFLOW = 7,        // internal: sparse posterior buffer too small, host retries with a full-size buffer
 	ST_INTERNAL = 8,
 	ST_BAND_UNSUPPORTED = 9,
+	ST_LIN_FAULT = 10,          // internal: the linear-domain kernel hit an FP32 range fault, host re-runs the read in the log2 domain
 };
 
 // Everything a warp needs to know about one read.  Built on the host, resident in HBM.

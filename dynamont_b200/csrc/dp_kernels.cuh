@@ -68,6 +68,8 @@ struct BatchArgs
 	double* out_prob;           // [sum Kc]
 	float m1, e2;               // log2 transition scores (e1 = log 1 = 0 is omitted, NT:33,85)
 	float thr2;                 // sparse-record threshold on max(log2 pM, log2 pE)
+	float m1_lin, e2_lin;       // the same transitions as plain probabilities (linear-domain kernels)
+	float thr_lin;              // 2^thr2
 	int mode;                   // 0: Z only (backward pass), 1: full alignment, 2: training statistics
 	// training (mode 2)
 	double* stat_w;             // [K] pooled sum of gamma              (NT:510)
@@ -853,19 +855,20 @@ DYN_DEV float coop_select(const float* v, uint32_t d, uint32_t kth, int lane)
 	return __uint_as_float(lo);
 }
 
+// phase 1 of pass 3: walk the decision bits, write the path (sc.pn) and the segment borders.  Returns false when
+// the path is incomplete; t_first = first path row.  Shared by the log2-domain and the linear-domain kernels.
 template <class CFG>
-DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
-	const ReadDesc& rd)
+DYN_DEV bool trace_decisions(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
+	const ReadDesc& rd, uint32_t& t_first_out)
 {
 	constexpr int CPL = CFG::CPL;
 	constexpr int SLOTS = CFG::SLOTS;
-	typedef LaneRec<CPL> Rec;
 	const int lane = w.lane;
 	const uint32_t T = w.T, N = w.N;
 	uint32_t* border = args.out_sigpos + rd.out_off;  // Kc = N-1 entries
 	uint16_t* sbits = reinterpret_cast<uint16_t*>(smem_raw);  // 32 rows x 32 lanes
 
-	// phase 1: walk the decision bits from (T-1, N-1) in state E (NT:398-452), one 32-row chunk at a time; within a
+	// walk the decision bits from (T-1, N-1) in state E (NT:398-452), one 32-row chunk at a time; within a
 	// chunk every lane tests one row, so a whole run of E rows in one column is consumed per step
 	int t = (int)T - 1, n = (int)N - 1;
 	int inM = 0;
@@ -925,10 +928,27 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 		__syncwarp();
 	}
 	// a complete path consumes every column: n == 0 and the first match sits at row 1
-	const uint32_t t_first = (uint32_t)t + 1;  // first path row
+	t_first_out = (uint32_t)t + 1;  // first path row
 	if (!((n == 0) && !inM)) return false;
 	__threadfence_block();
 	__syncwarp();
+	return true;
+}
+
+template <class CFG>
+DYN_DEV void segment_medians(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd);
+
+template <class CFG>
+DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
+	const ReadDesc& rd)
+{
+	constexpr int CPL = CFG::CPL;
+	constexpr int SLOTS = CFG::SLOTS;
+	typedef LaneRec<CPL> Rec;
+	const int lane = w.lane;
+	const uint32_t T = w.T;
+	uint32_t t_first = 0;
+	if (!trace_decisions<CFG>(w, sc, args, smem_raw, rd, t_first)) return false;
 
 	// phase 2: posterior of the path cell of every row, normalised by the row's recorded mass
 	const Rec* recs = static_cast<const Rec*>(sc.recs);
@@ -956,8 +976,17 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 	}
 	__threadfence_block();
 	__syncwarp();
+	segment_medians<CFG>(w, sc, args, rd);
+	return true;
+}
 
-	// phase 3: per-segment median of the path posteriors (NT:418-422, aligner.cpp:247-263), one segment at a time
+// phase 3 of pass 3: per-segment median of the path posteriors sc.pp (NT:418-422, aligner.cpp:247-263)
+template <class CFG>
+DYN_DEV void segment_medians(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd)
+{
+	const int lane = w.lane;
+	const uint32_t T = w.T, N = w.N;
+	const uint32_t* border = args.out_sigpos + rd.out_off;
 	double* prob = args.out_prob + rd.out_off;
 	const uint32_t Kc = N - 1;
 	uint32_t rs_ = border[0] + 1;
@@ -980,7 +1009,6 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 		if (lane == 0) prob[sgm] = (d & 1u) ? (double)up : ((double)dn + (double)up) / 2.0;
 		rs_ = re + 1;
 	}
-	return true;
 }
 
 // ------------------------------------------------------------------------------------------------------

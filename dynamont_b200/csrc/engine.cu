@@ -6,6 +6,7 @@
 // kernels; that build is test infrastructure and is never loaded by the product.)
 #include "../../include/dynamont_b200.h"
 #include "dp_kernels.cuh"
+#include "dp_linear.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -38,7 +39,7 @@ using namespace dyn;
 struct Rt
 {
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int device = 0;
 	int sms = 148;
 	size_t smem_optin = 0;
@@ -105,7 +106,7 @@ struct Rt
 	int device = 0;
 	int sms = 2;
 	size_t smem_optin = 227 * 1024;
-	double tm[4] = {0, 0, 0, 0};
+	double tm[6] = {0, 0, 0, 0, 0, 0};
 	void init(int) {}
 	void use_stream(void*) {}
 	void fini() {}
@@ -214,7 +215,7 @@ DYN_DEV void encode_read(const EncodeArgs& a, uint32_t r, int lane)
 	}
 }
 
-template <class CFG, int MODE>
+template <class CFG, int MODE, bool LIN>
 DYN_DEV void align_worker(const BatchArgs& args, unsigned char* smem_raw, int lane, unsigned slot)
 {
 	const SlotScratch sc = args.slots[slot];
@@ -236,7 +237,8 @@ DYN_DEV void align_worker(const BatchArgs& args, unsigned char* smem_raw, int la
 			}
 			continue;
 		}
-		align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
+		if (LIN) lin::align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
+		else align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
 		__syncwarp();
 	}
 }
@@ -276,11 +278,11 @@ __global__ void __launch_bounds__(32) k_encode(EncodeArgs a)
 {
 	for (uint32_t r = blockIdx.x; r < a.n_reads; r += gridDim.x) encode_read(a, r, threadIdx.x);
 }
-template <class CFG, int MODE, int MINB>
+template <class CFG, int MODE, int MINB, bool LIN>
 __global__ void __launch_bounds__(32, MINB) k_align(BatchArgs args)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	align_worker<CFG, MODE>(args, smem_raw, threadIdx.x, blockIdx.x);
+	align_worker<CFG, MODE, LIN>(args, smem_raw, threadIdx.x, blockIdx.x);
 }
 __global__ void __launch_bounds__(32) k_fold(FoldArgs a)
 {
@@ -301,29 +303,37 @@ void launch_encode(Rt& rt, const EncodeArgs& a)
 #endif
 }
 
-template <class CFG, int MINB>
-void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
+template <class CFG, int MINB, bool LIN>
+void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 {
 	const size_t smem = CFG::SMEM_BYTES;
 #ifndef DYN_HOST_EMU
 	static bool attr_set = false;
 	if (!attr_set)
 	{
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	if (mode == 0) k_align<CFG, 0, MINB><<<grid, 32, 0, rt.stream>>>(args);  // the backward pass alone needs no shared memory
-	else if (mode == 1) k_align<CFG, 1, MINB><<<grid, 32, smem, rt.stream>>>(args);
-	else k_align<CFG, 2, MINB><<<grid, 32, smem, rt.stream>>>(args);
+	if (mode == 0) k_align<CFG, 0, MINB, LIN><<<grid, 32, 0, rt.stream>>>(args);  // the backward pass alone needs no shared memory
+	else if (mode == 1) k_align<CFG, 1, MINB, LIN><<<grid, 32, smem, rt.stream>>>(args);
+	else k_align<CFG, 2, MINB, LIN><<<grid, 32, smem, rt.stream>>>(args);
 	CK_CUDA(cudaGetLastError());
 #else
 	(void)rt;
-	if (mode == 0) simt::launch(grid, smem, [&]() { align_worker<CFG, 0>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
-	else if (mode == 1) simt::launch(grid, smem, [&]() { align_worker<CFG, 1>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
-	else simt::launch(grid, smem, [&]() { align_worker<CFG, 2>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	if (mode == 0) simt::launch(grid, smem, [&]() { align_worker<CFG, 0, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else if (mode == 1) simt::launch(grid, smem, [&]() { align_worker<CFG, 1, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else simt::launch(grid, smem, [&]() { align_worker<CFG, 2, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 #endif
+}
+
+// lin: the linear-domain kernels (dp_linear.cuh); otherwise the log2-domain kernels (dp_kernels.cuh)
+template <class CFG, int MINB>
+void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode, bool lin)
+{
+	if (lin) launch_align_t<CFG, MINB, true>(rt, args, grid, mode);
+	else launch_align_t<CFG, MINB, false>(rt, args, grid, mode);
 }
 
 void launch_fold(Rt& rt, const FoldArgs& a)
@@ -389,6 +399,8 @@ struct dyn_aligner
 	// tuning
 	int warps_per_sm = 0;  // 0 = the variant's own occupancy
 	int variant = 3;  // measured fastest on B200
+	int arith = 0;    // 0: linear-domain kernels, reads with an FP32 range fault re-run in the log2 domain; 1: log2 domain only
+	uint64_t n_fallback = 0;  // reads of the last batch that were re-run in the log2 domain
 	double thr2 = -22.0;
 	double recs_per_row = 2.0;  // lane records per row (typical use: ~1.1)
 	double mem_fraction = 0.85;
@@ -694,6 +706,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	ba.m1 = (float)(A.trans[0] * LOG2E);
 	ba.e2 = (float)(A.trans[2] * LOG2E);
 	ba.thr2 = (float)A.thr2;
+	ba.m1_lin = (float)std::exp(A.trans[0]);
+	ba.e2_lin = (float)std::exp(A.trans[2]);
+	ba.thr_lin = (float)std::exp2(A.thr2);
 	ba.mode = mode;
 	ba.kmers = d_kmers;
 	if (mode == 2)
@@ -713,10 +728,35 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	}
 
 	// ---- K2..K5: the DP kernel ------------------------------------------------------------------------------------
+	const bool lin = (A.arith == 0);
+	A.n_fallback = 0;
 	rt.mark(2);
-	launch_align<CFG, MINB>(rt, ba, grid, mode);
+	launch_align<CFG, MINB>(rt, ba, grid, mode, lin);
 	rt.mark(3);
 	int launches = 2;
+	double fallback_ms = 0.0;
+	if (lin)
+	{
+		// reads the FP32 linear arithmetic could not represent (ST_LIN_FAULT) are re-run in the log2 domain
+		rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
+		rt.sync();
+		std::vector<uint32_t> again;
+		for (uint32_t r : order)
+			if (res.out[r].status == ST_LIN_FAULT) again.push_back(r);
+		if (!again.empty())
+		{
+			A.n_fallback = again.size();
+			rt.h2d(d_order, again.data(), again.size() * 4);
+			rt.zero(d_queue, 64);
+			ba.n_reads = (uint32_t)again.size();
+			rt.mark(4);
+			launch_align<CFG, MINB>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode, false);
+			rt.mark(5);
+			rt.sync();
+			fallback_ms = rt.elapsed(4, 5);
+			++launches;
+		}
+	}
 	if (mode == 2)
 	{
 		FoldArgs fa;
@@ -749,7 +789,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	}
 	rt.sync();
 	A.timing[0] = rt.elapsed(0, 1);
-	A.timing[1] = rt.elapsed(2, 3);
+	A.timing[1] = rt.elapsed(2, 3) + fallback_ms;
 	A.timing[2] = launches;
 	for (uint32_t r = 0; r < n; ++r)
 	{
@@ -1162,6 +1202,8 @@ const char* dyn_status_message(int status)
 
 const char* dyn_last_error(const dyn_aligner* A) { return A->last_error.c_str(); }
 
+uint64_t dyn_last_fallbacks(const dyn_aligner* A) { return A->n_fallback; }
+
 void dyn_last_timing(const dyn_aligner* A, double* out3)
 {
 	out3[0] = A->timing[0];
@@ -1185,6 +1227,7 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	std::lock_guard<std::mutex> g(A->mu);
 	const std::string k(key);
 	if (k == "warps_per_sm") A->warps_per_sm = std::max(0, (int)value);
+	else if (k == "arith") A->arith = std::min(1, std::max(0, (int)value));
 	else if (k == "variant") A->variant = std::min(N_VARIANTS - 1, std::max(0, (int)value));
 	else if (k == "thr2") A->thr2 = value;
 	else if (k == "recs_per_row") A->recs_per_row = value;

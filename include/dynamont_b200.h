@@ -123,6 +123,9 @@ const char* dyn_last_error(const dyn_aligner*);
 /* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
  * last batch call: [0] encode/emission-constant kernel, [1] main DP kernel, [2] number of kernel launches */
 void dyn_last_timing(const dyn_aligner*, double* out3);
+/* number of reads of the last batch call that the FP32 linear-domain kernels could not represent and that were
+ * re-run by the log2-domain kernels (same GPU); results are identical either way */
+uint64_t dyn_last_fallbacks(const dyn_aligner*);
 /* run all work of this handle on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
  * of the handle's own stream, so that the caller's CUDA events bracket it */
 int dyn_set_stream(dyn_aligner*, void* cuda_stream);

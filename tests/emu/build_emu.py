@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, "..", ".."))
 CSRC = os.path.join(ROOT, "dynamont_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libdynamont_emu.so")
-DEPS = [os.path.join(CSRC, f) for f in ("engine.cu", "dp_common.cuh", "dp_kernels.cuh")] + \
+DEPS = [os.path.join(CSRC, f) for f in ("engine.cu", "dp_common.cuh", "dp_kernels.cuh", "dp_linear.cuh")] + \
        [os.path.join(HERE, "simt_host.h"), os.path.join(ROOT, "include", "dynamont_b200.h")]
 
 

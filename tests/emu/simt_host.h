@@ -235,6 +235,11 @@ inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift)
 	shift &= 31;
 	return shift ? (hi << shift) | (lo >> (32 - shift)) : hi;
 }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
+{
+	shift &= 31;
+	return shift ? (lo >> shift) | (hi << (32 - shift)) : lo;
+}
 inline unsigned __float_as_uint(float f)
 {
 	unsigned u;
