@@ -21,10 +21,11 @@ def emu_lib():
     return build_emu.build()
 
 
-def _aligner(lib, case, variant=0, band=400):
+def _aligner(lib, case, variant=0, band=400, arith=0):
     from dynamont_b200 import Aligner
     al = Aligner(case.model_path, case.pore, band=band, _lib_path=lib)
     al.set_option("variant", variant)
+    al.set_option("arith", arith)  # 0: linear-domain kernels (+ log2-domain fallback), 1: log2-domain kernels only
     return al
 
 
@@ -34,6 +35,43 @@ def test_emulated_align_matches_reference(case, emu_lib):
     r = al.align(case.signal, case.sequence, True)
     check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
     assert al.align(case.signal, case.sequence, False)["Z"] == r["Z"]
+
+
+@pytest.mark.parametrize("case", [c for c in load_golden() if c.name in ("rna002_short", "rna002_dinuc")], ids=lambda c: c.name)
+def test_emulated_log2_domain_kernels(case, emu_lib):
+    """the log2-domain kernels (the fallback of the linear-domain path) on their own"""
+    al = _aligner(emu_lib, case, arith=1)
+    r = al.align(case.signal, case.sequence, True)
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    assert al.last_timing()["log2_fallback_reads"] == 0
+
+
+def test_emulated_range_fault_falls_back(emu_lib):
+    """Outlier samples that no kmer explains underflow FP32 probabilities: the linear-domain kernel must notice
+    (ST_LIN_FAULT) and the read must come back from the log2-domain kernels, identical to the oracle."""
+    from dynamont_b200.synth import native_model, synth_read
+    from oracle import Oracle
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    nm, ns = native_model(case.model_path, case.pore)
+    rng = np.random.default_rng(11)
+    s, q, _ = synth_read(rng, nm, ns, 5, 120, 9)
+    s[200] += 9.0
+    s[201] -= 8.0
+    s = s.astype(np.float32).astype(np.float64)
+    o = Oracle(case.model_path, case.pore).align(s, q, True)
+    al = _aligner(emu_lib, case)
+    clean = al.align(case.signal, case.sequence, True)
+    assert al.last_timing()["log2_fallback_reads"] == 0
+    check_alignment(clean, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    res = al.align_batch([case.signal, s], [case.sequence, q], True)
+    assert al.last_timing()["log2_fallback_reads"] == 1
+    check_alignment(res[0], case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    check_alignment(res[1], o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"], "spikes")
+    # training takes the same route and must not double-count the read's statistics
+    _, pooled_lin = al.train_batch([s], [q])
+    assert al.last_timing()["log2_fallback_reads"] == 1
+    _, pooled_log = _aligner(emu_lib, case, arith=1).train_batch([s], [q])
+    np.testing.assert_allclose(pooled_lin["w"], pooled_log["w"], rtol=1e-12)
 
 
 @pytest.mark.parametrize("variant", [1, 2])
@@ -77,6 +115,9 @@ def test_emulated_narrow_band_and_errors(emu_lib):
                 al.align(s, q, True)
             continue
         check_alignment(al.align(s, q, True), o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
+        # a band this narrow clips the alignment: forward and backward ridges separate by hundreds of bits, which the
+        # linear-domain kernel must detect (range guard) and hand to the log2-domain kernels
+        assert al.last_timing()["log2_fallback_reads"] == 1
     al = Aligner(path, "rna002", _lib_path=emu_lib)
     bad = [(np.zeros(0), "ACGTACGT", "Signal is empty"), (s[:50], "ACG", "Sequence shorter than model kmer size"),
            (s[:20], q[:40], "Signal too short compared to sequence"), (s, q[:30] + "N" + q[31:], "Invalid nucleotide: N")]

@@ -145,3 +145,49 @@ def test_band_cutoff_fails_like_reference(aligners, models_dir):
             check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
         except RuntimeError as e:
             assert isinstance(r, RuntimeError) and str(r) == str(e)
+
+
+def test_range_fault_reads_fall_back_to_log2_domain(aligners, models_dir):
+    """Reads the FP32 linear-domain kernels cannot represent (outlier samples no kmer explains; a band so narrow that
+    it clips the alignment) must be detected on the device and come back from the log2-domain kernels — identical to
+    the oracle either way, and clean reads of the same batch must not take the fallback."""
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import materialize_model
+    from oracle import Oracle
+    path = materialize_model("rna002_5mer", models_dir)
+    al = aligners(path, "rna002")
+    orc = Oracle(path, "rna002")
+    sigs, seqs = _synth_batch(path, "rna002", 12, 100, 400, 10, seed=77)
+    al.align_batch(sigs, seqs, True)
+    assert al.last_timing()["log2_fallback_reads"] == 0
+    rng = np.random.default_rng(5)
+    dirty = []
+    for i in (2, 5, 9):
+        s = sigs[i].copy()
+        pos = rng.integers(20, s.size - 20, size=3)
+        s[pos] += rng.choice([-1.0, 1.0], 3).astype(np.float32) * 9.0
+        sigs[i] = s
+        dirty.append(i)
+    res = al.align_batch(sigs, seqs, True)
+    assert al.last_timing()["log2_fallback_reads"] == len(dirty)
+    for s, q, r in zip(sigs, seqs, res):
+        o = orc.align(s.astype(np.float64), q, True)
+        check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
+    # both arithmetic paths agree on clean reads as well
+    al2 = Aligner(path, "rna002")
+    al2.set_option("arith", 1)
+    res2 = al2.align_batch(sigs, seqs, True)
+    for a, b in zip(res, res2):
+        assert np.array_equal(a["signal_positions"], b["signal_positions"])
+        assert np.abs(a["probabilities"] - b["probabilities"]).max() <= PROB_ATOL
+    # narrow band: the alignment hugs the band edge
+    aln = aligners(path, "rna002", band=10)
+    orn = Oracle(path, "rna002", band=10)
+    sigs, seqs = _synth_batch(path, "rna002", 4, 120, 200, 8, seed=3)
+    res = aln.align_batch(sigs, seqs, True)
+    for s, q, r in zip(sigs, seqs, res):
+        try:
+            o = orn.align(s.astype(np.float64), q, True)
+            check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
+        except RuntimeError as e:
+            assert isinstance(r, RuntimeError) and str(r) == str(e)
