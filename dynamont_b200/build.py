@@ -39,7 +39,7 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + os.environ.get("DYN_NVCC_EXTRA", "").split() + ["-o", LIB] + SOURCES
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + SOURCES
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(CSRC, "build.log"), "w") as fh:

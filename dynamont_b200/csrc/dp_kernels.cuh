@@ -61,8 +61,6 @@ struct BatchArgs
 	uint32_t* queue;            // atomic work counter
 	const float* signal;
 	const PosConst* pc;
-	const float* pc_soa;        // the same constants as three arrays a[pc_total], b[pc_total], c[pc_total] (linear-domain kernels)
-	uint64_t pc_total;
 	const SlotScratch* slots;   // [gridDim.x]
 	uint64_t rec_cap;           // sparse records per slot
 	ReadOut* out;               // [n_reads]

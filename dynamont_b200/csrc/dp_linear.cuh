@@ -72,109 +72,12 @@ DYN_DEV float max3f(float a, float b, float c)
 #endif
 }
 
-DYN_DEV float2 f2(float a, float b) { return make_float2(a, b); }
-
-// ------------------------------------------------------------------------------------------------------
-// register / memory layouts of the linear-domain kernels
-// ------------------------------------------------------------------------------------------------------
-// A lane's CPL cells are handled as NP = CPL/2 pairs (slots 2i, 2i+1) plus one single cell when CPL is odd: the packed
-// FP32 instructions of sm_100 (FFMA2 / FMUL2 / FADD2, two IEEE operations per issue slot) work on aligned register
-// pairs, so everything that feeds them is loaded / stored pair-wise:
-//   * emission constants come from structure-of-arrays copies (BatchArgs::pc_soa: a[], b[], c[] per column) with
-//     scalar loads straight into the pair registers (a 16-byte {a,b,c,pad} load would pin the wrong grouping);
-//   * shared-memory rows of the recomputed backward values: float2 [NP][32] (pair i, lane) then float [32] (single);
-//   * checkpoints: 32 floats (128 B) per lane: bM pairs | bE pairs | bM, bE of the single cell | OB — 8-byte
-//     stores in pass 1, 8-byte loads (after an L2 prefetch one block ahead) in pass 2;
-//   * sparse posterior records (LaneRec): PM pairs | PE pairs | PM, PE of the single cell | lane id.
-template <class CFG>
-struct Lay
-{
-	static constexpr int CPL = CFG::CPL;
-	static constexpr int NP = CPL / 2;
-	static constexpr int NPS = (CPL + 1) / 2;
-	static constexpr bool ODD = (CPL & 1) != 0;
-	static constexpr int ROWF = CPL * 32;                         // floats per shared-memory row: NP x [32] float2, then [32] float
-	static constexpr int CKPT_FLOATS = 32 * 32;                   // floats per checkpoint in HBM
-	static constexpr size_t OB_BYTES = 2 * 32 * 4;
-	static constexpr size_t ROWS_BYTES = (size_t)(CFG::CK + 2) * ROWF * 4;  // bE(t_lo) .. bE(t_lo+CK) and one row of match posteriors
-	static constexpr size_t SMEM_BYTES = OB_BYTES + ROWS_BYTES;
-	// record float index of the match / extend posterior of slot j
-	DYN_HD static int rec_m(int j) { return (ODD && j == CPL - 1) ? 4 * NP : j; }
-	DYN_HD static int rec_e(int j) { return (ODD && j == CPL - 1) ? 4 * NP + 1 : 2 * NP + j; }
-	static constexpr int REC_LANE = 4 * NP + 2;
-	static constexpr int REC_VALUES = 4 * NP + 2;                 // floats that hold posteriors
-	static_assert(CFG::RN == CFG::CK, "the linear-domain kernels renormalise once per checkpoint block");
-	static_assert(REC_LANE < LaneRec<CPL>::NF, "record too small");
-};
-
-DYN_DEV void prefetch_l2(const void* p)
-{
-#ifndef DYN_HOST_EMU
-	asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-	(void)p;
-#endif
-}
-
-// ---- emission constants from the structure-of-arrays copy --------------------------------------------------
-template <class CFG>
-struct Soa
-{
-	const float* a;
-	const float* b;
-	const float* c;
-};
-
-template <class CFG>
-DYN_DEV void activate(Warp<CFG>& w, const Soa<CFG>& so, int n)
-{
-	if (!w.valid_col(n)) return;
-	with_slot<CFG::CPL>(w.lane, pmod(n, CFG::SLOTS), SetEmis<CFG::CPL>{w.em, so.a[n], so.b[n], so.c[n]});
-}
-
-template <class CFG>
-DYN_DEV void load_window(Warp<CFG>& w, const Soa<CFG>& so, int mid)
-{
-	constexpr int CPL = CFG::CPL;
-	const int n0 = mid - w.bw;
-	const int nlast = min(mid + w.bw, (int)w.N - 1);
-#pragma unroll
-	for (int j = 0; j < CPL; ++j)
-	{
-		const int n = w.col_of_slot(w.lane * CPL + j, n0);
-		const bool in = (n >= 0 && n <= nlast);
-		w.em.a[j] = in ? so.a[n] : 0.0f;
-		w.em.b[j] = in ? so.b[n] : 0.0f;
-		w.em.c[j] = in ? so.c[n] : CNEG;
-	}
-}
-
-template <class CFG>
-DYN_DEV void slide_window_up(Warp<CFG>& w, const Soa<CFG>& so, int mid_from, int mid_to)
-{
-#pragma unroll 1
-	for (int m = mid_from + 1; m <= mid_to; ++m)
-	{
-		w.deactivate(m - 1 - w.bw);
-		activate<CFG>(w, so, m + w.bw);
-	}
-}
-
 // emission probability of the lane's CPL cells for sample x (inactive slots: c = CNEG -> 0)
 template <class CFG>
 DYN_DEV void emis_lin(const Warp<CFG>& w, float x, float (&p)[CFG::CPL])
 {
-	constexpr int CPL = CFG::CPL;
-	const float2 xx = f2(x, x);
 #pragma unroll
-	for (int j = 0; j + 1 < CPL; j += 2)
-	{
-		const float2 z = __ffma2_rn(xx, f2(w.em.a[j], w.em.a[j + 1]), f2(-w.em.b[j], -w.em.b[j + 1]));
-		const float2 q = __ffma2_rn(f2(-z.x, -z.y), z, f2(w.em.c[j], w.em.c[j + 1]));
-		p[j] = ex2(q.x);
-		p[j + 1] = ex2(q.y);
-	}
-	if (CPL & 1) p[CPL - 1] = ex2(emis2(x, w.em.a[CPL - 1], w.em.b[CPL - 1], w.em.c[CPL - 1]));
+	for (int j = 0; j < CFG::CPL; ++j) p[j] = ex2(emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]));
 }
 
 // New integer offset of this lane after a renormalisation.
@@ -220,59 +123,23 @@ DYN_DEV void bwd_row(Warp<CFG>& w, BwdL<CFG::CPL>& b, float x, float m1, float e
 {
 	constexpr int CPL = CFG::CPL;
 	float p[CPL], A[CPL];
-	const float2 xx = f2(x, x), mm = f2(m1, m1);
-	// A[n] = bM[t+1][n] * p(t,n) * m1 is consumed by column n-1.  Slots 0/1 go first: A[0] is what the left lane
-	// needs, and the shuffle that carries it has the rest of the row to complete.
-	{
-		const float2 z = __ffma2_rn(xx, f2(w.em.a[0], w.em.a[1]), f2(-w.em.b[0], -w.em.b[1]));
-		const float2 q = __ffma2_rn(f2(-z.x, -z.y), z, f2(w.em.c[0], w.em.c[1]));
-		p[0] = ex2(q.x);
-		p[1] = ex2(q.y);
-		const float2 a2 = __fmul2_rn(f2(b.bM[0], b.bM[1]), __fmul2_rn(f2(p[0], p[1]), mm));
-		A[0] = a2.x;
-		A[1] = a2.y;
-	}
-	const float Araw = __shfl_sync(FULL, A[0], (w.lane + 1) & 31);
+	emis_lin<CFG>(w, x, p);
 #pragma unroll
-	for (int j = 2; j + 1 < CPL; j += 2)
-	{
-		const float2 z = __ffma2_rn(xx, f2(w.em.a[j], w.em.a[j + 1]), f2(-w.em.b[j], -w.em.b[j + 1]));
-		const float2 q = __ffma2_rn(f2(-z.x, -z.y), z, f2(w.em.c[j], w.em.c[j + 1]));
-		p[j] = ex2(q.x);
-		p[j + 1] = ex2(q.y);
-	}
-	if (CPL & 1) p[CPL - 1] = ex2(emis2(x, w.em.a[CPL - 1], w.em.b[CPL - 1], w.em.c[CPL - 1]));
+	for (int j = 0; j < CPL; ++j) A[j] = b.bM[j] * (p[j] * m1);  // bM[t+1][n] * p(t,n) * m1, consumed by column n-1
+	const float Ar = (__shfl_sync(FULL, A[0], (w.lane + 1) & 31) * b.sR1) * b.sR2;
 #pragma unroll
-	for (int j = 2; j + 1 < CPL; j += 2)
+	for (int j = 0; j < CPL; ++j)
 	{
-		const float2 a2 = __fmul2_rn(f2(b.bM[j], b.bM[j + 1]), __fmul2_rn(f2(p[j], p[j + 1]), mm));
-		A[j] = a2.x;
-		A[j + 1] = a2.y;
+		const float ext1 = (j + 1 < CPL) ? A[j + 1] : Ar;
+		const float nm = b.bE[j] * p[j];   // bM[t][n] = bE[t+1][n] * p            (NT:200)
+		b.bE[j] = fmaf(nm, e2, ext1);      //                                      (NT:194,201,204)
+		b.bM[j] = nm;
 	}
-	if (CPL & 1) A[CPL - 1] = b.bM[CPL - 1] * (p[CPL - 1] * m1);
-	float nml = 0.0f;  // bM of the last slot, whose bE waits for the neighbour's A
-#pragma unroll
-	for (int j = 0; j + 1 < CPL; j += 2)
-	{
-		const float2 nm = __fmul2_rn(f2(b.bE[j], b.bE[j + 1]), f2(p[j], p[j + 1]));  // bM[t][n] = bE[t+1][n] * p  (NT:200)
-		b.bE[j] = fmaf(nm.x, e2, A[j + 1]);                                           //               (NT:194,201,204)
-		if (j + 2 < CPL) b.bE[j + 1] = fmaf(nm.y, e2, A[j + 2]);
-		else nml = nm.y;
-		b.bM[j] = nm.x;
-		b.bM[j + 1] = nm.y;
-	}
-	if (CPL & 1)
-	{
-		nml = b.bE[CPL - 1] * p[CPL - 1];
-		b.bM[CPL - 1] = nml;
-	}
-	const float Ar = (Araw * b.sR1) * b.sR2;
-	b.bE[CPL - 1] = fmaf(nml, e2, Ar);
 }
 
-// lane-local renormalisation by an exact power of two
+// lane-local renormalisation by an exact power of two; returns the exponent increment (new OB - old OB)
 template <class CFG>
-DYN_DEV void bwd_renorm(Warp<CFG>& w, BwdL<CFG::CPL>& b)
+DYN_DEV int bwd_renorm(Warp<CFG>& w, BwdL<CFG::CPL>& b)
 {
 	constexpr int CPL = CFG::CPL;
 	float lm = b.bE[0];
@@ -280,29 +147,22 @@ DYN_DEV void bwd_renorm(Warp<CFG>& w, BwdL<CFG::CPL>& b)
 	for (int j = 1; j + 1 < CPL; j += 2) lm = max3f(lm, b.bE[j], b.bE[j + 1]);
 	if ((CPL & 1) == 0) lm = fmaxf(lm, b.bE[CPL - 1]);
 	const int nO = renorm_offset<+1>(lm, b.OB, 0, w.lane);
-	const float sc = pow2i(b.OB - nO);
-	const float2 ss = f2(sc, sc);
+	const int inc = nO - b.OB;
+	const float sc = pow2i(-inc);
 #pragma unroll
-	for (int j = 0; j + 1 < CPL; j += 2)
+	for (int j = 0; j < CPL; ++j)
 	{
-		const float2 m = __fmul2_rn(f2(b.bM[j], b.bM[j + 1]), ss), e = __fmul2_rn(f2(b.bE[j], b.bE[j + 1]), ss);
-		b.bM[j] = m.x;
-		b.bM[j + 1] = m.y;
-		b.bE[j] = e.x;
-		b.bE[j + 1] = e.y;
-	}
-	if (CPL & 1)
-	{
-		b.bM[CPL - 1] *= sc;
-		b.bE[CPL - 1] *= sc;
+		b.bM[j] *= sc;
+		b.bE[j] *= sc;
 	}
 	b.OB = nO;
 	const int obr = __shfl_sync(FULL, nO, (w.lane + 1) & 31);
 	pow2_split(obr - nO, b.sR1, b.sR2);
+	return inc;
 }
 
 template <class CFG>
-DYN_DEV void bwd_step(Warp<CFG>& w, const Soa<CFG>& so, BwdL<CFG::CPL>& b, float x, bool slide, int& mid, float m1, float e2)
+DYN_DEV void bwd_step(Warp<CFG>& w, BwdL<CFG::CPL>& b, float x, bool slide, int& mid, float m1, float e2)
 {
 	constexpr int CPL = CFG::CPL;
 	if (slide)
@@ -310,7 +170,10 @@ DYN_DEV void bwd_step(Warp<CFG>& w, const Soa<CFG>& so, BwdL<CFG::CPL>& b, float
 		// see dp_kernels.cuh bwd_step: the column entering the band carried the ungated M-transition term
 		const int nb = mid - 1 - w.bw;
 		if (nb >= 0)
-			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetEmisState<CPL>{w.em, so.a[nb], so.b[nb], so.c[nb], b.bM, b.bE, 0.0f});
+		{
+			const PosConst v = w.pc[nb];
+			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetEmisState<CPL>{w.em, v.a, v.b, v.c, b.bM, b.bE, 0.0f});
+		}
 	}
 	bwd_row<CFG>(w, b, x, m1, e2);
 	if (slide)
@@ -339,68 +202,45 @@ DYN_DEV void bwd_init_terminal(Warp<CFG>& w, BwdL<CFG::CPL>& b)
 	pow2_split(obr - b.OB, b.sR1, b.sR2);
 }
 
-// checkpoint = 128 bytes per lane: bM pairs | bE pairs | bM, bE of the single cell | OB
+// checkpoints share the log-domain layout: [2*CPL][32] floats + one 8-byte word per lane (here: the int offset)
 template <class CFG>
 DYN_DEV void ckpt_store(const SlotScratch& sc, uint32_t idx, int lane, const BwdL<CFG::CPL>& b)
 {
-	typedef Lay<CFG> L;
-	float2* f = reinterpret_cast<float2*>(sc.ckpt + (size_t)idx * L::CKPT_FLOATS + lane * 32);
+	constexpr int CPL = CFG::CPL;
+	float* f = sc.ckpt + (size_t)idx * CFG::CKF;
 #pragma unroll
-	for (int i = 0; i < L::NP; ++i)
+	for (int j = 0; j < CPL; ++j)
 	{
-		f[i] = f2(b.bM[2 * i], b.bM[2 * i + 1]);
-		f[L::NP + i] = f2(b.bE[2 * i], b.bE[2 * i + 1]);
+		f[j * 32 + lane] = b.bM[j];
+		f[(CPL + j) * 32 + lane] = b.bE[j];
 	}
-	f[2 * L::NP] = L::ODD ? f2(b.bM[L::CPL - 1], b.bE[L::CPL - 1]) : f2(0.0f, 0.0f);
-	f[2 * L::NP + 1] = f2(__int_as_float(b.OB), 0.0f);
-}
-
-// from a 128-byte per-lane image (HBM or the staged copy in shared memory)
-template <class CFG>
-DYN_DEV void ckpt_unpack(const float2* f, int lane, BwdL<CFG::CPL>& b)
-{
-	typedef Lay<CFG> L;
-#pragma unroll
-	for (int i = 0; i < L::NP; ++i)
-	{
-		const float2 m = f[i], e = f[L::NP + i];
-		b.bM[2 * i] = m.x;
-		b.bM[2 * i + 1] = m.y;
-		b.bE[2 * i] = e.x;
-		b.bE[2 * i + 1] = e.y;
-	}
-	const float2 s = f[2 * L::NP], o = f[2 * L::NP + 1];
-	if (L::ODD)
-	{
-		b.bM[L::CPL - 1] = s.x;
-		b.bE[L::CPL - 1] = s.y;
-	}
-	b.OB = __float_as_int(o.x);
-	const int obr = __shfl_sync(FULL, b.OB, (lane + 1) & 31);
-	pow2_split(obr - b.OB, b.sR1, b.sR2);
+	reinterpret_cast<int*>(sc.ckpt_ob)[(size_t)idx * 64 + lane] = b.OB;
 }
 
 template <class CFG>
 DYN_DEV void ckpt_load(const SlotScratch& sc, uint32_t idx, int lane, BwdL<CFG::CPL>& b)
 {
-	ckpt_unpack<CFG>(reinterpret_cast<const float2*>(sc.ckpt + (size_t)idx * Lay<CFG>::CKPT_FLOATS + lane * 32), lane, b);
-}
-
-// pull this lane's 128 bytes of checkpoint idx into L2 ahead of use
-template <class CFG>
-DYN_DEV void ckpt_prefetch(const SlotScratch& sc, uint32_t idx, int lane)
-{
-	prefetch_l2(sc.ckpt + (size_t)idx * Lay<CFG>::CKPT_FLOATS + lane * 32);
+	constexpr int CPL = CFG::CPL;
+	const float* f = sc.ckpt + (size_t)idx * CFG::CKF;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		b.bM[j] = f[j * 32 + lane];
+		b.bE[j] = f[(CPL + j) * 32 + lane];
+	}
+	b.OB = reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)idx * 64 + lane];
+	const int obr = __shfl_sync(FULL, b.OB, (lane + 1) & 31);
+	pow2_split(obr - b.OB, b.sR1, b.sR2);
 }
 
 // pass 1: backward over the whole read.  Returns log2 Zb (double) in every lane (NaN/-inf on a range fault).
 template <class CFG, bool STORE>
-DYN_DEV double backward_pass(Warp<CFG>& w, const Soa<CFG>& so, const SlotScratch& sc, float m1, float e2)
+DYN_DEV double backward_pass(Warp<CFG>& w, const SlotScratch& sc, float m1, float e2)
 {
 	constexpr int CPL = CFG::CPL;
 	BwdL<CPL> b;
 	int mid = (int)band_mid(w.T - 1, w.ratio);
-	load_window<CFG>(w, so, mid);
+	w.load_window(mid);
 	bwd_init_terminal<CFG>(w, b);
 	if (STORE && ((w.T - 1) & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, (w.T - 1) / CFG::CK, w.lane, b);
 
@@ -417,12 +257,12 @@ DYN_DEV double backward_pass(Warp<CFG>& w, const Soa<CFG>& so, const SlotScratch
 		{
 			const uint32_t tt = base + i;
 			const float xn = __shfl_sync(FULL, cur.xv, (i - 1) & 31);
-			bwd_step<CFG>(w, so, b, x, (cur.smask >> i) & 1u, mid, m1, e2);
+			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid, m1, e2);
 			x = xn;
-			if ((tt & (CFG::CK - 1)) == 0)
+			if ((tt & (CFG::RN - 1)) == 0)
 			{
 				bwd_renorm<CFG>(w, b);
-				if (STORE) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
+				if (STORE && (tt & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
 			}
 		}
 		t = (int)base - 1;
@@ -457,32 +297,14 @@ DYN_DEV float kappa(int OF, int OB, int Z2i, float c0)
 template <class CFG>
 struct SmemL
 {
-	int* OB;      // [2][32]  backward lane offsets: [0] in force for row t_lo, [1] for rows t_lo+1 .. t_lo+CK
-	float* rows;  // [(CK+1)][ROWF]  recomputed backward rows bE(t_lo) .. bE(t_lo+CK); row t is overwritten with the
-	              //                 extend posteriors of row t once it has been consumed
-	float* pmrow; // [ROWF]          match posteriors of the current row
+	float* bE;  // [(CK+1)][CPL][32]
+	int* OB;    // [NRN][32]  backward lane offsets in force for the rows up to and including t_lo + i*RN
 	DYN_DEV explicit SmemL(unsigned char* p)
 	{
 		OB = reinterpret_cast<int*>(p);
-		rows = reinterpret_cast<float*>(p + Lay<CFG>::OB_BYTES);
-		pmrow = rows + (size_t)(CFG::CK + 1) * Lay<CFG>::ROWF;
+		bE = reinterpret_cast<float*>(p + (size_t)CFG::NRN * 32 * 8);
 	}
 };
-
-// a lane's pair i / single cell inside a shared-memory row
-template <class CFG>
-DYN_DEV float2* row_pair(float* row, int i, int lane) { return reinterpret_cast<float2*>(row) + i * 32 + lane; }
-template <class CFG>
-DYN_DEV float* row_single(float* row, int lane) { return row + Lay<CFG>::NP * 64 + lane; }
-
-template <class CFG>
-DYN_DEV void row_store(float* dst, int lane, const BwdL<CFG::CPL>& b)
-{
-	typedef Lay<CFG> L;
-#pragma unroll
-	for (int i = 0; i < L::NP; ++i) *row_pair<CFG>(dst, i, lane) = f2(b.bE[2 * i], b.bE[2 * i + 1]);
-	if (L::ODD) *row_single<CFG>(dst, lane) = b.bE[L::CPL - 1];
-}
 
 // lane-local renormalisation of the forward values (own maximum -> [1, 2), coupled to the left lane) and the range
 // guard.  brow: this lane's backward values of (about) the same row; OB: their offset.
@@ -504,20 +326,11 @@ DYN_DEV void fwd_renorm(Warp<CFG>& w, FwdL<CFG::CPL>& f, const float (&brow)[CFG
 	}
 	const int nO = renorm_offset<-1>(lm, f.OF, 0, w.lane);
 	const float sc = pow2i(f.OF - nO);
-	const float2 ss = f2(sc, sc);
 #pragma unroll
-	for (int j = 0; j + 1 < CPL; j += 2)
+	for (int j = 0; j < CPL; ++j)
 	{
-		const float2 m = __fmul2_rn(f2(f.fM[j], f.fM[j + 1]), ss), e = __fmul2_rn(f2(f.fE[j], f.fE[j + 1]), ss);
-		f.fM[j] = m.x;
-		f.fM[j + 1] = m.y;
-		f.fE[j] = e.x;
-		f.fE[j + 1] = e.y;
-	}
-	if (CPL & 1)
-	{
-		f.fM[CPL - 1] *= sc;
-		f.fE[CPL - 1] *= sc;
+		f.fM[j] *= sc;
+		f.fE[j] *= sc;
 	}
 	f.OF = nO;
 	const int ofl = __shfl_sync(FULL, nO, (w.lane + 31) & 31);
@@ -533,160 +346,59 @@ DYN_DEV void vit_renorm(Warp<CFG>& w, FwdL<CFG::CPL>& f)
 #pragma unroll
 	for (int j = 0; j < CPL; ++j) lm = max3f(lm, f.VM[j], f.VE[j]);
 	const int nO = renorm_offset<-1>(lm, f.OV, E0V, w.lane);
-	const float sc = pow2i(f.OV - nO);
-	const float2 ss = f2(sc, sc);
+	const int inc = nO - f.OV;
+	const float sc = pow2i(-inc);
 #pragma unroll
-	for (int j = 0; j + 1 < CPL; j += 2)
+	for (int j = 0; j < CPL; ++j)
 	{
-		const float2 m = __fmul2_rn(f2(f.VM[j], f.VM[j + 1]), ss), e = __fmul2_rn(f2(f.VE[j], f.VE[j + 1]), ss);
-		f.VM[j] = m.x;
-		f.VM[j + 1] = m.y;
-		f.VE[j] = e.x;
-		f.VE[j + 1] = e.y;
-	}
-	if (CPL & 1)
-	{
-		f.VM[CPL - 1] *= sc;
-		f.VE[CPL - 1] *= sc;
+		f.VM[j] *= sc;
+		f.VE[j] *= sc;
 	}
 	f.OV = nO;
 	const int ovl = __shfl_sync(FULL, nO, (w.lane + 31) & 31);
 	pow2_split(ovl - nO, f.sV1, f.sV2);
 }
 
-// Range guard at a block boundary (see the header comment): brow = this lane's backward values of the boundary row.
-template <class CFG>
-DYN_DEV void fwd_renorm_block(Warp<CFG>& w, FwdL<CFG::CPL>& f, float* brow, int OB, int Z2i, float c0)
-{
-	constexpr int CPL = CFG::CPL;
-	typedef Lay<CFG> L;
-	float bv[CPL];
-#pragma unroll
-	for (int i = 0; i < L::NP; ++i)
-	{
-		const float2 q = *row_pair<CFG>(brow, i, w.lane);
-		bv[2 * i] = q.x;
-		bv[2 * i + 1] = q.y;
-	}
-	if (L::ODD) bv[CPL - 1] = *row_single<CFG>(brow, w.lane);
-	fwd_renorm<CFG>(w, f, bv, OB, Z2i, c0);
-}
-
-// One row of pass 2, fused per pair of cells so that nothing row-sized lives in registers except the state itself
-// (f, V, the emission constants): for every pair, from the highest slot down (the left neighbours fE[j-1] / VE[j-1]
-// must still hold row t / row t-1 when slot j is updated):
-//     emission p(t,.)  ->  posteriors PE = fE * bE(t) * kapE, PM = fM * (bE(t+1) * p) * kapM   (NT:200,213-224)
-//     ->  posterior-Viterbi max-product update + decision bits (NT:357-362, test of NT:448)
-//     ->  forward recurrence to row t+1 (NT:141-150).
-// On entry f holds the forward values of row t and the Viterbi values of row t-1.  The backward values come straight
-// from shared memory (rowc = bE(t), rown = bE(t+1)); the posteriors are parked there too (PE over bE(t), which is
-// dead by then, PM in pmrow) for the few lanes that have to write a sparse record.
-//   DO_V: posteriors / Viterbi / bits / records    DO_STEP: forward step incl. the band slide between t and t+1
-// kapE / kapM: posterior factors of the extend and the match state of row t (they differ on the first row of a block:
-// bM[t] = bE[t+1] * p is formed in the offsets of row t+1).
+// One row of pass 2 (see dp_kernels.cuh fwd_row for the contract).  kapE / kapM: posterior factors of the extend and
+// the match state of row t (they differ on a renormalisation row: bM[t] = bE[t+1] * p is formed in the offsets of
+// row t+1).
 template <class CFG, bool DO_V, bool DO_STEP>
-DYN_DEV void fwd_row(Warp<CFG>& w, const Soa<CFG>& so, FwdL<CFG::CPL>& f, const SlotScratch& sc, RecSink& rs, float thr,
-	uint32_t t, float x, bool slide, int& mid_f, float* rowc, float* rown, float* pmrow, float kapE, float kapM,
+DYN_DEV void fwd_row(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, RecSink& rs, float thr, uint32_t t, float x,
+	bool slide, int& mid_f, float (&bc)[CFG::CPL], float (&bn)[CFG::CPL], const float* pf, float kapE, float kapM,
 	float m1, float e2)
 {
 	constexpr int CPL = CFG::CPL;
-	typedef Lay<CFG> L;
 	const int lane = w.lane;
-	// the values the right lane needs are those of the previous row: send them first, consume them last
-	const float vlraw = DO_V ? __shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31) : 0.0f;
-	const float flraw = DO_STEP ? __shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) : 0.0f;
-	if (DO_STEP && slide)
-	{
-		activate<CFG>(w, so, mid_f + 1 + w.bw);  // column entering band(t+1)
-		// column lo_t leaves the band at row t+1: bE[t+1][lo_t] is out of band (0 in the reference) and with it
-		// bM[t][lo_t]; the recomputed row holds the ungated neighbour term there (see dp_kernels.cuh bwd_step)
-		const int nold = mid_f - w.bw;
-		if (DO_V && nold >= 0)
-		{
-			const int q = pmod(nold, CFG::SLOTS);
-			const int ql = q / CPL, j = q - ql * CPL;
-			if (lane == ql)
-			{
-				if (L::ODD && j == CPL - 1) *row_single<CFG>(rown, lane) = 0.0f;
-				else reinterpret_cast<float*>(row_pair<CFG>(rown, j >> 1, lane))[j & 1] = 0.0f;
-			}
-		}
-	}
-	const float2 xx = f2(x, x), kE = f2(kapE, kapE), kM = f2(kapM, kapM), ee = f2(e2, e2), mm = f2(m1, m1);
-	const float vl = (vlraw * f.sV1) * f.sV2;
-	const float fl = (flraw * f.sL1) * f.sL2;
-	unsigned acc = 0;
-	float lmax = 0.0f;
-	if (L::ODD)
-	{
-		const int j = CPL - 1;
-		float pj = 0.0f;
-		if (DO_STEP) pj = ex2(emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]));
-		if (DO_V)
-		{
-			const float pe = f.fE[j] * (*row_single<CFG>(rowc, lane) * kapE);
-			const float pm = DO_STEP ? f.fM[j] * ((*row_single<CFG>(rown, lane) * pj) * kapM) : 0.0f;
-			const float vmx = fmaxf(f.VM[j], f.VE[j]);
-			acc = __funnelshift_l(__float_as_uint(f.VM[j] - f.VE[j]), acc, 1);
-			f.VM[j] = f.VE[j - 1] * pm;
-			f.VE[j] = vmx * pe;
-			lmax = max3f(lmax, pm, pe);
-			*row_single<CFG>(rowc, lane) = pe;
-			*row_single<CFG>(pmrow, lane) = pm;
-		}
-		if (DO_STEP)
-		{
-			const float ne = fmaf(f.fE[j], e2, f.fM[j]) * pj;  // (fM + fE*e2) * p    (NT:146-150, e1 = 1)
-			f.fM[j] = f.fE[j - 1] * (pj * m1);                 // fE[t][n-1] * p * m1  (NT:143)
-			f.fE[j] = ne;
-		}
-	}
-#pragma unroll
-	for (int j = (CPL & ~1) - 2; j >= 0; j -= 2)
-	{
-		float2 pp = f2(0.0f, 0.0f);
-		if (DO_STEP)
-		{
-			const float2 z = __ffma2_rn(xx, f2(w.em.a[j], w.em.a[j + 1]), f2(-w.em.b[j], -w.em.b[j + 1]));
-			const float2 q = __ffma2_rn(f2(-z.x, -z.y), z, f2(w.em.c[j], w.em.c[j + 1]));
-			pp = f2(ex2(q.x), ex2(q.y));
-		}
-		if (DO_V)
-		{
-			const float2 bc2 = *row_pair<CFG>(rowc, j >> 1, lane);
-			const float2 pe = __fmul2_rn(f2(f.fE[j], f.fE[j + 1]), __fmul2_rn(bc2, kE));
-			float2 pm = f2(0.0f, 0.0f);  // the last row has no match state
-			if (DO_STEP)
-			{
-				const float2 bn2 = *row_pair<CFG>(rown, j >> 1, lane);
-				pm = __fmul2_rn(f2(f.fM[j], f.fM[j + 1]), __fmul2_rn(__fmul2_rn(bn2, pp), kM));  // bM[t] = bE[t+1] * p  (NT:200)
-			}
-			const float2 vmx = f2(fmaxf(f.VM[j], f.VE[j]), fmaxf(f.VM[j + 1], f.VE[j + 1]));
-			const float2 d = __fadd2_rn(f2(f.VM[j], f.VM[j + 1]), f2(-f.VE[j], -f.VE[j + 1]));
-			acc = __funnelshift_l(__float_as_uint(d.y), acc, 1);
-			acc = __funnelshift_l(__float_as_uint(d.x), acc, 1);
-			f.VM[j + 1] = f.VE[j] * pm.y;
-			f.VM[j] = ((j > 0) ? f.VE[j - 1] : vl) * pm.x;
-			const float2 ve = __fmul2_rn(vmx, pe);
-			f.VE[j] = ve.x;
-			f.VE[j + 1] = ve.y;
-			lmax = max3f(lmax, pm.x, pe.x);
-			lmax = max3f(lmax, pm.y, pe.y);
-			*row_pair<CFG>(rowc, j >> 1, lane) = pe;
-			*row_pair<CFG>(pmrow, j >> 1, lane) = pm;
-		}
-		if (DO_STEP)
-		{
-			const float2 ne = __fmul2_rn(__ffma2_rn(f2(f.fE[j], f.fE[j + 1]), ee, f2(f.fM[j], f.fM[j + 1])), pp);
-			const float2 pm1 = __fmul2_rn(pp, mm);
-			f.fM[j + 1] = f.fE[j] * pm1.y;
-			f.fM[j] = ((j > 0) ? f.fE[j - 1] : fl) * pm1.x;
-			f.fE[j] = ne.x;
-			f.fE[j + 1] = ne.y;
-		}
-	}
+	if (DO_STEP && slide) w.activate(mid_f + 1 + w.bw);  // column entering band(t+1)
+
+	float p[CPL], PM[CPL], PE[CPL];
+	if (DO_STEP) emis_lin<CFG>(w, x, p);
 	if (DO_V)
 	{
+#pragma unroll
+		for (int j = 0; j < CPL; ++j)
+		{
+			PE[j] = f.fE[j] * (bc[j] * kapE);
+			// bM[t][n] = bE[t+1][n] * p(t,n) (NT:200); the last row has no match state
+			PM[j] = DO_STEP ? f.fM[j] * ((bn[j] * p[j]) * kapM) : 0.0f;
+		}
+		if (DO_STEP && slide && mid_f - w.bw >= 0)
+			with_slot<CPL>(lane, pmod(mid_f - w.bw, CFG::SLOTS), SetOne<CPL>{PM, 0.0f});  // see dp_kernels.cuh fwd_row
+		// posterior-Viterbi fill (NT:357-362) as a max-product, in place from the highest slot down;
+		// decision bit = sign(VM - VE): set <=> the E state of this cell is entered from E (test of NT:448)
+		const float vl = (__shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31) * f.sV1) * f.sV2;
+		unsigned acc = 0;
+		float lmax = 0.0f;
+#pragma unroll
+		for (int j = CPL - 1; j >= 0; --j)
+		{
+			const float vmx = fmaxf(f.VM[j], f.VE[j]);
+			acc = __funnelshift_l(__float_as_uint(f.VM[j] - f.VE[j]), acc, 1);
+			const float left = (j > 0) ? f.VE[j - 1] : vl;
+			f.VM[j] = left * PM[j];
+			f.VE[j] = vmx * PE[j];
+			lmax = max3f(lmax, PM[j], PE[j]);
+		}
 		if ((t & (CFG::RV - 1)) == 0) vit_renorm<CFG>(w, f);
 		sc.bits[(size_t)t * 32 + lane] = (uint16_t)acc;
 
@@ -699,16 +411,20 @@ DYN_DEV void fwd_row(Warp<CFG>& w, const Soa<CFG>& so, FwdL<CFG::CPL>& f, const 
 			const uint32_t pos = rs.n + __popc(hm & ((1u << lane) - 1u));
 			if (hot && pos < rs.cap)
 			{
-				// copy this lane's parked posteriors (its own writes) into the record, 8 bytes at a time
-				float2* dst = reinterpret_cast<float2*>(static_cast<LaneRec<CPL>*>(rs.recs) + pos);
+				typedef LaneRec<CPL> Rec;
+				float4* dst = reinterpret_cast<float4*>(static_cast<Rec*>(rs.recs) + pos);
+				float tmp[Rec::NF];
 #pragma unroll
-				for (int i = 0; i < L::NP; ++i)
+				for (int j = 0; j < CPL; ++j)
 				{
-					dst[i] = *row_pair<CFG>(pmrow, i, lane);
-					dst[L::NP + i] = *row_pair<CFG>(rowc, i, lane);
+					tmp[j] = PM[j];
+					tmp[CPL + j] = PE[j];
 				}
-				dst[2 * L::NP] = L::ODD ? f2(*row_single<CFG>(pmrow, lane), *row_single<CFG>(rowc, lane)) : f2(0.0f, 0.0f);
-				dst[2 * L::NP + 1] = f2(__int_as_float(lane), 0.0f);
+				tmp[2 * CPL] = __int_as_float(lane);
+#pragma unroll
+				for (int q = 2 * CPL + 1; q < Rec::NF; ++q) tmp[q] = 0.0f;
+#pragma unroll
+				for (int q = 0; q < Rec::NF / 4; ++q) dst[q] = make_float4(tmp[4 * q], tmp[4 * q + 1], tmp[4 * q + 2], tmp[4 * q + 3]);
 			}
 			rs.n += __popc(hm);
 			if (rs.n > rs.cap)
@@ -718,25 +434,48 @@ DYN_DEV void fwd_row(Warp<CFG>& w, const Soa<CFG>& so, FwdL<CFG::CPL>& f, const 
 			}
 		}
 	}
-	if (DO_STEP && slide)
+	if (DO_STEP)
 	{
-		const int nold = mid_f - w.bw;
-		if (nold >= 0)
-			with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, f.fM, f.fE, 0.0f});
-		++mid_f;
+		const float fl = (__shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) * f.sL1) * f.sL2;
+		if (pf)
+		{
+#pragma unroll
+			for (int j = 0; j < CPL; ++j)
+			{
+				bc[j] = pf[j * 32 + lane];
+				bn[j] = pf[CFG::ROWF + j * 32 + lane];
+			}
+		}
+#pragma unroll
+		for (int j = CPL - 1; j >= 0; --j)
+		{
+			const float left = (j > 0) ? f.fE[j - 1] : fl;
+			const float ne = fmaf(f.fE[j], e2, f.fM[j]) * p[j];  // (fM + fE*e2) * p    (NT:146-150, e1 = 1)
+			f.fM[j] = left * (p[j] * m1);                        // fE[t][n-1] * p * m1  (NT:143)
+			f.fE[j] = ne;
+		}
+		if (slide)
+		{
+			const int nold = mid_f - w.bw;
+			if (nold >= 0)
+				with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, f.fM, f.fE, 0.0f});
+			++mid_f;
+		}
 	}
 }
 
 // pass 2: forward + posterior + posterior-Viterbi fill.  Returns log2 Zf - log2 Zb (NaN on a range fault).
 template <class CFG>
-DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const Soa<CFG>& so, const SlotScratch& sc, const BatchArgs& args,
-	unsigned char* smem_raw, double Z2, float thr, float m1, float e2, uint32_t& nrec_out, bool& overflow)
+DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
+	double Z2, float thr, float m1, float e2, uint32_t& nrec_out, bool& overflow)
 {
 	constexpr int CPL = CFG::CPL;
 	constexpr int CK = CFG::CK;
-	typedef Lay<CFG> L;
+	constexpr int RN = CFG::RN;
+	constexpr int ROWF = CFG::ROWF;
 	SmemL<CFG> sm(smem_raw);
 	FwdL<CPL> f;
+	BwdL<CPL> b;
 	const int lane = w.lane;
 	const uint32_t T = w.T;
 	RecSink rs;
@@ -750,7 +489,10 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const Soa<CFG>& so, const Sl
 	const float c0 = (float)exp2(Z2f - Z2);
 
 	int mid_f = 0;
-	load_window<CFG>(w, so, 0);
+	float bc[CPL], bn[CPL];
+#pragma unroll
+	for (int j = 0; j < CPL; ++j) bc[j] = bn[j] = 0.0f;
+	w.load_window(0);
 	const uint32_t kb = (T - 1) / CK;
 	Chunk cur = chunk_load<CFG>(w, 0);
 	Chunk nxtc = chunk_load<CFG>(w, 32);
@@ -765,43 +507,40 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const Soa<CFG>& so, const Sl
 			nxtc = chunk_load<CFG>(w, t_lo + 32);
 		}
 		// ---- step a: recompute the backward rows of this block into shared memory -----------------------
+		// sm.OB[i] = backward offsets in force for rows t_lo + (i-1)*RN + 1 .. t_lo + i*RN
 		const bool from_ckpt = (t_hi <= T - 1);
 		const uint32_t src_row = from_ckpt ? t_hi : T - 1;
 		int mid_b = (int)band_mid(src_row, w.ratio);
-		slide_window_up<CFG>(w, so, mid_f, mid_b);
+		w.slide_window_up(mid_f, mid_b);
+		if (from_ckpt) ckpt_load<CFG>(sc, k + 1, lane, b);
+		else bwd_init_terminal<CFG>(w, b);
 		{
-			BwdL<CPL> b;
-			if (from_ckpt)
-			{
-				ckpt_load<CFG>(sc, k + 1, lane, b);
-				if (t_hi + CK <= T - 1) ckpt_prefetch<CFG>(sc, k + 2, lane);
-			}
-			else
-				bwd_init_terminal<CFG>(w, b);
-			row_store<CFG>(sm.rows + (size_t)(src_row - t_lo) * L::ROWF, lane, b);
-			sm.OB[32 + lane] = b.OB;  // offsets of rows t_lo+1 .. src_row
-			float xb = __shfl_sync(FULL, cur.xv, ((int)src_row - 1) & 31);
+			float* dst = sm.bE + (size_t)(src_row - t_lo) * ROWF;
+#pragma unroll
+			for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
+			sm.OB[((src_row - t_lo + RN - 1) / RN) * 32 + lane] = b.OB;
+		}
+		float xb = __shfl_sync(FULL, cur.xv, ((int)src_row - 1) & 31);
 #pragma unroll 1
-			for (int tt = (int)src_row - 1; tt >= (int)t_lo; --tt)
+		for (int tt = (int)src_row - 1; tt >= (int)t_lo; --tt)
+		{
+			const int i = tt & 31;
+			const float x = xb;
+			xb = __shfl_sync(FULL, cur.xv, (i - 1) & 31);
+			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid_b, m1, e2);
+			float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
+			if ((tt & (RN - 1)) == 0)
 			{
-				const int i = tt & 31;
-				const float x = xb;
-				xb = __shfl_sync(FULL, cur.xv, (i - 1) & 31);
-				bwd_step<CFG>(w, so, b, x, (cur.smask >> i) & 1u, mid_b, m1, e2);
-				if (tt == (int)t_lo)
-				{
-					bwd_renorm<CFG>(w, b);
-					sm.OB[lane] = b.OB;
-				}
-				row_store<CFG>(sm.rows + (size_t)(tt - (int)t_lo) * L::ROWF, lane, b);
+				bwd_renorm<CFG>(w, b);
+				sm.OB[((tt - (int)t_lo) / RN) * 32 + lane] = b.OB;
 			}
+#pragma unroll
+			for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
 		}
 		__syncwarp();
 
-		// ---- step b: forward rows t_lo .. min(t_hi, T - 1) - 1 ------------------------------------------
+		// ---- step b: forward rows t_lo .. min(t_hi, T) - 1 ----------------------------------------------
 		uint32_t t = t_lo;
-		const uint32_t t_end = min(t_hi, T - 1);
-		const int ob1 = sm.OB[32 + lane];
 		if (k == 0)
 		{
 			// row 0: fE[0][0] = 1 (NT:120), VE[0][0] = 1 (NT:336)
@@ -827,10 +566,21 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const Soa<CFG>& so, const Sl
 				const int ovl = __shfl_sync(FULL, f.OV, (lane + 31) & 31);
 				pow2_split(ovl - f.OV, f.sV1, f.sV2);
 			}
-			fwd_row<CFG, false, true>(w, so, f, sc, rs, thr, 0, __shfl_sync(FULL, cur.xv, 0), cur.smask & 1u, mid_f, sm.rows,
-				sm.rows + L::ROWF, sm.pmrow, 0.0f, 0.0f, m1, e2);
-			f.kap = kappa(f.OF, ob1, Z2i, c0);  // rows 1 .. CK
+			fwd_row<CFG, false, true>(w, f, sc, rs, thr, 0, __shfl_sync(FULL, cur.xv, 0), cur.smask & 1u, mid_f, bc, bn,
+				nullptr, 0.0f, 0.0f, m1, e2);
+			f.kap = kappa(f.OF, sm.OB[32 + lane], Z2i, c0);  // rows 1 .. RN
 			t = 1;
+		}
+		const uint32_t t_end = min(t_hi, T - 1);
+		if (t < t_end)
+		{
+			const float* row = sm.bE + (size_t)(t - t_lo) * ROWF;
+#pragma unroll
+			for (int j = 0; j < CPL; ++j)
+			{
+				bc[j] = row[j * 32 + lane];
+				bn[j] = row[ROWF + j * 32 + lane];
+			}
 		}
 		float x = __shfl_sync(FULL, cur.xv, t & 31);
 #pragma unroll 1
@@ -838,22 +588,25 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const Soa<CFG>& so, const Sl
 		{
 			const int i = t & 31;
 			const uint32_t r = t - t_lo;
-			// on the first row of a block (the renormalisation row) bM[t] = bE[t+1] * p lives in the offsets of the next rows
-			const float kapN = (r == 0) ? kappa(f.OF, ob1, Z2i, c0) : f.kap;
+			const bool rn_row = (t & (RN - 1)) == 0;
+			// on a renormalisation row bM[t] = bE[t+1] * p lives in the offsets of the next rows
+			const float kapN = rn_row ? kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0) : f.kap;
 			const float xn = __shfl_sync(FULL, cur.xv, (i + 1) & 31);
-			float* rowc = sm.rows + (size_t)r * L::ROWF;
-			fwd_row<CFG, true, true>(w, so, f, sc, rs, thr, t, x, (cur.smask >> i) & 1u, mid_f, rowc, rowc + L::ROWF, sm.pmrow,
-				f.kap, kapN, m1, e2);
+			fwd_row<CFG, true, true>(w, f, sc, rs, thr, t, x, (cur.smask >> i) & 1u, mid_f, bc, bn,
+				(t + 1 < t_end) ? sm.bE + (size_t)(r + 1) * ROWF : nullptr, f.kap, kapN, m1, e2);
 			f.kap = kapN;
+			// the forward values are now those of row t+1 (bc: the backward row t+1, or still row t at a block end)
+			if (((t + 1) & (RN - 1)) == 0) fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 1) / RN) * 32 + lane], Z2i, c0);
 			x = xn;
 		}
-		// the forward values are now those of row t_end; renormalise at block boundaries
-		if ((t_end & (CK - 1)) == 0 && t_end > t_lo)
-			fwd_renorm_block<CFG>(w, f, sm.rows + (size_t)(t_end - t_lo) * L::ROWF, ob1, Z2i, c0);
 		__syncwarp();
 	}
-	fwd_row<CFG, true, false>(w, so, f, sc, rs, thr, T - 1, 0.0f, false, mid_f, sm.rows + (size_t)((T - 1) - kb * CK) * L::ROWF,
-		sm.rows, sm.pmrow, f.kap, 0.0f, m1, e2);
+	{
+		const float* row = sm.bE + (size_t)((T - 1) - kb * CK) * ROWF;
+#pragma unroll
+		for (int j = 0; j < CPL; ++j) bc[j] = row[j * 32 + lane];
+		fwd_row<CFG, true, false>(w, f, sc, rs, thr, T - 1, 0.0f, false, mid_f, bc, bn, nullptr, f.kap, 0.0f, m1, e2);
+	}
 	// Zf = fE[T-1][N-1] (NT:285)
 	float v = 0.0f;
 	with_slot<CPL>(lane, pmod((int)w.N - 1, CFG::SLOTS), GetOne<CPL>{f.fE, v});
@@ -879,7 +632,6 @@ DYN_DEV int traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs&
 	constexpr int CPL = CFG::CPL;
 	constexpr int SLOTS = CFG::SLOTS;
 	typedef LaneRec<CPL> Rec;
-	typedef Lay<CFG> L;
 	const int lane = w.lane;
 	const uint32_t T = w.T;
 	uint32_t t_first = 0;
@@ -894,18 +646,18 @@ DYN_DEV int traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs&
 		const bool isM = (v >> 31) != 0;
 		const int q = (int)(col % SLOTS);
 		const int ql = q / CPL, j = q - ql * CPL;
-		const int fi = isM ? L::rec_m(j) : L::rec_e(j);
 		const uint32_t r0 = sc.rowptr[r], r1 = sc.rowptr[r + 1];
 		float mass = 0.0f, lp = 0.0f;
 		for (uint32_t i = r0; i < r1; ++i)
 		{
 			const float* f = recs[i].v;
-			for (int c = 0; c < L::REC_VALUES; ++c) mass += f[c];
-			if (__float_as_int(f[L::REC_LANE]) == ql) lp = f[fi];
+			for (int c = 0; c < 2 * CPL; ++c) mass += f[c];
+			if (__float_as_int(f[2 * CPL]) == ql) lp = f[(isM ? 0 : CPL) + j];
 		}
 		if (!(fabsf(mass - 1.0f) <= LIN_MASS_TOL)) bad = true;
 		sc.pp[r] = lp / mass;
 	}
+	// rows before the first path row (t_first > 1 never happens for a complete path, which starts at row 1)
 	if (__any_sync(FULL, bad)) return 2;
 	__threadfence_block();
 	__syncwarp();
@@ -920,7 +672,6 @@ DYN_DEV bool train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchAr
 {
 	constexpr int CPL = CFG::CPL;
 	typedef LaneRec<CPL> Rec;
-	typedef Lay<CFG> L;
 	const Rec* recs = static_cast<const Rec*>(sc.recs);
 	const int lane = w.lane;
 	double sm_ = 0.0, se_ = 0.0;
@@ -934,7 +685,7 @@ DYN_DEV bool train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchAr
 		for (uint32_t i = r0; i < r1; ++i)
 		{
 			const float* f = recs[i].v;
-			for (int c = 0; c < L::REC_VALUES; ++c) mass += f[c];
+			for (int c = 0; c < 2 * CPL; ++c) mass += f[c];
 		}
 		if (!(fabsf(mass - 1.0f) <= LIN_MASS_TOL)) bad = true;
 	}
@@ -946,7 +697,7 @@ DYN_DEV bool train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchAr
 		for (uint32_t i = r0; i < r1; ++i)
 		{
 			const float* f = recs[i].v;
-			for (int c = 0; c < L::REC_VALUES; ++c) mass += (double)f[c];
+			for (int c = 0; c < 2 * CPL; ++c) mass += (double)f[c];
 		}
 		const double inv = 1.0 / mass;
 		const double xo = (double)w.sig[r - 1];
@@ -954,10 +705,10 @@ DYN_DEV bool train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchAr
 		for (uint32_t i = r0; i < r1; ++i)
 		{
 			const float* f = recs[i].v;
-			const int rl = __float_as_int(f[L::REC_LANE]);
+			const int rl = __float_as_int(f[2 * CPL]);
 			for (int j = 0; j < CPL; ++j)
 			{
-				const double pm = (double)f[L::rec_m(j)] * inv, pe = (double)f[L::rec_e(j)] * inv;
+				const double pm = (double)f[j] * inv, pe = (double)f[CPL + j] * inv;
 				const double g = pm + pe;
 				if (!(g > 1e-12)) continue;
 				const int col = w.col_of_slot(rl * CPL + j, n0);
@@ -996,10 +747,6 @@ DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx
 	w.m1 = args.m1;
 	w.e2 = args.e2;
 	const float m1 = args.m1_lin, e2 = args.e2_lin;
-	Soa<CFG> so;
-	so.a = args.pc_soa + rd.pc_off;
-	so.b = so.a + args.pc_total;
-	so.c = so.b + args.pc_total;
 
 	ReadOut out;
 	out.Z = 0.0;
@@ -1009,7 +756,7 @@ DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx
 	out.xi_m = 0.0;
 	out.xi_e = 0.0;
 
-	const double Z2 = (MODE == 0) ? backward_pass<CFG, false>(w, so, sc, m1, e2) : backward_pass<CFG, true>(w, so, sc, m1, e2);
+	const double Z2 = (MODE == 0) ? backward_pass<CFG, false>(w, sc, m1, e2) : backward_pass<CFG, true>(w, sc, m1, e2);
 	out.Z = Z2 * LN2;
 	if (!(Z2 > -1.0e30 && Z2 < 1.0e30))
 		out.status = ST_LIN_FAULT;  // underflow of every path or NaN/inf: let the log2-domain kernels decide
@@ -1017,7 +764,7 @@ DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx
 	{
 		uint32_t nrec = 0;
 		bool overflow = false;
-		const double dz2 = forward_posterior_pass<CFG>(w, so, sc, args, smem_raw, Z2, args.thr_lin, m1, e2, nrec, overflow);
+		const double dz2 = forward_posterior_pass<CFG>(w, sc, args, smem_raw, Z2, args.thr_lin, m1, e2, nrec, overflow);
 		out.nrec = nrec;
 		out.dZ = dz2 * LN2;
 		if (!(fabs(dz2) <= LIN_Z_TOL)) out.status = ST_LIN_FAULT;

@@ -140,11 +140,6 @@ namespace
 using Cfg16 = Cfg<13, 16, 4, 8>;
 using Cfg8 = Cfg<13, 8, 4, 8>;
 constexpr int N_VARIANTS = 4;
-// the linear-domain kernels keep nothing row-sized in registers: 12 single-warp CTAs per SM (<= 168 registers, 16.5 KB smem)
-#ifndef DYN_LIN_MINB
-#define DYN_LIN_MINB 12
-#endif
-constexpr int LIN_MINB = DYN_LIN_MINB;
 
 struct EncodeArgs
 {
@@ -155,8 +150,6 @@ struct EncodeArgs
 	int k;
 	const PosConst* table;
 	PosConst* pc;
-	float* pc_soa;      // a[pc_total] | b[pc_total] | c[pc_total]
-	uint64_t pc_total;
 	int32_t* kmers;
 	uint32_t* bad_pos;
 };
@@ -185,16 +178,12 @@ DYN_DEV void encode_read(const EncodeArgs& a, uint32_t r, int lane)
 	const char* s = a.seq + a.seq_off[r];
 	const uint32_t Kc = rd.N - 1;
 	PosConst* pc = a.pc + rd.pc_off;
-	float* sa = a.pc_soa + rd.pc_off;
-	float* sb = sa + a.pc_total;
-	float* sc = sb + a.pc_total;
 	int32_t* km = a.kmers + rd.pc_off;
 	if (lane == 0)
 	{
 		PosConst z;
 		z.a = 0.0f; z.b = 0.0f; z.c = CNEG; z.pad = 0.0f;
 		pc[0] = z;  // column 0 scores no kmer
-		sa[0] = 0.0f; sb[0] = 0.0f; sc[0] = CNEG;
 		km[0] = -1;
 	}
 	uint32_t bad = 0xffffffffu;
@@ -214,9 +203,7 @@ DYN_DEV void encode_read(const EncodeArgs& a, uint32_t r, int lane)
 		}
 		if (id >= 0)
 		{
-			const PosConst v = a.table[id];
-			pc[c + 1] = v;
-			sa[c + 1] = v.a; sb[c + 1] = v.b; sc[c + 1] = v.c;
+			pc[c + 1] = a.table[id];
 			km[c + 1] = id;
 		}
 	}
@@ -250,7 +237,7 @@ DYN_DEV void align_worker(const BatchArgs& args, unsigned char* smem_raw, int la
 			}
 			continue;
 		}
-		if constexpr (LIN) lin::align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
+		if (LIN) lin::align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
 		else align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
 		__syncwarp();
 	}
@@ -316,17 +303,10 @@ void launch_encode(Rt& rt, const EncodeArgs& a)
 #endif
 }
 
-template <class CFG, bool LIN>
-constexpr size_t align_smem_bytes()
-{
-	if constexpr (LIN) return lin::Lay<CFG>::SMEM_BYTES;
-	else return CFG::SMEM_BYTES;
-}
-
 template <class CFG, int MINB, bool LIN>
 void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 {
-	const size_t smem = align_smem_bytes<CFG, LIN>();
+	const size_t smem = CFG::SMEM_BYTES;
 #ifndef DYN_HOST_EMU
 	static bool attr_set = false;
 	if (!attr_set)
@@ -352,10 +332,7 @@ void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 template <class CFG, int MINB>
 void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode, bool lin)
 {
-	// the linear-domain kernels renormalise by exact powers of two, so one renormalisation per checkpoint block
-	// (RN = CK = 8) gives bit-identical results to more frequent ones; they share the log2-domain scratch layout
-	typedef Cfg<CFG::CPL, 8, 8, 8> LCFG;
-	if (lin) launch_align_t<LCFG, LIN_MINB, true>(rt, args, grid, mode);
+	if (lin) launch_align_t<CFG, MINB, true>(rt, args, grid, mode);
 	else launch_align_t<CFG, MINB, false>(rt, args, grid, mode);
 }
 
@@ -429,7 +406,7 @@ struct dyn_aligner
 	double mem_fraction = 0.85;
 	// device state
 	DevBuf d_table, d_sig, d_seq, d_seqoff, d_desc, d_order, d_pc, d_kmers, d_bad, d_out, d_sigpos, d_prob, d_scratch,
-		d_slots, d_queue, d_rw, d_rx, d_rxx, d_sw, d_sx, d_sxx, d_pcsoa;
+		d_slots, d_queue, d_rw, d_rx, d_rxx, d_sw, d_sx, d_sxx;
 	bool table_dirty = true;
 	double timing[3] = {0, 0, 0};
 
@@ -654,7 +631,6 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	rt.h2d(d_order, order.data(), order.size() * 4);
 	PosConst* d_pc = (PosConst*)A.d_pc.get(rt, pc_total * sizeof(PosConst));
 	int32_t* d_kmers = (int32_t*)A.d_kmers.get(rt, pc_total * 4);
-	float* d_pcsoa = (float*)A.d_pcsoa.get(rt, pc_total * 12);
 	uint32_t* d_bad = (uint32_t*)A.d_bad.get(rt, (size_t)n * 4);
 	rt.fill_ff(d_bad, (size_t)n * 4);
 	ReadOut* d_out = (ReadOut*)A.d_out.get(rt, (size_t)n * sizeof(ReadOut));
@@ -672,25 +648,24 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	// ---- K1: kmer encoding + emission constants ---------------------------------------------------------------
 	EncodeArgs ea;
 	ea.reads = d_desc; ea.n_reads = n; ea.seq = d_seq; ea.seq_off = d_seqoff; ea.k = A.k;
-	ea.table = (const PosConst*)A.d_table.p; ea.pc = d_pc; ea.pc_soa = d_pcsoa; ea.pc_total = pc_total; ea.kmers = d_kmers; ea.bad_pos = d_bad;
+	ea.table = (const PosConst*)A.d_table.p; ea.pc = d_pc; ea.kmers = d_kmers; ea.bad_pos = d_bad;
 	rt.mark(0);
 	launch_encode(rt, ea);
 	rt.mark(1);
 
 	// ---- scratch: one slot per resident warp, sized for the longest read --------------------------------------
 	// Z-only runs the backward pass alone: <= 128 registers and no shared memory, i.e. 16 single-warp CTAs per SM
-	const bool lin = (A.arith == 0);
-	const int resident = (mode == 0) ? 16 : (lin ? LIN_MINB : MINB);
+	const int resident = (mode == 0) ? 16 : MINB;
 	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * (A.warps_per_sm > 0 ? A.warps_per_sm : resident), order.size());
 	size_t per_slot = 0;
 	uint64_t rec_cap = 0;
 	size_t o_ck = 0, o_ob = 0, o_bits = 0, o_rp = 0, o_rec = 0, o_pn = 0, o_pp = 0;
 	if (mode != 0)
 	{
-		const size_t nck = (size_t)maxT / std::min(CFG::CK, 8) + 2;
+		const size_t nck = (size_t)maxT / CFG::CK + 2;
 		rec_cap = (uint64_t)std::min<double>((double)maxT * A.recs_per_row, (double)maxT * 32.0) + 64;
 		size_t o = 0;
-		o_ck = o; o = align_up(o + nck * std::max<size_t>(CFG::CKF, 32 * 32) * 4, 256);  // linear-domain checkpoints: 128 B per lane
+		o_ck = o; o = align_up(o + nck * CFG::CKF * 4, 256);
 		o_ob = o; o = align_up(o + nck * 32 * 8, 256);
 		o_bits = o; o = align_up(o + ((size_t)maxT + 32) * 64, 256);
 		o_rp = o; o = align_up(o + ((size_t)maxT + 2) * 4, 256);
@@ -726,7 +701,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	BatchArgs ba;
 	memset(&ba, 0, sizeof(ba));
 	ba.reads = d_desc; ba.order = d_order; ba.n_reads = (uint32_t)order.size(); ba.queue = d_queue;
-	ba.signal = d_sig; ba.pc = d_pc; ba.pc_soa = d_pcsoa; ba.pc_total = pc_total; ba.slots = d_slots; ba.rec_cap = rec_cap; ba.out = d_out;
+	ba.signal = d_sig; ba.pc = d_pc; ba.slots = d_slots; ba.rec_cap = rec_cap; ba.out = d_out;
 	ba.out_sigpos = d_sigpos; ba.out_prob = d_prob;
 	ba.m1 = (float)(A.trans[0] * LOG2E);
 	ba.e2 = (float)(A.trans[2] * LOG2E);
@@ -753,6 +728,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	}
 
 	// ---- K2..K5: the DP kernel ------------------------------------------------------------------------------------
+	const bool lin = (A.arith == 0);
 	A.n_fallback = 0;
 	rt.mark(2);
 	launch_align<CFG, MINB>(rt, ba, grid, mode, lin);
@@ -898,7 +874,7 @@ void dyn_destroy(dyn_aligner* A)
 		A->rt.bind();
 		for (DevBuf* b : {&A->d_table, &A->d_sig, &A->d_seq, &A->d_seqoff, &A->d_desc, &A->d_order, &A->d_pc, &A->d_kmers,
 				 &A->d_bad, &A->d_out, &A->d_sigpos, &A->d_prob, &A->d_scratch, &A->d_slots, &A->d_queue, &A->d_rw,
-				 &A->d_rx, &A->d_rxx, &A->d_sw, &A->d_sx, &A->d_sxx, &A->d_pcsoa})
+				 &A->d_rx, &A->d_rxx, &A->d_sw, &A->d_sx, &A->d_sxx})
 			b->release(A->rt);
 		A->rt.fini();
 	}

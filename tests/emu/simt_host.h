@@ -230,15 +230,6 @@ struct float4
 	float x, y, z, w;
 };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
-struct float2
-{
-	float x, y;
-};
-inline float2 make_float2(float x, float y) { return float2{x, y}; }
-// packed FP32 (FFMA2 / FMUL2 / FADD2 on sm_100): two independent IEEE round-to-nearest operations
-inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
-inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
-inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift)
 {
 	shift &= 31;

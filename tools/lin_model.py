@@ -31,7 +31,7 @@ def scale2(a, e):
         return ftz(np.ldexp(a.astype(f32), np.clip(e, -400, 400).astype(np.int32)).astype(f32))
 
 
-def align_lin(x, kmers, mean, stdev, trans, k, band=400, R=int(__import__("os").environ.get("LIN_R", "4")), RV=8, thr=2.0 ** -22, CPL=13, D=100, E0V=20,
+def align_lin(x, kmers, mean, stdev, trans, k, band=400, R=4, RV=8, thr=2.0 ** -22, CPL=13, D=100, E0V=20,
               mass_tol=1e-3):
     x = np.asarray(x, dtype=f32)
     S = x.size
