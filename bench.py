@@ -320,17 +320,18 @@ def main():
 
     def step_device():
         """One step: every batch through the C ABI with device-resident inputs.  Returns (#ok reads, kernel ms, launches)."""
-        ok, kms, nl = 0, 0.0, 0
+        ok, kms, nl, fb = 0, 0.0, 0, 0
         for b in batches:
             res, _, _, _ = al.align_packed(b["sig"].data_ptr(), b["sig_off"], b["bases"].data_ptr(), b["seq_off"],
                                            not args.z_only, device=True)
             tm = al.last_timing()
             kms += tm["dp_ms"]
             nl += tm["launches"]
+            fb += tm["log2_fallback_reads"]
             ok += sum(1 for i in range(b["sig_off"].size - 1) if res[i].status == 0)
-        return ok, kms, nl
+        return ok, kms, nl, fb
 
-    dp_ms, launches = [], 0
+    dp_ms, launches, fallbacks = [], 0, 0
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local_rank)
@@ -340,9 +341,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        n_ok, kms, nl = step_device()
+        n_ok, kms, nl, fb = step_device()
         dp_ms.append(kms)
         launches += nl
+        fallbacks += fb
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / args.steps
@@ -412,18 +414,28 @@ def main():
     mufu_peak = 16.0 * sms * clk_mhz * 1e6 / 1e9           # G MUFU op/s at the clock seen under load
     mufu_peak_max = 16.0 * sms * (peaks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
     dp_s = dp_ms_all * 1e-3
-    alg_mufu = 4.0 * cells / dp_s / 1e9                     # forward + backward: 2 MUFU per cell-update each
-    exe_mufu = 6.0 * cells / dp_s / 1e9                     # executed: backward, backward recompute, forward
-    # algorithmic HBM bytes per read: 4*S signal in + 16*N emission constants + 12*Kc out + spill
-    # (checkpoints 3584 B per 16 rows written+read, decision bits 64 B/row written+read, records ~ 12 B * few / row)
-    hbm_bytes = n_samples * 4.0 + n_bases * 17.0 + (n_samples / 16.0) * 3584 * 2 + n_samples * 64.0 * 2 + n_samples * 12.0 * 3 * 2
+    # algorithmic work: the log-space forward + backward of the reference = 2 passes x 2 MUFU (ex2 + lg2)
+    # per cell.  Executed: the linear-domain kernels run 3 passes (backward, backward recomputation, forward) x 1 MUFU
+    # (the emission ex2) per cell; the log2-domain kernels (--opt arith=1, and the fallback reads) 3 x 2.
+    lin = not any(kv.startswith("arith=") and float(kv.split("=")[1]) != 0 for kv in args.opt)
+    alg_mufu = 4.0 * cells / dp_s / 1e9
+    exe_mufu = (3.0 if lin else 6.0) * cells / dp_s / 1e9
+    # algorithmic HBM bytes per launch: 4*S signal in + 16*N emission constants + 12*Kc out + spill
+    # (checkpoints 3584 B per 8 rows written+read, decision bits 64 B/row written+read, records ~1.1 x 112 B / row
+    # written + read once)
+    hbm_bytes = n_samples * 4.0 + n_bases * 17.0 + (n_samples / 8.0) * 3584 * 2 + n_samples * 64.0 * 2 + n_samples * 125.0 * 2
     roofline = {
-        "bound": "sfu", "kernel": "k_align<Cfg<13,CK,4,8>,1> (library default variant unless --variant)",
+        "bound": "sfu",
+        "kernel": ("k_align<Cfg<13,8,4,8>,1,8,LIN=1> (linear-domain FP32, 1 MUFU per cell-update)" if lin else
+                   "k_align<Cfg<13,8,4,8>,1,8,LIN=0> (log2-domain FP32, 2 MUFU per cell-update)"),
         "achieved": alg_mufu, "peak": mufu_peak, "unit": "G MUFU op/s", "frac": alg_mufu / mufu_peak,
+        "achieved_definition": "algorithmic: 4 MUFU per lattice cell (log-space forward + backward, SURVEY 8d) x cells / kernel time",
         "executed": exe_mufu, "executed_frac": exe_mufu / mufu_peak,
         "peak_at_max_clock": mufu_peak_max, "peak_source": "16 MUFU/clk/SM x SMs x SM clock sampled by nvidia-smi during the timed region",
         "cell_updates_per_s": 3.0 * cells / dp_s, "kernel_ms": dp_ms_all,
+        "log2_fallback_reads": int(fallbacks),
         "traffic": None,
+        "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1d_k_align_lin_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
         "hbm": {"achieved": hbm_bytes / dp_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "note": "algorithmic signal + constants + checkpoint/decision-bit/record spill per launch"},
     }
