@@ -123,18 +123,25 @@ DYN_DEV void bwd_row(Warp<CFG>& w, BwdL<CFG::CPL>& b, float x, float m1, float e
 {
 	constexpr int CPL = CFG::CPL;
 	float p[CPL], A[CPL];
-	emis_lin<CFG>(w, x, p);
+	// A[n] = bM[t+1][n] * p(t,n) * m1 is consumed by column n-1.  Slot 0 goes first: A[0] is what the left lane needs,
+	// and the shuffle that carries it then has the rest of the row to complete.
+	p[0] = ex2(emis2(x, w.em.a[0], w.em.b[0], w.em.c[0]));
+	A[0] = b.bM[0] * (p[0] * m1);
+	const float Araw = __shfl_sync(FULL, A[0], (w.lane + 1) & 31);
 #pragma unroll
-	for (int j = 0; j < CPL; ++j) A[j] = b.bM[j] * (p[j] * m1);  // bM[t+1][n] * p(t,n) * m1, consumed by column n-1
-	const float Ar = (__shfl_sync(FULL, A[0], (w.lane + 1) & 31) * b.sR1) * b.sR2;
+	for (int j = 1; j < CPL; ++j) p[j] = ex2(emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]));
 #pragma unroll
-	for (int j = 0; j < CPL; ++j)
+	for (int j = 1; j < CPL; ++j) A[j] = b.bM[j] * (p[j] * m1);
+#pragma unroll
+	for (int j = 0; j + 1 < CPL; ++j)
 	{
-		const float ext1 = (j + 1 < CPL) ? A[j + 1] : Ar;
 		const float nm = b.bE[j] * p[j];   // bM[t][n] = bE[t+1][n] * p            (NT:200)
-		b.bE[j] = fmaf(nm, e2, ext1);      //                                      (NT:194,201,204)
+		b.bE[j] = fmaf(nm, e2, A[j + 1]);  //                                      (NT:194,201,204)
 		b.bM[j] = nm;
 	}
+	const float nml = b.bE[CPL - 1] * p[CPL - 1];
+	b.bM[CPL - 1] = nml;
+	b.bE[CPL - 1] = fmaf(nml, e2, (Araw * b.sR1) * b.sR2);
 }
 
 // lane-local renormalisation by an exact power of two; returns the exponent increment (new OB - old OB)
@@ -231,6 +238,25 @@ DYN_DEV void ckpt_load(const SlotScratch& sc, uint32_t idx, int lane, BwdL<CFG::
 	b.OB = reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)idx * 64 + lane];
 	const int obr = __shfl_sync(FULL, b.OB, (lane + 1) & 31);
 	pow2_split(obr - b.OB, b.sR1, b.sR2);
+}
+
+// pull checkpoint idx towards L2 ahead of its use: a lane's values are CPL*2 rows of 128 bytes, one sector each
+template <class CFG>
+DYN_DEV void ckpt_prefetch(const SlotScratch& sc, uint32_t idx, int lane)
+{
+#ifndef DYN_HOST_EMU
+	const float* f = sc.ckpt + (size_t)idx * CFG::CKF;
+	// 2*CPL rows x 128 B = 104 sectors of 32 B for CPL = 13; lane l touches sectors l, l+32, l+64, l+96
+#pragma unroll
+	for (int q = 0; q < (2 * CFG::CPL * 4 + 31) / 32; ++q)
+	{
+		const int sct = q * 32 + lane;
+		if (sct < 2 * CFG::CPL * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(f + sct * 8));
+	}
+	if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(sc.ckpt_ob) + (size_t)idx * 256 + lane * 32));
+#else
+	(void)sc; (void)idx; (void)lane;
+#endif
 }
 
 // pass 1: backward over the whole read.  Returns log2 Zb (double) in every lane (NaN/-inf on a range fault).
@@ -364,11 +390,14 @@ DYN_DEV void vit_renorm(Warp<CFG>& w, FwdL<CFG::CPL>& f)
 // row t+1).
 template <class CFG, bool DO_V, bool DO_STEP>
 DYN_DEV void fwd_row(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, RecSink& rs, float thr, uint32_t t, float x,
-	bool slide, int& mid_f, float (&bc)[CFG::CPL], float (&bn)[CFG::CPL], const float* pf, float kapE, float kapM,
+	bool slide, int& mid_f, float (&bc)[CFG::CPL], float (&bn)[CFG::CPL], const float* pf, bool has_pf, float kapE, float kapM,
 	float m1, float e2)
 {
 	constexpr int CPL = CFG::CPL;
 	const int lane = w.lane;
+	// the values the right lane needs are those of the previous row: send them first, consume them last
+	const float vlraw = DO_V ? __shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31) : 0.0f;
+	const float flraw = DO_STEP ? __shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) : 0.0f;
 	if (DO_STEP && slide) w.activate(mid_f + 1 + w.bw);  // column entering band(t+1)
 
 	float p[CPL], PM[CPL], PE[CPL];
@@ -386,7 +415,7 @@ DYN_DEV void fwd_row(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, Rec
 			with_slot<CPL>(lane, pmod(mid_f - w.bw, CFG::SLOTS), SetOne<CPL>{PM, 0.0f});  // see dp_kernels.cuh fwd_row
 		// posterior-Viterbi fill (NT:357-362) as a max-product, in place from the highest slot down;
 		// decision bit = sign(VM - VE): set <=> the E state of this cell is entered from E (test of NT:448)
-		const float vl = (__shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31) * f.sV1) * f.sV2;
+		const float vl = (vlraw * f.sV1) * f.sV2;
 		unsigned acc = 0;
 		float lmax = 0.0f;
 #pragma unroll
@@ -436,8 +465,8 @@ DYN_DEV void fwd_row(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, Rec
 	}
 	if (DO_STEP)
 	{
-		const float fl = (__shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31) * f.sL1) * f.sL2;
-		if (pf)
+		const float fl = (flraw * f.sL1) * f.sL2;
+		if (has_pf)
 		{
 #pragma unroll
 			for (int j = 0; j < CPL; ++j)
@@ -512,7 +541,11 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 		const uint32_t src_row = from_ckpt ? t_hi : T - 1;
 		int mid_b = (int)band_mid(src_row, w.ratio);
 		w.slide_window_up(mid_f, mid_b);
-		if (from_ckpt) ckpt_load<CFG>(sc, k + 1, lane, b);
+		if (from_ckpt)
+		{
+			ckpt_load<CFG>(sc, k + 1, lane, b);
+			if (t_hi + CK <= T - 1) ckpt_prefetch<CFG>(sc, k + 2, lane);  // pull the next block's checkpoint into L2
+		}
 		else bwd_init_terminal<CFG>(w, b);
 		{
 			float* dst = sm.bE + (size_t)(src_row - t_lo) * ROWF;
@@ -567,7 +600,7 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 				pow2_split(ovl - f.OV, f.sV1, f.sV2);
 			}
 			fwd_row<CFG, false, true>(w, f, sc, rs, thr, 0, __shfl_sync(FULL, cur.xv, 0), cur.smask & 1u, mid_f, bc, bn,
-				nullptr, 0.0f, 0.0f, m1, e2);
+				sm.bE, false, 0.0f, 0.0f, m1, e2);
 			f.kap = kappa(f.OF, sm.OB[32 + lane], Z2i, c0);  // rows 1 .. RN
 			t = 1;
 		}
@@ -593,7 +626,7 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 			const float kapN = rn_row ? kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0) : f.kap;
 			const float xn = __shfl_sync(FULL, cur.xv, (i + 1) & 31);
 			fwd_row<CFG, true, true>(w, f, sc, rs, thr, t, x, (cur.smask >> i) & 1u, mid_f, bc, bn,
-				(t + 1 < t_end) ? sm.bE + (size_t)(r + 1) * ROWF : nullptr, f.kap, kapN, m1, e2);
+				sm.bE + (size_t)(r + 1) * ROWF, t + 1 < t_end, f.kap, kapN, m1, e2);
 			f.kap = kapN;
 			// the forward values are now those of row t+1 (bc: the backward row t+1, or still row t at a block end)
 			if (((t + 1) & (RN - 1)) == 0) fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 1) / RN) * 32 + lane], Z2i, c0);
@@ -605,7 +638,7 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 		const float* row = sm.bE + (size_t)((T - 1) - kb * CK) * ROWF;
 #pragma unroll
 		for (int j = 0; j < CPL; ++j) bc[j] = row[j * 32 + lane];
-		fwd_row<CFG, true, false>(w, f, sc, rs, thr, T - 1, 0.0f, false, mid_f, bc, bn, nullptr, f.kap, 0.0f, m1, e2);
+		fwd_row<CFG, true, false>(w, f, sc, rs, thr, T - 1, 0.0f, false, mid_f, bc, bn, sm.bE, false, f.kap, 0.0f, m1, e2);
 	}
 	// Zf = fE[T-1][N-1] (NT:285)
 	float v = 0.0f;
