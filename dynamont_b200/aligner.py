@@ -121,6 +121,42 @@ class Aligner:
             raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
         return res, seqpos, sigpos, prob
 
+    # ---- resquiggle (NTK) mode: pre-pass stages (reference NTK_aligner_api.cpp:120-441) ---------------------
+    def ntk_transitions(self) -> dict:
+        t = np.zeros(18)
+        self._lib.dyn_ntk_transitions(self._h, t.ctypes.data_as(f64p))
+        names = ["a1", "a2", "p1", "p2", "p3", "s1", "s2", "s3", "e1", "e2", "e3", "e4", "i1", "i2",
+                 "tn_m", "tn_e", "tk_m", "tk_e"]
+        return dict(zip(names, t.tolist()))
+
+    def ntk_prepass(self, signal, sequence: str) -> dict:
+        """Dense TN / TK pre-passes of resquiggle mode on the GPU: boolean row masks ``tn`` [T, N] and ``tk`` [T, K]
+        (the reference's tnMap / tkMap), the sorted sparse-lattice ``keys`` and ``Z`` = (Zf, Zb) of both passes."""
+        sig = np.ascontiguousarray(signal, dtype=np.float32)
+        seq = sequence.encode("latin-1")
+        S, L = sig.size, len(seq)
+        T, N, K = S + 1, max(L - self.kmer_size + 2, 1), self.num_kmers
+        wn, wk = (N + 31) // 32, (K + 31) // 32
+        tn = np.zeros((T, wn), dtype=np.uint32)
+        tk = np.zeros((T, wk), dtype=np.uint32)
+        z4 = np.zeros(4)
+        nk = C.c_uint64(0)
+        cap = 1 << 16
+        while True:
+            keys = np.zeros(cap, dtype=np.uint64)
+            rc = self._lib.dyn_ntk_prepass(self._h, C.c_void_p(sig.ctypes.data if S else 0), S, seq, L, C.c_void_p(tn.ctypes.data),
+                                           C.c_void_p(tk.ctypes.data), C.c_void_p(keys.ctypes.data), cap, C.byref(nk),
+                                           z4.ctypes.data_as(f64p))
+            if rc < 0:
+                raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+            if rc > 0:
+                raise RuntimeError(self._lib.dyn_status_message(rc).decode())
+            if nk.value <= cap:
+                break
+            cap = int(nk.value)
+        unpack = lambda m, C_: np.unpackbits(m.view(np.uint8), axis=1, bitorder="little")[:, :C_].astype(bool)  # noqa: E731
+        return {"tn": unpack(tn, N), "tk": unpack(tk, K), "keys": keys[:nk.value].copy(), "Z": z4}
+
     def read_cells(self, S: int, L: int) -> int:
         return int(self._lib.dyn_read_cells(self._h, int(S), int(L)))
 

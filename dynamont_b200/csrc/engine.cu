@@ -7,6 +7,7 @@
 #include "../../include/dynamont_b200.h"
 #include "dp_kernels.cuh"
 #include "dp_linear.cuh"
+#include "ntk_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -399,6 +400,8 @@ struct dyn_aligner
 	// tuning
 	int warps_per_sm = 0;  // 0 = the variant's own occupancy
 	int variant = 3;  // measured fastest on B200
+	bool ntk = false; // resquiggle (NTK) mode: only the pre-pass stages are built (dyn_ntk_prepass)
+	double ntk_trans[18] = {0};  // log a1,a2,p1-3,s1-3,e1-4,i1,i2, then log ntMatch/ntExtend for TN and TK (NTK:35-104)
 	int arith = 0;    // 0: linear-domain kernels, reads with an FP32 range fault re-run in the log2 domain; 1: log2 domain only
 	uint64_t n_fallback = 0;  // reads of the last batch that were re-run in the log2 domain
 	double thr2 = -22.0;
@@ -835,14 +838,31 @@ dyn_aligner* dyn_create(const char* model_path, const char* pore, const char* mo
 			throw std::invalid_argument(std::string("Unknown pore type: ") + pore);  // aligner_bindings.cpp:31
 		}
 		const std::string m(mode ? mode : "basic");
-		if (m == "resquiggle" || m == "ntk")
-			throw std::runtime_error("dynamont_b200: resquiggle (NTK) mode is not built yet; use mode='basic'");
-		if (m != "basic" && m != "nt")
+		const bool ntk = (m == "resquiggle" || m == "ntk");
+		if (!ntk && m != "basic" && m != "nt")
 		{
 			if (err_kind) *err_kind = 1;
 			throw std::invalid_argument("Unknown aligner mode: " + m);  // aligner_bindings.cpp:50
 		}
 		A = new dyn_aligner();
+		A->ntk = ntk;
+		{
+			// NTKAligner::initializeTransitions (NTK_aligner_api.cpp:35-104)
+			static const double RNA002_T[14] = {0.019326040280789637, 0.19725479693713352, 0.1979799841413514,
+				0.0006135538271005425, 0.7669801909288386, 0.27034500789657623, 0.00032463686748883153,
+				0.02916688206070035, 1.0, 0.7296549921055607, 0.8020200158564497, 0.9797333838008437,
+				2.3852272324574183e-06, 0.006598130068516047};
+			static const double RNA004_T[14] = {0.029709838889618322, 0.2837864344979079, 0.15353628902814298,
+				0.0041495012884881655, 0.47456322874771467, 0.05012685122100474, 0.0006112333189296363,
+				0.13506593503589423, 1.0, 0.949873148779652, 0.8464637109688202, 0.9654529072452087,
+				7.651926003806137e-05, 0.10658440170772512};
+			static const double ONES_T[14] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+			const std::string pn(pi->name);
+			const double* tv = (pn == "rna002") ? RNA002_T : (pn == "dna_r9") ? ONES_T : RNA004_T;
+			for (int i = 0; i < 14; ++i) A->ntk_trans[i] = std::log(tv[i]);
+			A->ntk_trans[14] = A->ntk_trans[16] = std::log(pi->m1);
+			A->ntk_trans[15] = A->ntk_trans[17] = std::log(pi->e2);
+		}
 		A->rna = pi->rna;
 		A->k = pi->k;
 		A->band = band;
@@ -967,12 +987,15 @@ uint64_t dyn_batch_cells(const dyn_aligner* A, const uint64_t* sig_off, const ui
 	return total;
 }
 
+static const char* NTK_PARTIAL = "dynamont_b200: resquiggle (NTK) mode: only the pre-pass stages are built (dyn_ntk_prepass); use mode='basic' for alignments";
+
 static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilities, dyn_read_result* results,
 	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities)
 {
 	std::lock_guard<std::mutex> g(A->mu);
 	try
 	{
+		if (A->ntk) throw std::runtime_error(NTK_PARTIAL);
 		BatchResult res;
 		const uint64_t seg_total = dyn_count_segments(A, io.seq_off, io.n);
 		std::vector<uint32_t> sigpos(calc_probabilities ? seg_total : 0);
@@ -1089,6 +1112,7 @@ int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off
 	std::lock_guard<std::mutex> g(A->mu);
 	try
 	{
+		if (A->ntk) throw std::runtime_error(NTK_PARTIAL);
 		BatchIO io;
 		io.sig_host = signal; io.seq_host = seq; io.sig_off = sig_off; io.seq_off = seq_off; io.n = n_reads;
 		BatchResult res;
@@ -1184,6 +1208,160 @@ int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off
 	}
 }
 
+void dyn_ntk_transitions(const dyn_aligner* A, double* out18) { std::memcpy(out18, A->ntk_trans, sizeof(A->ntk_trans)); }
+
+int dyn_ntk_prepass(dyn_aligner* A, const float* signal, uint64_t S, const char* seq, uint64_t L, uint32_t* tn_mask,
+	uint32_t* tk_mask, uint64_t* keys, uint64_t keys_cap, uint64_t* n_keys, double* z4)
+{
+#ifdef DYN_HOST_EMU
+	(void)signal; (void)S; (void)seq; (void)L; (void)tn_mask; (void)tk_mask; (void)keys; (void)keys_cap; (void)n_keys; (void)z4;
+	A->last_error = "dyn_ntk_prepass: not available in the emulator build";
+	return -1;
+#else
+	std::lock_guard<std::mutex> g(A->mu);
+	try
+	{
+		using namespace dyn::ntk;
+		Rt& rt = A->rt;
+		rt.bind();
+		// Aligner::validateInput (aligner.cpp:145-164) and sequenceToKmers (:166-205)
+		if (S < 1) return DYN_SIGNAL_EMPTY;
+		if (L < (uint64_t)A->k) return DYN_SEQ_SHORT;
+		const uint64_t Kc = L - A->k + 1;
+		if (S < 2 * Kc) return DYN_SIGNAL_SHORT;
+		std::vector<int32_t> kmers(Kc);
+		for (uint64_t c = 0; c < Kc; ++c)
+		{
+			uint64_t id = 0;
+			for (int i = 0; i < A->k; ++i)
+			{
+				const int d = host_digit((unsigned char)seq[c + i]);
+				if (d < 0 || d > 3) return DYN_INVALID_NT;
+				id = id * 4 + (uint64_t)d;
+			}
+			kmers[c] = (int32_t)id;
+		}
+		const uint32_t T = (uint32_t)(S + 1), N = (uint32_t)(Kc + 1), K = (uint32_t)A->K;
+		const uint32_t wn = (N + 31) / 32, wk = (K + 31) / 32;
+		uint32_t hp = 1;
+		for (int i = 1; i < A->k; ++i) hp *= 4;
+		const size_t C = std::max<size_t>(N, K);
+		// device buffers (released at the end: this is a stage API, not the streaming path)
+		std::vector<KmerModel> km(K);
+		for (uint32_t q = 0; q < K; ++q)
+		{
+			km[q].mean = A->mean[q];
+			km[q].stdev = A->stdev[q];
+			km[q].log_stdev = std::log(A->stdev[q]);
+		}
+		std::vector<double> sig(S);
+		for (uint64_t i = 0; i < S; ++i) sig[i] = (double)signal[i];
+		DevBuf b_model, b_sig, b_kmers, b_lat, b_z, b_tn, b_tk, b_cnt, b_keys;
+		auto release = [&]() {
+			for (DevBuf* b : {&b_model, &b_sig, &b_kmers, &b_lat, &b_z, &b_tn, &b_tk, &b_cnt, &b_keys}) b->release(rt);
+		};
+		try
+		{
+			KmerModel* d_model = (KmerModel*)b_model.get(rt, K * sizeof(KmerModel));
+			double* d_sig = (double*)b_sig.get(rt, S * 8);
+			int32_t* d_kmers = (int32_t*)b_kmers.get(rt, Kc * 4);
+			double* d_lat = (double*)b_lat.get(rt, (size_t)5 * T * C * 8);
+			double* d_z = (double*)b_z.get(rt, 4 * 8);
+			uint32_t* d_tn = (uint32_t*)b_tn.get(rt, (size_t)T * wn * 4);
+			uint32_t* d_tk = (uint32_t*)b_tk.get(rt, (size_t)T * wk * 4);
+			uint64_t* d_cnt = (uint64_t*)b_cnt.get(rt, (size_t)T * 8);
+			rt.h2d(d_model, km.data(), K * sizeof(KmerModel));
+			rt.h2d(d_sig, sig.data(), S * 8);
+			rt.h2d(d_kmers, kmers.data(), Kc * 4);
+			PrepassArgs pa;
+			pa.signal = d_sig; pa.kmers = d_kmers; pa.T = T; pa.N = N; pa.K = K; pa.hp = hp;
+			pa.c.model = d_model;
+			pa.c.half_log_2pi = 0.5 * std::log(2.0 * M_PI);
+			// SPARSETHRESHOLD (NTK_aligner_api.cpp:17): the literal the reference ships, commented there as log(0.95)
+			// but numerically log10(0.95), i.e. a posterior mass of 0.97797
+			const double threshold = -0.02227639471;
+			double z[4] = {0, 0, 0, 0};
+			const double EPS = 1e-8;
+			// ---- TN (preProcTN, NTK:315-354)
+			pa.c.m = A->ntk_trans[14]; pa.c.e = A->ntk_trans[15];
+			pa.fM = d_lat; pa.fE = d_lat + (size_t)T * N; pa.bM = d_lat + (size_t)2 * T * N; pa.bE = d_lat + (size_t)3 * T * N;
+			pa.LP = d_lat + (size_t)4 * T * N; pa.z = d_z;
+			k_tn_fill<<<1, 1024, 0, rt.stream>>>(pa);
+			CK_CUDA(cudaGetLastError());
+			rt.d2h(z, d_z, 16);
+			rt.sync();
+			if (std::abs(z[0] - z[1]) / (double)((size_t)T * N) > EPS || std::isinf(z[0]) || std::isinf(z[1]))
+			{
+				release();
+				return DYN_NTK_TN_FAILED;
+			}
+			k_dense_logp<<<std::min<size_t>(((size_t)T * N + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * N, z[0]);  // Zf (NTK:336)
+			k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, N, wn, d_tn, threshold);
+			CK_CUDA(cudaGetLastError());
+			rt.sync();
+			// ---- TK (preProcTK, NTK:356-400)
+			pa.c.m = A->ntk_trans[16]; pa.c.e = A->ntk_trans[17];
+			pa.fM = d_lat; pa.fE = d_lat + (size_t)T * K; pa.bM = d_lat + (size_t)2 * T * K; pa.bE = d_lat + (size_t)3 * T * K;
+			pa.LP = d_lat + (size_t)4 * T * K; pa.z = d_z + 2;
+			k_tk_fill<<<1, 1024, 0, rt.stream>>>(pa);
+			CK_CUDA(cudaGetLastError());
+			rt.d2h(z + 2, d_z + 2, 16);
+			rt.sync();
+			if (std::abs(z[2] - z[3]) / (double)((size_t)T * K) > EPS || std::isinf(z[2]) || std::isinf(z[3]))
+			{
+				release();
+				return DYN_NTK_TK_FAILED;
+			}
+			k_dense_logp<<<std::min<size_t>(((size_t)T * K + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * K, z[3]);  // Zb (NTK:382)
+			k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, K, wk, d_tk, threshold);
+			CK_CUDA(cudaGetLastError());
+			// ---- keys (preProcTNK, NTK:402-441)
+			KeyArgs ka;
+			ka.tn = d_tn; ka.tk = d_tk; ka.kmers = d_kmers; ka.T = T; ka.N = N; ka.K = K; ka.wn = wn; ka.wk = wk;
+			ka.count = d_cnt; ka.keys = nullptr;
+			k_keys<false><<<(T + 127) / 128, 128, 0, rt.stream>>>(ka);
+			CK_CUDA(cudaGetLastError());
+			std::vector<uint64_t> cnt(T);
+			rt.d2h(cnt.data(), d_cnt, (size_t)T * 8);
+			rt.sync();
+			uint64_t total = 0;
+			for (uint32_t t = 0; t < T; ++t)
+			{
+				const uint64_t c = cnt[t];
+				cnt[t] = total;
+				total += c;
+			}
+			if (n_keys) *n_keys = total;
+			if (keys && total <= keys_cap && total)
+			{
+				uint64_t* d_keys = (uint64_t*)b_keys.get(rt, total * 8);
+				rt.h2d(d_cnt, cnt.data(), (size_t)T * 8);
+				ka.keys = d_keys;
+				k_keys<true><<<(T + 127) / 128, 128, 0, rt.stream>>>(ka);
+				CK_CUDA(cudaGetLastError());
+				rt.d2h(keys, d_keys, total * 8);
+			}
+			if (tn_mask) rt.d2h(tn_mask, d_tn, (size_t)T * wn * 4);
+			if (tk_mask) rt.d2h(tk_mask, d_tk, (size_t)T * wk * 4);
+			rt.sync();
+			if (z4) std::memcpy(z4, z, sizeof(z));
+		}
+		catch (...)
+		{
+			release();
+			throw;
+		}
+		release();
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		A->last_error = e.what();
+		return -1;
+	}
+#endif
+}
+
 const char* dyn_status_message(int status)
 {
 	switch (status)
@@ -1195,6 +1373,8 @@ const char* dyn_status_message(int status)
 	case DYN_INVALID_NT: return "Invalid nucleotide: ";
 	case DYN_ALIGN_FAILED: return "Alignment failed: alignment scores do not match";
 	case DYN_TRAIN_FAILED: return "Training failed: alignment scores do not match";
+	case DYN_NTK_TN_FAILED: return "NTK preprocessing TN failed: alignment scores do not match";
+	case DYN_NTK_TK_FAILED: return "NTK preprocessing TK failed: alignment scores do not match";
 	case DYN_BAND_UNSUPPORTED: return "dynamont_b200: band too wide for this build (band/2 must be <= 207)";
 	default: return "dynamont_b200: internal error";
 	}

@@ -33,7 +33,9 @@ enum
 	DYN_TRAIN_FAILED = 6,   /* NT_aligner_api.cpp:625  "Training failed: alignment scores do not match" */
 	DYN_REC_OVERFLOW = 7,   /* internal, never returned: resolved by an automatic retry */
 	DYN_INTERNAL = 8,
-	DYN_BAND_UNSUPPORTED = 9 /* band wider than this build's ring capacity */
+	DYN_BAND_UNSUPPORTED = 9, /* band wider than this build's ring capacity */
+	DYN_NTK_TN_FAILED = 11,  /* NTK_aligner_api.cpp:335  "NTK preprocessing TN failed: alignment scores do not match" */
+	DYN_NTK_TK_FAILED = 12   /* NTK_aligner_api.cpp:381  "NTK preprocessing TK failed: alignment scores do not match" */
 };
 
 typedef struct
@@ -119,6 +121,21 @@ int dyn_train_batch(dyn_aligner*, const float* signal, const uint64_t* sig_off, 
 const char* dyn_status_message(int status);
 /* message of the last runtime failure on this handle */
 const char* dyn_last_error(const dyn_aligner*);
+
+/* ---- resquiggle ("NTK") mode, pre-pass stages (reference NTK_aligner_api.cpp:120-441; rows B1-B6 of SURVEY.md 8a).
+ * A handle created with mode "resquiggle"/"ntk" offers these stage entry points; dyn_align_batch on such a handle fails
+ * until the sparse 5-state stages (NTK:443-927) are built.
+ *
+ * dyn_ntk_transitions: the 14 log transition scores a1,a2,p1,p2,p3,s1,s2,s3,e1,e2,e3,e4,i1,i2 followed by
+ *   log ntMatch / log ntExtend of the TN and of the TK pre-pass (NTKAligner::initializeTransitions, NTK:35-104).
+ * dyn_ntk_prepass: one read.  tn_mask [T][ceil(N/32)] and tk_mask [T][ceil(K/32)] receive the posterior-mass row
+ *   sets tnMap / tkMap of preProcTN / preProcTK (NTK:315-400) as bitmaps (bit i of word i/32); keys receives the sorted
+ *   key list t*N*K + n*K + q of preProcTNK (NTK:402-441) when it fits keys_cap, *n_keys its length either way;
+ *   z4 = {Zf, Zb} of the TN pass then of the TK pass.  T = S + 1, N = L - k + 2, K = 4^k.
+ *   Returns 0, a dyn_status (input validation as in dyn_align_batch, DYN_NTK_TN_FAILED, DYN_NTK_TK_FAILED) or -1. */
+void dyn_ntk_transitions(const dyn_aligner*, double* out18);
+int dyn_ntk_prepass(dyn_aligner*, const float* signal, uint64_t S, const char* seq, uint64_t L, uint32_t* tn_mask,
+	uint32_t* tk_mask, uint64_t* keys, uint64_t keys_cap, uint64_t* n_keys, double* z4);
 
 /* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
  * last batch call: [0] encode/emission-constant kernel, [1] main DP kernel, [2] number of kernel launches */

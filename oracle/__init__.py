@@ -52,10 +52,11 @@ def have_reference() -> bool:
 class Reference:
     """The unmodified reference C++ (oracle/_ref)."""
 
-    def __init__(self, model_file: str, pore: str, mode: str = "basic", band: int = 400):
-        path = _build.build_reference()
+    def __init__(self, model_file: str, pore: str, mode: str = "basic", band: int = 400, ntk_fix: bool = False):
+        # ntk_fix: the reference with the two-line repair of resquiggle mode (oracle/build.py, SURVEY.md F2)
+        path = _build.build_reference_ntkfix() if ntk_fix else _build.build_reference()
         if path is None:
-            raise FileNotFoundError("oracle/_ref/libdynamont_ref.so not built and /root/reference absent")
+            raise FileNotFoundError("oracle/_ref reference library not built and /root/reference absent")
         self._lib = lib = C.CDLL(path)
         lib.ref_create.restype = C.c_void_p
         lib.ref_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
@@ -162,6 +163,35 @@ class Reference:
         if rc:
             raise RuntimeError(err.value.decode())
         return {"Zf": Zf.value, "Zb": Zb.value, "rows": out, "w": w, "sx": sx, "sxx": sxx}
+
+
+def _ntk_prepass(self, signal, sequence: str, want_z: bool = True) -> dict:
+    """Reference resquiggle (NTK) mode, the stages that work as shipped (NTK_aligner_api.cpp:197-441): row masks
+    of the dense TN / TK pre-passes and the sorted sparse-lattice keys."""
+    sig = np.ascontiguousarray(signal, dtype=np.float64)
+    T, N, K = sig.size + 1, len(sequence) - self.k + 2, self.K
+    tn = np.zeros((T, N), dtype=np.uint8)
+    tk = np.zeros((T, K), dtype=np.uint8)
+    cap = 64 * T * 64
+    keys = np.zeros(cap, dtype=np.uint64)
+    nk = C.c_size_t()
+    z4 = np.zeros(4)
+    tr = np.zeros(18)
+    err = C.create_string_buffer(512)
+    self._lib.ref_ntk_prepass.argtypes = [C.c_void_p, _c_double_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), _c_double_p, _c_double_p,
+                                          C.c_char_p, C.c_size_t]
+    rc = self._lib.ref_ntk_prepass(self._h, _ptr(sig, _c_double_p), sig.size, sequence.encode(), tn.ctypes.data,
+                                   tk.ctypes.data, keys.ctypes.data, cap, C.byref(nk),
+                                   _ptr(z4, _c_double_p) if want_z else None, _ptr(tr, _c_double_p), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    if nk.value > cap:
+        raise RuntimeError("key buffer too small")
+    return {"tn": tn.astype(bool), "tk": tk.astype(bool), "keys": keys[:nk.value].copy(), "Z": z4, "transitions": tr}
+
+
+Reference.ntk_prepass = _ntk_prepass
 
 
 def load_model_native(path: str, pore: str):

@@ -60,8 +60,48 @@ def build_reference(force: bool = False) -> str | None:
     return REF_SO
 
 
+REF_NTKFIX_SO = os.path.join(REF_DIR, "libdynamont_ref_ntkfix.so")
+
+
+def build_reference_ntkfix(force: bool = False) -> str | None:
+    """The reference with the two-line repair of resquiggle (NTK) mode described in SURVEY.md F2 / 8c: as shipped,
+    ``NTKAligner::logF`` / ``logB`` (NTK_aligner_api.cpp:443-607) write their results into the sparse map only after
+    the loop, so every predecessor lookup inside the loop reads -inf and every input throws.  The patch makes each
+    result visible immediately (``forAPSEI[tnk] = computed[idx];`` after :508, ``backAPSEI[tnk] = computed[idx];``
+    after :600) — the evident intent, and what ``decodeMAP`` (:862) already does.  The patched translation unit is
+    generated in a temporary directory and deleted; only the ``.so`` lands in ``oracle/_ref/``."""
+    import shutil
+    import tempfile
+    srcs = reference_sources()
+    shim = os.path.join(HERE, "ref_shim.cpp")
+    if not all(os.path.exists(s) for s in srcs):
+        return REF_NTKFIX_SO if os.path.exists(REF_NTKFIX_SO) else None
+    if not force and _newer(REF_NTKFIX_SO, srcs + [shim]):
+        return REF_NTKFIX_SO
+    os.makedirs(REF_DIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="dyn_ntkfix_")
+    try:
+        text = open(srcs[2]).read()
+        marker = "computed[idx] = {a, p, s, e, i};"
+        parts = text.split(marker)
+        if len(parts) != 3:
+            raise RuntimeError("NTK_aligner_api.cpp does not look like the surveyed snapshot (marker count %d)" % (len(parts) - 1))
+        text = (parts[0] + marker + "\n\t\tforAPSEI[tnk] = computed[idx];" + parts[1] + marker +
+                "\n\t\tbackAPSEI[tnk] = computed[idx];" + parts[2])
+        patched = os.path.join(tmp, "NTK_aligner_api_ntkfix.cpp")
+        with open(patched, "w") as fh:
+            fh.write(text)
+        cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-DNDEBUG",
+               "-I", os.path.join(REFERENCE, "include"), "-o", REF_NTKFIX_SO, shim, srcs[0], srcs[1], patched]
+        subprocess.run(cmd, check=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return REF_NTKFIX_SO
+
+
 def build_all(force: bool = False) -> dict:
-    return {"oracle": build_oracle(force), "reference": build_reference(force)}
+    return {"oracle": build_oracle(force), "reference": build_reference(force),
+            "reference_ntkfix": build_reference_ntkfix(force)}
 
 
 if __name__ == "__main__":

@@ -238,4 +238,72 @@ int ref_nt_stages(void* h, const double* signal, size_t S, const char* seq,
 	}
 }
 
+
+// Resquiggle (NTK) mode, stages that work in the reference as shipped (NTK_aligner_api.cpp:197-441): the dense TN
+// and TK pre-passes with their 95 %-mass row masks, and the sorted key list of the sparse lattice.
+//   tn_mask [T*N] / tk_mask [T*K] bytes (1 = member of tnMap[t] / tkMap[t]); keys: up to keys_cap entries.
+// z4 = { Zf_TN, Zb_TN, Zf_TK, Zb_TK } recomputed from the private pre-pass routines.
+int ref_ntk_prepass(void* h, const double* signal, size_t S, const char* seq, unsigned char* tn_mask,
+	unsigned char* tk_mask, unsigned long long* keys, size_t keys_cap, size_t* n_keys, double* z4, double* trans18,
+	char* err, size_t errlen)
+{
+	try
+	{
+		auto* a = dynamic_cast<dynamont::NTKAligner*>(static_cast<RefHandle*>(h)->aligner.get());
+		if (!a) throw std::runtime_error("not a resquiggle-mode aligner");
+		const std::string sequence(seq);
+		a->validateInput(S, sequence.size());
+		const std::vector<int> kmers = a->sequenceToKmers(sequence);
+		const size_t T = S + 1, N = kmers.size() + 1, K = a->numKmers_;
+		dynamont::NTKAligner::ColumnMask tn, tk;
+		a->preProcTN(signal, kmers.data(), tn, T, N);
+		a->preProcTK(signal, tk, T, K);
+		std::memset(tn_mask, 0, T * N);
+		std::memset(tk_mask, 0, T * K);
+		for (size_t t = 0; t < T; ++t)
+		{
+			for (size_t n : tn[t]) tn_mask[t * N + n] = 1;
+			for (size_t k : tk[t]) tk_mask[t * K + k] = 1;
+		}
+		const std::vector<size_t> allowed = a->preProcTNK(signal, kmers.data(), T, N, K);
+		*n_keys = allowed.size();
+		for (size_t i = 0; i < allowed.size() && i < keys_cap; ++i) keys[i] = allowed[i];
+		if (z4)
+		{
+			const double NI = -std::numeric_limits<double>::infinity();
+			std::vector<double> fM(T * N, NI), fE(T * N, NI), bM(T * N, NI), bE(T * N, NI);
+			a->ppForTN(signal, kmers.data(), fM.data(), fE.data(), T, N);
+			a->ppBackTN(signal, kmers.data(), bM.data(), bE.data(), T, N);
+			z4[0] = fE[T * N - 1];
+			z4[1] = bE[0];
+			std::vector<double> gM(T * K, NI), gE(T * K, NI), hM(T * K, NI), hE(T * K, NI);
+			a->ppForTK(signal, gM.data(), gE.data(), T, K);
+			a->ppBackTK(signal, hM.data(), hE.data(), T, K);
+			double Zf = NI, Zb = NI;
+			for (size_t k = 0; k < K; ++k)
+			{
+				Zf = dynamont::Aligner::logPlus(Zf, gE[T * K - 1 - k]);
+				Zb = dynamont::Aligner::logPlus(Zb, hE[k]);
+			}
+			z4[2] = Zf;
+			z4[3] = Zb;
+		}
+		if (trans18)
+		{
+			static const char* names[14] = {"a1", "a2", "p1", "p2", "p3", "s1", "s2", "s3", "e1", "e2", "e3", "e4", "i1", "i2"};
+			for (int i = 0; i < 14; ++i) trans18[i] = a->transitions_.at(names[i]);
+			trans18[14] = a->ppTNm_;
+			trans18[15] = a->ppTNe_;
+			trans18[16] = a->ppTKm_;
+			trans18[17] = a->ppTKe_;
+		}
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		put_err(err, errlen, e.what());
+		return 1;
+	}
+}
+
 } // extern "C"

@@ -1,0 +1,123 @@
+"""Resquiggle ("NTK") mode, pre-pass stages.
+
+Golden vectors: tests/golden/ntk_golden.npz (tools/make_golden_ntk.py) — stage outputs of the UNMODIFIED reference C++
+for the part of this mode that works as shipped (dense TN / TK pre-passes, row masks, sparse-lattice keys), and the
+end-to-end alignment of the reference with the two-line repair of SURVEY.md F2 (kept for the sparse stages, which are
+not built yet).  CPU tests pin the golden file against the compiled reference where it is available; the GPU test
+compares the CUDA stage kernels with the golden vectors through the C ABI (dyn_ntk_prepass)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import MODELS_DIR, ROOT
+
+GOLDEN_NTK = os.path.join(ROOT, "tests", "golden", "ntk_golden.npz")
+
+
+class NtkCase:
+    def __init__(self, z, name):
+        g = lambda k: z[name + "/" + k]  # noqa: E731
+        self.name = name
+        self.pore, self.model_name = str(g("pore")), str(g("model"))
+        self.signal = g("signal").astype(np.float64)
+        self.sequence = str(g("sequence"))
+        self.tn_ptr, self.tn_idx, self.tk_ptr, self.tk_idx = g("tn_ptr"), g("tn_idx"), g("tk_ptr"), g("tk_idx")
+        self.keys, self.Z, self.transitions = g("keys"), g("Z"), g("transitions")
+        self.has_alignment = (name + "/align_Z") in z.files
+        if self.has_alignment:
+            self.align_Z = float(g("align_Z"))
+            self.signal_positions, self.states, self.polishes = g("signal_positions"), g("states"), g("polishes")
+
+    @property
+    def model_path(self):
+        from dynamont_b200.synth import materialize_model
+        return materialize_model(self.model_name, MODELS_DIR)
+
+    def mask(self, which, C):
+        ptr, idx = (self.tn_ptr, self.tn_idx) if which == "tn" else (self.tk_ptr, self.tk_idx)
+        m = np.zeros((ptr.size - 1, C), dtype=bool)
+        rows = np.repeat(np.arange(ptr.size - 1), np.diff(ptr))
+        m[rows, idx] = True
+        return m
+
+
+def load_ntk():
+    with np.load(GOLDEN_NTK) as z:
+        return [NtkCase(z, str(n)) for n in z["names"]]
+
+
+def test_golden_file_shape():
+    cases = load_ntk()
+    assert len(cases) >= 4
+    for c in cases:
+        T = c.signal.size + 1
+        assert c.tn_ptr.size == T + 1 and c.tk_ptr.size == T + 1
+        assert np.all(np.diff(c.keys.astype(np.int64)) > 0)           # sorted, unique (NTK:438-440)
+        assert np.all(np.diff(c.tn_ptr) >= 1) and np.all(np.diff(c.tk_ptr) >= 1)  # every row keeps at least one column
+        assert c.keys[0] == 0                                          # the seed (0, 0, 0) (NTK:421-425)
+        assert abs(c.Z[0] - c.Z[1]) < 1e-6 and abs(c.Z[2] - c.Z[3]) < 1e-6
+        if c.has_alignment:
+            assert set(c.states.tolist()) <= {"M", "P"} and len(c.polishes) == len(c.states)
+
+
+@pytest.mark.parametrize("case", load_ntk(), ids=lambda c: c.name)
+def test_golden_pinned_against_reference(case):
+    """Regenerate the stage outputs with the compiled reference (dev container only) and compare bit for bit."""
+    from oracle import Reference, have_reference
+    if not have_reference():
+        pytest.skip("reference library not available")
+    ref = Reference(case.model_path, case.pore, mode="resquiggle")
+    if case.signal.size > 700:
+        pytest.skip("kept short: the larger cases are pinned by tools/make_golden_ntk.py")
+    st = ref.ntk_prepass(case.signal, case.sequence)
+    assert np.array_equal(st["keys"], case.keys)
+    assert np.array_equal(st["tn"], case.mask("tn", st["tn"].shape[1]))
+    assert np.array_equal(st["tk"], case.mask("tk", st["tk"].shape[1]))
+    assert np.array_equal(st["Z"], case.Z)
+    # the unmodified reference throws for every input in this mode ...
+    with pytest.raises(RuntimeError, match="NTK alignment failed"):
+        ref.align(case.signal, case.sequence, True)
+    # ... the repaired one reproduces the stored alignment
+    if case.has_alignment:
+        fix = Reference(case.model_path, case.pore, mode="resquiggle", ntk_fix=True)
+        a = fix.align(case.signal, case.sequence, True)
+        assert a["Z"] == case.align_Z and np.array_equal(a["signal_positions"], case.signal_positions)
+        assert a["polishes"] == case.polishes.tolist()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", load_ntk(), ids=lambda c: c.name)
+def test_gpu_prepass_matches_reference(case):
+    """CUDA TN / TK pre-passes, row masks and keys (through the C ABI) against the reference's stage outputs.
+    FP64 log-space on both sides; CUDA's exp/log1p differ from glibc's in the last ulp, so Z agrees to ~1e-12 relative
+    and a mask decision can only move when a cumulative mass lands on the threshold within rounding."""
+    from dynamont_b200 import Aligner
+    al = Aligner(case.model_path, case.pore, mode="resquiggle")
+    np.testing.assert_allclose([al.ntk_transitions()[k] for k in ("a1", "a2", "p1", "p2", "p3", "s1", "s2", "s3", "e1", "e2", "e3",
+                                                                  "e4", "i1", "i2", "tn_m", "tn_e", "tk_m", "tk_e")],
+                               case.transitions, rtol=0, atol=0)
+    r = al.ntk_prepass(case.signal, case.sequence)
+    np.testing.assert_allclose(r["Z"], case.Z, rtol=1e-10, atol=1e-9)
+    tn, tk = case.mask("tn", r["tn"].shape[1]), case.mask("tk", r["tk"].shape[1])
+    rows_tn = (r["tn"] == tn).all(1).mean()
+    rows_tk = (r["tk"] == tk).all(1).mean()
+    assert rows_tn >= 0.999 and rows_tk >= 0.999, (rows_tn, rows_tk)
+    inter = np.intersect1d(r["keys"], case.keys).size
+    assert inter >= 0.999 * max(r["keys"].size, case.keys.size)
+    if rows_tn == 1.0 and rows_tk == 1.0:
+        assert np.array_equal(r["keys"], case.keys)
+    with pytest.raises(RuntimeError, match="only the pre-pass stages are built"):
+        al.align(case.signal, case.sequence, True)
+
+
+@pytest.mark.gpu
+def test_gpu_prepass_input_errors():
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import materialize_model
+    al = Aligner(materialize_model("rna002_5mer", MODELS_DIR), "rna002", mode="ntk")
+    x = np.zeros(40, dtype=np.float32)
+    for sig, seq, msg in [(x[:0], "ACGTACGT", "Signal is empty"), (x, "ACG", "Sequence shorter than model kmer size"),
+                          (x[:6], "ACGTACGTACGT", "Signal too short compared to sequence"), (x, "ACGTNACGTA", "Invalid nucleotide")]:
+        with pytest.raises(RuntimeError, match=msg):
+            al.ntk_prepass(sig, seq)
