@@ -63,6 +63,7 @@ class Aligner:
             msg = err.value.decode()
             raise (ValueError if kind.value == 1 else RuntimeError)(msg)
         self.kmer_size = self._lib.dyn_kmer_size(self._h)
+        self._ntk = str(mode) in ("resquiggle", "ntk")
         self.num_kmers = int(self._lib.dyn_num_kmers(self._h))
         self.rna = bool(self._lib.dyn_is_rna(self._h))
 
@@ -232,8 +233,45 @@ class Aligner:
         sig = np.asarray(signal)
         if sig.ndim != 1:
             raise ValueError("Signal must be a one-dimensional array")
+        if self._ntk:
+            return self._ntk_align(sig, sequence, calc_probabilities)
         return self.align_batch([np.ascontiguousarray(sig, dtype=np.float64)], [sequence], calc_probabilities,
                                 raise_errors=True)[0]
+
+    def _int_to_kmer(self, q: int) -> str:
+        """Aligner::intToKmer (aligner.cpp:222-239): base-4 digits, most significant first; reversed for RNA pores."""
+        k = self.kmer_size
+        s = "".join("ACGT"[(q >> (2 * (k - 1 - i))) & 3] for i in range(k))
+        return s[::-1] if self.rna else s
+
+    def _ntk_align(self, sig, sequence: str, calc_probabilities: bool) -> dict:
+        """NTKAligner::align (NTK_aligner_api.cpp:881-927) through dyn_ntk_align: segments carry 'M' / 'P' states and
+        the polished kmer."""
+        x = np.ascontiguousarray(sig, dtype=np.float32)
+        seq = sequence.encode("latin-1")
+        cap = x.size + len(seq) + 16
+        Z = C.c_double(0.0)
+        ns = C.c_uint64(0)
+        states = C.create_string_buffer(cap)
+        seqpos = np.zeros(cap, dtype=np.uint64)
+        sigpos = np.zeros(cap, dtype=np.uint64)
+        prob = np.zeros(cap)
+        pk = np.zeros(cap, dtype=np.uint32)
+        rc = self._lib.dyn_ntk_align(self._h, C.c_void_p(x.ctypes.data if x.size else 0), x.size, seq, len(seq),
+                                     int(calc_probabilities), C.byref(Z), C.byref(ns), states, seqpos.ctypes.data_as(u64p),
+                                     sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p), C.c_void_p(pk.ctypes.data), cap)
+        if rc < 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        if rc > 0:
+            msg = self._lib.dyn_status_message(rc).decode()
+            if rc == 4:  # DYN_INVALID_NT: the reference names the offending character (aligner.cpp:182)
+                bad = next((ch for ch in sequence if ch not in "ACGTUacgtu"), "?")
+                msg += bad
+            raise RuntimeError(msg)
+        n = int(ns.value)
+        return {"Z": Z.value, "sequence_positions": seqpos[:n].copy(), "signal_positions": sigpos[:n].copy(),
+                "probabilities": prob[:n].copy(), "states": [chr(c) for c in states.raw[:n]],
+                "polishes": [self._int_to_kmer(int(q)) for q in pk[:n]]}
 
     # --------------------------------------------------------------------------------------------- train
     def train_batch(self, signals, sequences, per_read_model: bool = False):

@@ -987,7 +987,7 @@ uint64_t dyn_batch_cells(const dyn_aligner* A, const uint64_t* sig_off, const ui
 	return total;
 }
 
-static const char* NTK_PARTIAL = "dynamont_b200: resquiggle (NTK) mode: only the pre-pass stages are built (dyn_ntk_prepass); use mode='basic' for alignments";
+static const char* NTK_PARTIAL = "dynamont_b200: resquiggle (NTK) mode handles are served by dyn_ntk_align (one read per call); the batched entry points and training are basic mode only";
 
 static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilities, dyn_read_result* results,
 	uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities)
@@ -1210,6 +1210,140 @@ int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off
 
 void dyn_ntk_transitions(const dyn_aligner* A, double* out18) { std::memcpy(out18, A->ntk_trans, sizeof(A->ntk_trans)); }
 
+#ifndef DYN_HOST_EMU
+namespace
+{
+
+// device state of one resquiggle-mode read between the pre-pass and the sparse stages
+struct NtkRun
+{
+	DevBuf b_model, b_sig, b_kmers, b_lat, b_z, b_tn, b_tk, b_cnt, b_keys, b_sparse, b_seg;
+	uint32_t T = 0, N = 0, K = 0, hp = 1, wn = 0, wk = 0;
+	uint64_t Kc = 0, total = 0;
+	double z[4] = {0, 0, 0, 0};
+	std::vector<uint64_t> rowptr;  // [T+1]
+	dyn::ntk::Consts consts;
+	void release(Rt& rt)
+	{
+		for (DevBuf* b : {&b_model, &b_sig, &b_kmers, &b_lat, &b_z, &b_tn, &b_tk, &b_cnt, &b_keys, &b_sparse, &b_seg}) b->release(rt);
+	}
+};
+
+// validation + kmer encoding + TN / TK pre-passes + row masks + keys (NTK_aligner_api.cpp:197-441), all on the device.
+// Returns a dyn_status; throws on CUDA errors.
+int ntk_prepass_device(dyn_aligner* A, const float* signal, uint64_t S, const char* seq, uint64_t L, NtkRun& R)
+{
+	using namespace dyn::ntk;
+	Rt& rt = A->rt;
+	rt.bind();
+	// Aligner::validateInput (aligner.cpp:145-164) and sequenceToKmers (:166-205)
+	if (S < 1) return DYN_SIGNAL_EMPTY;
+	if (L < (uint64_t)A->k) return DYN_SEQ_SHORT;
+	const uint64_t Kc = L - A->k + 1;
+	if (S < 2 * Kc) return DYN_SIGNAL_SHORT;
+	std::vector<int32_t> kmers(Kc);
+	for (uint64_t c = 0; c < Kc; ++c)
+	{
+		uint64_t id = 0;
+		for (int i = 0; i < A->k; ++i)
+		{
+			const int d = host_digit((unsigned char)seq[c + i]);
+			if (d < 0 || d > 3) return DYN_INVALID_NT;
+			id = id * 4 + (uint64_t)d;
+		}
+		kmers[c] = (int32_t)id;
+	}
+	const uint32_t T = (uint32_t)(S + 1), N = (uint32_t)(Kc + 1), K = (uint32_t)A->K;
+	const uint32_t wn = (N + 31) / 32, wk = (K + 31) / 32;
+	uint32_t hp = 1;
+	for (int i = 1; i < A->k; ++i) hp *= 4;
+	R.T = T; R.N = N; R.K = K; R.hp = hp; R.wn = wn; R.wk = wk; R.Kc = Kc;
+	const size_t C = std::max<size_t>(N, K);
+	std::vector<KmerModel> km(K);
+	for (uint32_t q = 0; q < K; ++q)
+	{
+		km[q].mean = A->mean[q];
+		km[q].stdev = A->stdev[q];
+		km[q].log_stdev = std::log(A->stdev[q]);
+	}
+	std::vector<double> sig(S);
+	for (uint64_t i = 0; i < S; ++i) sig[i] = (double)signal[i];
+	KmerModel* d_model = (KmerModel*)R.b_model.get(rt, K * sizeof(KmerModel));
+	double* d_sig = (double*)R.b_sig.get(rt, S * 8);
+	int32_t* d_kmers = (int32_t*)R.b_kmers.get(rt, Kc * 4);
+	double* d_lat = (double*)R.b_lat.get(rt, (size_t)5 * T * C * 8);
+	double* d_z = (double*)R.b_z.get(rt, 4 * 8);
+	uint32_t* d_tn = (uint32_t*)R.b_tn.get(rt, (size_t)T * wn * 4);
+	uint32_t* d_tk = (uint32_t*)R.b_tk.get(rt, (size_t)T * wk * 4);
+	uint64_t* d_cnt = (uint64_t*)R.b_cnt.get(rt, ((size_t)T + 1) * 8);
+	rt.h2d(d_model, km.data(), K * sizeof(KmerModel));
+	rt.h2d(d_sig, sig.data(), S * 8);
+	rt.h2d(d_kmers, kmers.data(), Kc * 4);
+	PrepassArgs pa;
+	pa.signal = d_sig; pa.kmers = d_kmers; pa.T = T; pa.N = N; pa.K = K; pa.hp = hp;
+	pa.c.model = d_model;
+	pa.c.half_log_2pi = 0.5 * std::log(2.0 * M_PI);
+	// SPARSETHRESHOLD (NTK_aligner_api.cpp:17): the literal the reference ships, commented there as log(0.95)
+	// but numerically log10(0.95), i.e. a posterior mass of 0.97797
+	const double threshold = -0.02227639471;
+	const double EPS = 1e-8;
+	double* z = R.z;
+	// ---- TN (preProcTN, NTK:315-354)
+	pa.c.m = A->ntk_trans[14]; pa.c.e = A->ntk_trans[15];
+	pa.fM = d_lat; pa.fE = d_lat + (size_t)T * N; pa.bM = d_lat + (size_t)2 * T * N; pa.bE = d_lat + (size_t)3 * T * N;
+	pa.LP = d_lat + (size_t)4 * T * N; pa.z = d_z;
+	k_tn_fill<<<1, 1024, 0, rt.stream>>>(pa);
+	CK_CUDA(cudaGetLastError());
+	rt.d2h(z, d_z, 16);
+	rt.sync();
+	if (std::abs(z[0] - z[1]) / (double)((size_t)T * N) > EPS || std::isinf(z[0]) || std::isinf(z[1])) return DYN_NTK_TN_FAILED;
+	k_dense_logp<<<(unsigned)std::min<size_t>(((size_t)T * N + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * N, z[0]);  // Zf (NTK:336)
+	k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, N, wn, d_tn, threshold);
+	CK_CUDA(cudaGetLastError());
+	rt.sync();
+	// ---- TK (preProcTK, NTK:356-400)
+	pa.c.m = A->ntk_trans[16]; pa.c.e = A->ntk_trans[17];
+	pa.fM = d_lat; pa.fE = d_lat + (size_t)T * K; pa.bM = d_lat + (size_t)2 * T * K; pa.bE = d_lat + (size_t)3 * T * K;
+	pa.LP = d_lat + (size_t)4 * T * K; pa.z = d_z + 2;
+	k_tk_fill<<<1, 1024, 0, rt.stream>>>(pa);
+	CK_CUDA(cudaGetLastError());
+	rt.d2h(z + 2, d_z + 2, 16);
+	rt.sync();
+	if (std::abs(z[2] - z[3]) / (double)((size_t)T * K) > EPS || std::isinf(z[2]) || std::isinf(z[3])) return DYN_NTK_TK_FAILED;
+	k_dense_logp<<<(unsigned)std::min<size_t>(((size_t)T * K + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * K, z[3]);  // Zb (NTK:382)
+	k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, K, wk, d_tk, threshold);
+	CK_CUDA(cudaGetLastError());
+	// ---- keys (preProcTNK, NTK:402-441)
+	KeyArgs ka;
+	ka.tn = d_tn; ka.tk = d_tk; ka.kmers = d_kmers; ka.T = T; ka.N = N; ka.K = K; ka.wn = wn; ka.wk = wk;
+	ka.count = d_cnt; ka.keys = nullptr;
+	k_keys<false><<<(T + 127) / 128, 128, 0, rt.stream>>>(ka);
+	CK_CUDA(cudaGetLastError());
+	R.rowptr.assign((size_t)T + 1, 0);
+	rt.d2h(R.rowptr.data(), d_cnt, (size_t)T * 8);
+	rt.sync();
+	uint64_t total = 0;
+	for (uint32_t t = 0; t < T; ++t)
+	{
+		const uint64_t c = R.rowptr[t];
+		R.rowptr[t] = total;
+		total += c;
+	}
+	R.rowptr[T] = total;
+	R.total = total;
+	uint64_t* d_keys = (uint64_t*)R.b_keys.get(rt, std::max<uint64_t>(total, 1) * 8);
+	rt.h2d(d_cnt, R.rowptr.data(), ((size_t)T + 1) * 8);
+	ka.keys = d_keys;
+	if (total) k_keys<true><<<(T + 127) / 128, 128, 0, rt.stream>>>(ka);
+	CK_CUDA(cudaGetLastError());
+	rt.sync();
+	R.consts = pa.c;
+	return 0;
+}
+
+} // namespace
+#endif
+
 int dyn_ntk_prepass(dyn_aligner* A, const float* signal, uint64_t S, const char* seq, uint64_t L, uint32_t* tn_mask,
 	uint32_t* tk_mask, uint64_t* keys, uint64_t keys_cap, uint64_t* n_keys, double* z4)
 {
@@ -1219,143 +1353,114 @@ int dyn_ntk_prepass(dyn_aligner* A, const float* signal, uint64_t S, const char*
 	return -1;
 #else
 	std::lock_guard<std::mutex> g(A->mu);
+	NtkRun R;
+	try
+	{
+		const int st = ntk_prepass_device(A, signal, S, seq, L, R);
+		if (st == 0)
+		{
+			Rt& rt = A->rt;
+			if (n_keys) *n_keys = R.total;
+			if (keys && R.total && R.total <= keys_cap) rt.d2h(keys, R.b_keys.p, R.total * 8);
+			if (tn_mask) rt.d2h(tn_mask, R.b_tn.p, (size_t)R.T * R.wn * 4);
+			if (tk_mask) rt.d2h(tk_mask, R.b_tk.p, (size_t)R.T * R.wk * 4);
+			rt.sync();
+			if (z4) std::memcpy(z4, R.z, sizeof(R.z));
+		}
+		R.release(A->rt);
+		return st;
+	}
+	catch (const std::exception& e)
+	{
+		R.release(A->rt);
+		A->last_error = e.what();
+		return -1;
+	}
+#endif
+}
+
+int dyn_ntk_align(dyn_aligner* A, const float* signal, uint64_t S, const char* seq, uint64_t L, int calc_probabilities,
+	double* Z, uint64_t* n_segments, char* states, uint64_t* sequence_positions, uint64_t* signal_positions,
+	double* probabilities, uint32_t* polish_kmers, uint64_t cap)
+{
+#ifdef DYN_HOST_EMU
+	(void)signal; (void)S; (void)seq; (void)L; (void)calc_probabilities; (void)Z; (void)n_segments; (void)states;
+	(void)sequence_positions; (void)signal_positions; (void)probabilities; (void)polish_kmers; (void)cap;
+	A->last_error = "dyn_ntk_align: not available in the emulator build";
+	return -1;
+#else
+	std::lock_guard<std::mutex> g(A->mu);
+	NtkRun R;
 	try
 	{
 		using namespace dyn::ntk;
 		Rt& rt = A->rt;
-		rt.bind();
-		// Aligner::validateInput (aligner.cpp:145-164) and sequenceToKmers (:166-205)
-		if (S < 1) return DYN_SIGNAL_EMPTY;
-		if (L < (uint64_t)A->k) return DYN_SEQ_SHORT;
-		const uint64_t Kc = L - A->k + 1;
-		if (S < 2 * Kc) return DYN_SIGNAL_SHORT;
-		std::vector<int32_t> kmers(Kc);
-		for (uint64_t c = 0; c < Kc; ++c)
+		if (n_segments) *n_segments = 0;
+		int st = ntk_prepass_device(A, signal, S, seq, L, R);
+		if (st == 0)
 		{
-			uint64_t id = 0;
-			for (int i = 0; i < A->k; ++i)
+			const uint64_t nk = std::max<uint64_t>(R.total, 1);
+			const uint32_t T = R.T, N = R.N;
+			// F, B, LP, V [nk][5] doubles; Z[2]; status; segment arrays [T + N]
+			const size_t segcap = (size_t)T + N + 8;
+			const size_t sparse_bytes = nk * 5 * 8 * 4;
+			double* d_sparse = (double*)R.b_sparse.get(rt, sparse_bytes);
+			size_t o = 0;
+			auto carve = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 16); return at; };
+			const size_t o_z = carve(16), o_st = carve(4), o_ns = carve(4), o_state = carve(segcap), o_seq = carve(segcap * 8),
+						 o_sig = carve(segcap * 8), o_pr = carve(segcap * 8), o_km = carve(segcap * 4), o_buf = carve(segcap * 8);
+			unsigned char* d_seg = (unsigned char*)R.b_seg.get(rt, o);
+			rt.zero(d_seg, o);
+			SparseArgs sa;
+			sa.signal = (const double*)R.b_sig.p; sa.kmers = (const int32_t*)R.b_kmers.p;
+			sa.keys = (const uint64_t*)R.b_keys.p; sa.rowptr = (const uint64_t*)R.b_cnt.p; sa.nk = R.total;
+			sa.T = T; sa.N = N; sa.K = R.K; sa.hp = R.hp; sa.k = (uint32_t)A->k;
+			sa.c = R.consts;
+			for (int i = 0; i < 14; ++i) sa.tr[i] = A->ntk_trans[i];
+			sa.F = d_sparse; sa.B = d_sparse + nk * 5; sa.LP = d_sparse + nk * 10; sa.V = d_sparse + nk * 15;
+			sa.out_z = (double*)(d_seg + o_z); sa.out_status = (int32_t*)(d_seg + o_st); sa.seg_n = (uint32_t*)(d_seg + o_ns);
+			sa.seg_state = (char*)(d_seg + o_state); sa.seg_seqpos = (uint64_t*)(d_seg + o_seq); sa.seg_sigpos = (uint64_t*)(d_seg + o_sig);
+			sa.seg_prob = (double*)(d_seg + o_pr); sa.seg_kmer = (uint32_t*)(d_seg + o_km); sa.prob_buf = (double*)(d_seg + o_buf);
+			sa.calc_prob = calc_probabilities;
+			k_ntk_sparse<<<1, 32, 0, rt.stream>>>(sa);
+			CK_CUDA(cudaGetLastError());
+			std::vector<unsigned char> h(o);
+			rt.d2h(h.data(), d_seg, o);
+			rt.sync();
+			const double* hz = (const double*)(h.data() + o_z);
+			const int32_t kst = *(const int32_t*)(h.data() + o_st);
+			if (kst == 1) st = DYN_NTK_ALIGN_FAILED;  // NTK:913-918
+			else if (kst != 0) st = DYN_INTERNAL;
+			else
 			{
-				const int d = host_digit((unsigned char)seq[c + i]);
-				if (d < 0 || d > 3) return DYN_INVALID_NT;
-				id = id * 4 + (uint64_t)d;
+				if (Z) *Z = hz[1];  // result.Z = Zb (NTK:920)
+				const uint32_t ns = *(const uint32_t*)(h.data() + o_ns);
+				if (calc_probabilities)
+				{
+					if (ns > cap) st = DYN_INTERNAL;
+					else
+					{
+						// the traceback emits segments from the end of the read: reverse (NTK:800)
+						for (uint32_t i = 0; i < ns; ++i)
+						{
+							const uint32_t j = ns - 1 - i;
+							states[i] = ((const char*)(h.data() + o_state))[j];
+							sequence_positions[i] = ((const uint64_t*)(h.data() + o_seq))[j];
+							signal_positions[i] = ((const uint64_t*)(h.data() + o_sig))[j];
+							probabilities[i] = ((const double*)(h.data() + o_pr))[j];
+							polish_kmers[i] = ((const uint32_t*)(h.data() + o_km))[j];
+						}
+						if (n_segments) *n_segments = ns;
+					}
+				}
 			}
-			kmers[c] = (int32_t)id;
 		}
-		const uint32_t T = (uint32_t)(S + 1), N = (uint32_t)(Kc + 1), K = (uint32_t)A->K;
-		const uint32_t wn = (N + 31) / 32, wk = (K + 31) / 32;
-		uint32_t hp = 1;
-		for (int i = 1; i < A->k; ++i) hp *= 4;
-		const size_t C = std::max<size_t>(N, K);
-		// device buffers (released at the end: this is a stage API, not the streaming path)
-		std::vector<KmerModel> km(K);
-		for (uint32_t q = 0; q < K; ++q)
-		{
-			km[q].mean = A->mean[q];
-			km[q].stdev = A->stdev[q];
-			km[q].log_stdev = std::log(A->stdev[q]);
-		}
-		std::vector<double> sig(S);
-		for (uint64_t i = 0; i < S; ++i) sig[i] = (double)signal[i];
-		DevBuf b_model, b_sig, b_kmers, b_lat, b_z, b_tn, b_tk, b_cnt, b_keys;
-		auto release = [&]() {
-			for (DevBuf* b : {&b_model, &b_sig, &b_kmers, &b_lat, &b_z, &b_tn, &b_tk, &b_cnt, &b_keys}) b->release(rt);
-		};
-		try
-		{
-			KmerModel* d_model = (KmerModel*)b_model.get(rt, K * sizeof(KmerModel));
-			double* d_sig = (double*)b_sig.get(rt, S * 8);
-			int32_t* d_kmers = (int32_t*)b_kmers.get(rt, Kc * 4);
-			double* d_lat = (double*)b_lat.get(rt, (size_t)5 * T * C * 8);
-			double* d_z = (double*)b_z.get(rt, 4 * 8);
-			uint32_t* d_tn = (uint32_t*)b_tn.get(rt, (size_t)T * wn * 4);
-			uint32_t* d_tk = (uint32_t*)b_tk.get(rt, (size_t)T * wk * 4);
-			uint64_t* d_cnt = (uint64_t*)b_cnt.get(rt, (size_t)T * 8);
-			rt.h2d(d_model, km.data(), K * sizeof(KmerModel));
-			rt.h2d(d_sig, sig.data(), S * 8);
-			rt.h2d(d_kmers, kmers.data(), Kc * 4);
-			PrepassArgs pa;
-			pa.signal = d_sig; pa.kmers = d_kmers; pa.T = T; pa.N = N; pa.K = K; pa.hp = hp;
-			pa.c.model = d_model;
-			pa.c.half_log_2pi = 0.5 * std::log(2.0 * M_PI);
-			// SPARSETHRESHOLD (NTK_aligner_api.cpp:17): the literal the reference ships, commented there as log(0.95)
-			// but numerically log10(0.95), i.e. a posterior mass of 0.97797
-			const double threshold = -0.02227639471;
-			double z[4] = {0, 0, 0, 0};
-			const double EPS = 1e-8;
-			// ---- TN (preProcTN, NTK:315-354)
-			pa.c.m = A->ntk_trans[14]; pa.c.e = A->ntk_trans[15];
-			pa.fM = d_lat; pa.fE = d_lat + (size_t)T * N; pa.bM = d_lat + (size_t)2 * T * N; pa.bE = d_lat + (size_t)3 * T * N;
-			pa.LP = d_lat + (size_t)4 * T * N; pa.z = d_z;
-			k_tn_fill<<<1, 1024, 0, rt.stream>>>(pa);
-			CK_CUDA(cudaGetLastError());
-			rt.d2h(z, d_z, 16);
-			rt.sync();
-			if (std::abs(z[0] - z[1]) / (double)((size_t)T * N) > EPS || std::isinf(z[0]) || std::isinf(z[1]))
-			{
-				release();
-				return DYN_NTK_TN_FAILED;
-			}
-			k_dense_logp<<<std::min<size_t>(((size_t)T * N + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * N, z[0]);  // Zf (NTK:336)
-			k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, N, wn, d_tn, threshold);
-			CK_CUDA(cudaGetLastError());
-			rt.sync();
-			// ---- TK (preProcTK, NTK:356-400)
-			pa.c.m = A->ntk_trans[16]; pa.c.e = A->ntk_trans[17];
-			pa.fM = d_lat; pa.fE = d_lat + (size_t)T * K; pa.bM = d_lat + (size_t)2 * T * K; pa.bE = d_lat + (size_t)3 * T * K;
-			pa.LP = d_lat + (size_t)4 * T * K; pa.z = d_z + 2;
-			k_tk_fill<<<1, 1024, 0, rt.stream>>>(pa);
-			CK_CUDA(cudaGetLastError());
-			rt.d2h(z + 2, d_z + 2, 16);
-			rt.sync();
-			if (std::abs(z[2] - z[3]) / (double)((size_t)T * K) > EPS || std::isinf(z[2]) || std::isinf(z[3]))
-			{
-				release();
-				return DYN_NTK_TK_FAILED;
-			}
-			k_dense_logp<<<std::min<size_t>(((size_t)T * K + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * K, z[3]);  // Zb (NTK:382)
-			k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, K, wk, d_tk, threshold);
-			CK_CUDA(cudaGetLastError());
-			// ---- keys (preProcTNK, NTK:402-441)
-			KeyArgs ka;
-			ka.tn = d_tn; ka.tk = d_tk; ka.kmers = d_kmers; ka.T = T; ka.N = N; ka.K = K; ka.wn = wn; ka.wk = wk;
-			ka.count = d_cnt; ka.keys = nullptr;
-			k_keys<false><<<(T + 127) / 128, 128, 0, rt.stream>>>(ka);
-			CK_CUDA(cudaGetLastError());
-			std::vector<uint64_t> cnt(T);
-			rt.d2h(cnt.data(), d_cnt, (size_t)T * 8);
-			rt.sync();
-			uint64_t total = 0;
-			for (uint32_t t = 0; t < T; ++t)
-			{
-				const uint64_t c = cnt[t];
-				cnt[t] = total;
-				total += c;
-			}
-			if (n_keys) *n_keys = total;
-			if (keys && total <= keys_cap && total)
-			{
-				uint64_t* d_keys = (uint64_t*)b_keys.get(rt, total * 8);
-				rt.h2d(d_cnt, cnt.data(), (size_t)T * 8);
-				ka.keys = d_keys;
-				k_keys<true><<<(T + 127) / 128, 128, 0, rt.stream>>>(ka);
-				CK_CUDA(cudaGetLastError());
-				rt.d2h(keys, d_keys, total * 8);
-			}
-			if (tn_mask) rt.d2h(tn_mask, d_tn, (size_t)T * wn * 4);
-			if (tk_mask) rt.d2h(tk_mask, d_tk, (size_t)T * wk * 4);
-			rt.sync();
-			if (z4) std::memcpy(z4, z, sizeof(z));
-		}
-		catch (...)
-		{
-			release();
-			throw;
-		}
-		release();
-		return 0;
+		R.release(A->rt);
+		return st;
 	}
 	catch (const std::exception& e)
 	{
+		R.release(A->rt);
 		A->last_error = e.what();
 		return -1;
 	}
@@ -1375,6 +1480,7 @@ const char* dyn_status_message(int status)
 	case DYN_TRAIN_FAILED: return "Training failed: alignment scores do not match";
 	case DYN_NTK_TN_FAILED: return "NTK preprocessing TN failed: alignment scores do not match";
 	case DYN_NTK_TK_FAILED: return "NTK preprocessing TK failed: alignment scores do not match";
+	case DYN_NTK_ALIGN_FAILED: return "NTK alignment failed: alignment scores do not match";
 	case DYN_BAND_UNSUPPORTED: return "dynamont_b200: band too wide for this build (band/2 must be <= 207)";
 	default: return "dynamont_b200: internal error";
 	}

@@ -336,6 +336,440 @@ __global__ void k_keys(KeyArgs a)
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------
+// sparse 5-state stages (rows B7-B10): logF / logB (NTK:443-607, with each result visible to later keys at once —
+// the repair of SURVEY.md F2), Z check (:897-918), sparse logP (:159-177), MAP fill + traceback (:628-879).
+// States A=0 P=1 S=2 E=3 I=4.  One warp per read: the keys of a lattice row are independent except for the I state
+// (same row, column n-1 / n+1), which one lane then completes in key order; row t only needs rows t-1 / t+1.
+// A key is found by binary search inside its row's slice of the sorted key list.
+// ------------------------------------------------------------------------------------------------------
+struct SparseArgs
+{
+	const double* signal;     // [S]
+	const int32_t* kmers;     // [N-1]
+	const uint64_t* keys;     // [nk] ascending
+	const uint64_t* rowptr;   // [T+1] first key of row t
+	uint64_t nk;
+	uint32_t T, N, K, hp, k;
+	Consts c;
+	double tr[14];            // log a1,a2,p1,p2,p3,s1,s2,s3,e1,e2,e3,e4,i1,i2
+	double *F, *B, *LP, *V;   // [nk][5]
+	double* out_z;            // [2] Zf, Zb
+	int32_t* out_status;      // 0 ok, 1 scores do not match, 2 traceback stuck (undefined in the reference)
+	// segments, in traceback order (the host reverses): state ('M'/'P'), n-1+k/2, t-1, median probability, polish kmer id
+	uint32_t* seg_n;
+	char* seg_state;
+	uint64_t* seg_seqpos;
+	uint64_t* seg_sigpos;
+	double* seg_prob;
+	uint32_t* seg_kmer;
+	double* prob_buf;         // [T + N] scratch for the probabilities of one segment
+	int calc_prob;
+};
+
+enum { TA1 = 0, TA2, TP1, TP2, TP3, TS1, TS2, TS3, TE1, TE2, TE3, TE4, TI1, TI2 };
+
+__device__ __forceinline__ int64_t sp_find(const SparseArgs& a, uint32_t t, uint32_t n, uint32_t q)
+{
+	const uint64_t key = ((uint64_t)t * a.N + n) * a.K + q;
+	uint64_t lo = a.rowptr[t], hi = a.rowptr[t + 1];
+	while (lo < hi)
+	{
+		const uint64_t mid = (lo + hi) >> 1;
+		const uint64_t v = a.keys[mid];
+		if (v < key) lo = mid + 1;
+		else hi = mid;
+	}
+	return (lo < a.rowptr[t + 1] && a.keys[lo] == key) ? (int64_t)lo : -1;
+}
+
+__device__ __forceinline__ double sp_get(const double* M, int64_t idx, int st) { return idx < 0 ? neg_inf() : M[idx * 5 + st]; }
+
+// scoreHD / score (NTK:120-140)
+__device__ __forceinline__ double sp_score(const SparseArgs& a, double x, uint32_t kn, uint32_t kk)
+{
+	int dist = 0;
+	if (kn != kk)
+	{
+		uint32_t u = kn, v = kk;
+		for (uint32_t i = 0; i < a.k; ++i)
+		{
+			dist += ((u & 3u) != (v & 3u));
+			u >>= 2;
+			v >>= 2;
+		}
+	}
+	return score_kmer(a.c, x, kn) + score_kmer(a.c, x, kk) + (double)(-2 * dist);
+}
+
+__device__ __forceinline__ void sp_decode(const SparseArgs& a, uint64_t key, uint32_t& t, uint32_t& n, uint32_t& q)
+{
+	const uint64_t NK = (uint64_t)a.N * a.K;
+	t = (uint32_t)(key / NK);
+	const uint64_t r = key % NK;
+	n = (uint32_t)(r / a.K);
+	q = (uint32_t)(r % a.K);
+}
+
+// one pass of logF (MAXP = false) or of the MAP fill of decodeMAP (MAXP = true, NTK:814-863) over all rows
+template <bool MAXP>
+__device__ void sp_forward(const SparseArgs& a, int lane)
+{
+	const double NI = neg_inf();
+	double* M = MAXP ? a.V : a.F;
+	for (uint32_t t = 0; t < a.T; ++t)
+	{
+		const uint64_t r0 = a.rowptr[t], r1 = a.rowptr[t + 1];
+		for (uint64_t idx = r0 + lane; idx < r1; idx += 32)
+		{
+			uint32_t tt, n, q;
+			sp_decode(a, a.keys[idx], tt, n, q);
+			double va = NI, vp = NI, vs = NI, ve = NI;
+			if (t == 0 && n == 0) ve = 0.0;
+			else if (t > 0 && n > 0)
+			{
+				const double sc = MAXP ? 0.0 : sp_score(a, a.signal[t - 1], (uint32_t)a.kmers[n - 1], q);
+				const double* lp = a.LP + idx * 5;
+				for (uint32_t pre = q / 4; pre < a.K; pre += a.hp)
+				{
+					const int64_t ia = sp_find(a, t - 1, n - 1, pre), ip = sp_find(a, t - 1, n, pre);
+					if (MAXP)
+					{
+						va = fmax(va, sp_get(M, ia, 3) + lp[0]);
+						va = fmax(va, sp_get(M, ia, 4) + lp[0]);
+						vp = fmax(vp, sp_get(M, ip, 2) + lp[1]);
+						vp = fmax(vp, sp_get(M, ip, 3) + lp[1]);
+						vp = fmax(vp, sp_get(M, ip, 4) + lp[1]);
+					}
+					else
+					{
+						va = log_plus(va, sp_get(M, ia, 3) + a.tr[TA1] + sc);
+						va = log_plus(va, sp_get(M, ia, 4) + a.tr[TA2] + sc);
+						vp = log_plus(vp, sp_get(M, ip, 2) + a.tr[TP1] + sc);
+						vp = log_plus(vp, sp_get(M, ip, 3) + a.tr[TP2] + sc);
+						vp = log_plus(vp, sp_get(M, ip, 4) + a.tr[TP3] + sc);
+					}
+				}
+				const int64_t is = sp_find(a, t - 1, n - 1, q), ie = sp_find(a, t - 1, n, q);
+				if (MAXP)
+				{
+					vs = fmax(vs, sp_get(M, is, 1) + lp[2]);
+					vs = fmax(vs, sp_get(M, is, 3) + lp[2]);
+					vs = fmax(vs, sp_get(M, is, 4) + lp[2]);
+					ve = fmax(ve, sp_get(M, ie, 0) + lp[3]);
+					ve = fmax(ve, sp_get(M, ie, 1) + lp[3]);
+					ve = fmax(ve, sp_get(M, ie, 2) + lp[3]);
+					ve = fmax(ve, sp_get(M, ie, 3) + lp[3]);
+				}
+				else
+				{
+					vs = log_plus(vs, sp_get(M, is, 1) + a.tr[TS1] + sc);
+					vs = log_plus(vs, sp_get(M, is, 3) + a.tr[TS2] + sc);
+					vs = log_plus(vs, sp_get(M, is, 4) + a.tr[TS3] + sc);
+					ve = log_plus(ve, sp_get(M, ie, 0) + sc);
+					ve = log_plus(ve, sp_get(M, ie, 1) + a.tr[TE2] + sc);
+					ve = log_plus(ve, sp_get(M, ie, 2) + a.tr[TE3] + sc);
+					ve = log_plus(ve, sp_get(M, ie, 3) + a.tr[TE4] + sc);
+				}
+			}
+			double* o = M + idx * 5;
+			o[0] = va; o[1] = vp; o[2] = vs; o[3] = ve; o[4] = NI;
+		}
+		__syncwarp();
+		// the I state consumes no sample: (t, n-1, q) of the same row, an earlier key (NTK:503-505, 857-858)
+		if (lane == 0 && t > 0)
+		{
+			for (uint64_t idx = r0; idx < r1; ++idx)
+			{
+				uint32_t tt, n, q;
+				sp_decode(a, a.keys[idx], tt, n, q);
+				if (n == 0) continue;
+				const int64_t ii = sp_find(a, t, n - 1, q);
+				double vi = NI;
+				if (MAXP)
+				{
+					const double l4 = a.LP[idx * 5 + 4];
+					vi = fmax(vi, sp_get(M, ii, 3) + l4);
+					vi = fmax(vi, sp_get(M, ii, 4) + l4);
+				}
+				else
+				{
+					const double sc = sp_score(a, a.signal[t - 1], (uint32_t)a.kmers[n - 1], q);
+					vi = log_plus(vi, sp_get(M, ii, 3) + a.tr[TI1] + sc);
+					vi = log_plus(vi, sp_get(M, ii, 4) + a.tr[TI2] + sc);
+				}
+				M[idx * 5 + 4] = vi;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+// logB (NTK:517-607)
+__device__ void sp_backward(const SparseArgs& a, int lane)
+{
+	const double NI = neg_inf();
+	double* M = a.B;
+	const uint32_t T = a.T, N = a.N;
+	for (uint32_t t = T; t-- > 0;)
+	{
+		const uint64_t r0 = a.rowptr[t], r1 = a.rowptr[t + 1];
+		for (uint64_t idx = r0 + lane; idx < r1; idx += 32)
+		{
+			uint32_t tt, n, q;
+			sp_decode(a, a.keys[idx], tt, n, q);
+			double va = NI, vp = NI, vs = NI, ve = NI, vi = NI;
+			if (t == T - 1 && n == N - 1) ve = 0.0;
+			if (t < T - 1)
+			{
+				const uint32_t s0 = (q % a.hp) * 4;
+				const double x = a.signal[t];
+				if (n > 0)
+				{
+					const uint32_t kn = (uint32_t)a.kmers[n - 1];
+					double sc = sp_score(a, x, kn, q);
+					const int64_t ie = sp_find(a, t + 1, n, q);
+					const double fe = sp_get(M, ie, 3);
+					va = log_plus(va, fe + sc);
+					vp = log_plus(vp, fe + a.tr[TE2] + sc);
+					vs = log_plus(vs, fe + a.tr[TE3] + sc);
+					ve = log_plus(ve, fe + a.tr[TE4] + sc);
+					for (uint32_t suc = s0; suc < s0 + 4; ++suc)
+					{
+						sc = sp_score(a, x, kn, suc);
+						const double fp = sp_get(M, sp_find(a, t + 1, n, suc), 1);
+						vs = log_plus(vs, fp + a.tr[TP1] + sc);
+						ve = log_plus(ve, fp + a.tr[TP2] + sc);
+						vi = log_plus(vi, fp + a.tr[TP3] + sc);
+					}
+				}
+				if (n < N - 1)
+				{
+					const uint32_t kn = (uint32_t)a.kmers[n];
+					double sc = sp_score(a, x, kn, q);
+					const double fs = sp_get(M, sp_find(a, t + 1, n + 1, q), 2);
+					vp = log_plus(vp, fs + a.tr[TS1] + sc);
+					ve = log_plus(ve, fs + a.tr[TS2] + sc);
+					vi = log_plus(vi, fs + a.tr[TS3] + sc);
+					for (uint32_t suc = s0; suc < s0 + 4; ++suc)
+					{
+						sc = sp_score(a, x, kn, suc);
+						const double fa = sp_get(M, sp_find(a, t + 1, n + 1, suc), 0);
+						ve = log_plus(ve, fa + a.tr[TA1] + sc);
+						vi = log_plus(vi, fa + a.tr[TA2] + sc);
+					}
+				}
+			}
+			double* o = M + idx * 5;
+			o[0] = va; o[1] = vp; o[2] = vs; o[3] = ve; o[4] = vi;
+		}
+		__syncwarp();
+		// the I move into (t, n+1, q) of the same row, a later key: descending key order (NTK:592-598)
+		if (lane == 0 && t > 0)
+		{
+			for (uint64_t idx = r1; idx-- > r0;)
+			{
+				uint32_t tt, n, q;
+				sp_decode(a, a.keys[idx], tt, n, q);
+				if (n >= N - 1) continue;
+				const double sc = sp_score(a, a.signal[t - 1], (uint32_t)a.kmers[n], q);
+				const double fi = sp_get(M, sp_find(a, t, n + 1, q), 4);
+				double* o = M + idx * 5;
+				o[3] = log_plus(o[3], fi + a.tr[TI1] + sc);
+				o[4] = log_plus(o[4], fi + a.tr[TI2] + sc);
+			}
+		}
+		__syncwarp();
+	}
+}
+
+// formattedMedian (aligner.cpp:247-263) of v[0..m); sorts v in place
+__device__ double sp_median(double* v, uint32_t m)
+{
+	if (m == 0) return 0.0;
+	for (uint32_t i = 1; i < m; ++i)
+	{
+		const double x = v[i];
+		uint32_t j = i;
+		while (j > 0 && v[j - 1] > x)
+		{
+			v[j] = v[j - 1];
+			--j;
+		}
+		v[j] = x;
+	}
+	return (m & 1u) ? v[m / 2] : (v[m / 2 - 1] + v[m / 2]) / 2.0;
+}
+
+__device__ void sp_push_segment(const SparseArgs& a, uint32_t& ns, char state, uint64_t seqpos, uint64_t sigpos, double* prob,
+	uint32_t& np, uint32_t q)
+{
+	a.seg_state[ns] = state;
+	a.seg_seqpos[ns] = seqpos;
+	a.seg_sigpos[ns] = sigpos;
+	a.seg_prob[ns] = sp_median(prob, np);
+	a.seg_kmer[ns] = q;
+	++ns;
+	np = 0;
+}
+
+// NTKAligner::traceback (NTK:628-801), one thread
+__device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_t q)
+{
+	const double* V = a.V;
+	const double* LP = a.LP;
+	double* prob = a.prob_buf;
+	uint32_t np = 0, ns = 0;
+	int state = 3;
+	int64_t cur = sp_find(a, t, n, q);
+	const uint32_t half = a.k / 2;
+	uint64_t guard = (uint64_t)a.T + a.N + 8;
+	while (t)
+	{
+		if (guard-- == 0) return 2;
+		if (state == 3)
+		{
+			if (t == 1)
+			{
+				sp_push_segment(a, ns, 'M', half, 0, prob, np, q);
+				break;
+			}
+			const int64_t prev = sp_find(a, t - 1, n, q);
+			const double sc = sp_get(V, cur, 3), ls = sp_get(LP, cur, 3);
+			prob[np++] = exp(ls);
+			if (sc == sp_get(V, prev, 3) + ls) state = 3;
+			else if (sc == sp_get(V, prev, 0) + ls) state = 0;
+			else if (sc == sp_get(V, prev, 2) + ls) state = 2;
+			else if (sc == sp_get(V, prev, 1) + ls) state = 1;
+			--t;
+			cur = prev;
+		}
+		else if (state == 0 || state == 1)
+		{
+			const bool isA = (state == 0);
+			if (t == 1 && (!isA || n == 1))
+			{
+				sp_push_segment(a, ns, isA ? 'M' : 'P', half, 0, prob, np, q);
+				break;
+			}
+			const double sc = sp_get(V, cur, state), ls = sp_get(LP, cur, state);
+			prob[np++] = exp(ls);
+			bool moved = false;
+			for (uint32_t pre = q / 4; pre < a.K && !moved; pre += a.hp)
+			{
+				const int64_t prev = sp_find(a, t - 1, isA ? n - 1 : n, pre);
+				int nstate = -1;
+				if (sc == sp_get(V, prev, 3) + ls) nstate = 3;
+				else if (!isA && sc == sp_get(V, prev, 2) + ls) nstate = 2;
+				else if (sc == sp_get(V, prev, 4) + ls) nstate = 4;
+				if (nstate >= 0)
+				{
+					sp_push_segment(a, ns, isA ? 'M' : 'P', (uint64_t)n - 1 + half, (uint64_t)t - 1, prob, np, q);
+					state = nstate;
+					--t;
+					if (isA) --n;
+					q = pre;
+					cur = prev;
+					moved = true;
+				}
+			}
+			if (!moved) return 2;  // the reference would spin here
+		}
+		else if (state == 2)
+		{
+			if (t == 1 && n == 1) break;
+			const int64_t prev = sp_find(a, t - 1, n - 1, q);
+			const double sc = sp_get(V, cur, 2), ls = sp_get(LP, cur, 2);
+			prob[np++] = exp(ls);
+			if (sc == sp_get(V, prev, 3) + ls) state = 3;
+			else if (sc == sp_get(V, prev, 1) + ls) state = 1;
+			else if (sc == sp_get(V, prev, 4) + ls) state = 4;
+			--t;
+			--n;
+			cur = prev;
+		}
+		else
+		{
+			if (n == 1) break;
+			const int64_t prev = sp_find(a, t, n - 1, q);
+			const double sc = sp_get(V, cur, 4), ls = sp_get(LP, cur, 4);
+			prob[np++] = exp(ls);
+			if (sc == sp_get(V, prev, 4) + ls) state = 4;
+			else if (sc == sp_get(V, prev, 3) + ls) state = 3;
+			--n;
+			cur = prev;
+		}
+	}
+	*a.seg_n = ns;
+	return 0;
+}
+
+__global__ void __launch_bounds__(32) k_ntk_sparse(SparseArgs a)
+{
+	const int lane = threadIdx.x;
+	const double NI = neg_inf();
+	sp_forward<false>(a, lane);
+	sp_backward(a, lane);
+	__syncwarp();
+	// Zf, Zb (NTK:897-918): sequential log-sum-exp over q of the E state of (T-1, N-1, q) / (0, 0, q)
+	double Zf = NI, Zb = NI;
+	if (lane == 0)
+	{
+		for (uint64_t idx = a.rowptr[a.T - 1]; idx < a.rowptr[a.T]; ++idx)
+		{
+			uint32_t t, n, q;
+			sp_decode(a, a.keys[idx], t, n, q);
+			if (n == a.N - 1) Zf = log_plus(Zf, a.F[idx * 5 + 3]);
+		}
+		for (uint64_t idx = a.rowptr[0]; idx < a.rowptr[1]; ++idx)
+		{
+			uint32_t t, n, q;
+			sp_decode(a, a.keys[idx], t, n, q);
+			if (n == 0) Zb = log_plus(Zb, a.B[idx * 5 + 3]);
+		}
+		a.out_z[0] = Zf;
+		a.out_z[1] = Zb;
+	}
+	Zf = __shfl_sync(0xffffffffu, Zf, 0);
+	Zb = __shfl_sync(0xffffffffu, Zb, 0);
+	const double cells = (double)a.T * (double)a.N * (double)a.K;
+	if (fabs(Zf - Zb) / cells >= 1e-8 || isinf(Zf) || isinf(Zb))
+	{
+		if (lane == 0) *a.out_status = 1;
+		return;
+	}
+	if (lane == 0) *a.out_status = 0;
+	if (!a.calc_prob) return;
+	// sparse logP (NTK:159-177)
+	for (uint64_t i = lane; i < a.nk * 5; i += 32) a.LP[i] = a.F[i] + a.B[i] - Zb;
+	__syncwarp();
+	sp_forward<true>(a, lane);
+	__syncwarp();
+	if (lane == 0)
+	{
+		// end kmer: the LAST q whose score is >= the best so far (NTK:865-876); absent keys count as -inf
+		double best = NI;
+		uint32_t bestq = a.K - 1;
+		bool any = false;
+		for (uint64_t idx = a.rowptr[a.T - 1]; idx < a.rowptr[a.T]; ++idx)
+		{
+			uint32_t t, n, q;
+			sp_decode(a, a.keys[idx], t, n, q);
+			if (n != a.N - 1) continue;
+			const double cand = a.V[idx * 5 + 3];
+			if (cand >= best && !(isinf(cand) && cand < 0))
+			{
+				best = cand;
+				bestq = q;
+				any = true;
+			}
+		}
+		if (!any) bestq = a.K - 1;
+		const int rc = sp_traceback(a, a.T - 1, a.N - 1, bestq);
+		if (rc) *a.out_status = rc;
+	}
+}
+
 } // namespace ntk
 } // namespace dyn
 

@@ -35,7 +35,8 @@ enum
 	DYN_INTERNAL = 8,
 	DYN_BAND_UNSUPPORTED = 9, /* band wider than this build's ring capacity */
 	DYN_NTK_TN_FAILED = 11,  /* NTK_aligner_api.cpp:335  "NTK preprocessing TN failed: alignment scores do not match" */
-	DYN_NTK_TK_FAILED = 12   /* NTK_aligner_api.cpp:381  "NTK preprocessing TK failed: alignment scores do not match" */
+	DYN_NTK_TK_FAILED = 12,  /* NTK_aligner_api.cpp:381  "NTK preprocessing TK failed: alignment scores do not match" */
+	DYN_NTK_ALIGN_FAILED = 13 /* NTK_aligner_api.cpp:916  "NTK alignment failed: alignment scores do not match" */
 };
 
 typedef struct
@@ -123,8 +124,8 @@ const char* dyn_status_message(int status);
 const char* dyn_last_error(const dyn_aligner*);
 
 /* ---- resquiggle ("NTK") mode, pre-pass stages (reference NTK_aligner_api.cpp:120-441; rows B1-B6 of SURVEY.md 8a).
- * A handle created with mode "resquiggle"/"ntk" offers these stage entry points; dyn_align_batch on such a handle fails
- * until the sparse 5-state stages (NTK:443-927) are built.
+ * A handle created with mode "resquiggle"/"ntk" is served by dyn_ntk_align (one read per call: the reference's
+ * NTKAligner::align, NTK:881-927) and by the stage entry points below; the batched basic-mode entry points fail on it.
  *
  * dyn_ntk_transitions: the 14 log transition scores a1,a2,p1,p2,p3,s1,s2,s3,e1,e2,e3,e4,i1,i2 followed by
  *   log ntMatch / log ntExtend of the TN and of the TK pre-pass (NTKAligner::initializeTransitions, NTK:35-104).
@@ -136,6 +137,16 @@ const char* dyn_last_error(const dyn_aligner*);
 void dyn_ntk_transitions(const dyn_aligner*, double* out18);
 int dyn_ntk_prepass(dyn_aligner*, const float* signal, uint64_t S, const char* seq, uint64_t L, uint32_t* tn_mask,
 	uint32_t* tk_mask, uint64_t* keys, uint64_t keys_cap, uint64_t* n_keys, double* z4);
+/* dyn_ntk_align = NTKAligner::align (NTK_aligner_api.cpp:881-927) for one read: pre-passes, sparse 5-state forward /
+ * backward over the keys (logF / logB, :443-607, each result visible to later keys at once — the repair described in
+ * INTEGRATION.md; as shipped the reference throws for every input in this mode), Z check (:913-918), sparse posteriors,
+ * MAP fill and traceback (:628-879).  Output arrays hold `cap` entries (cap >= S + L is always enough); segment i has
+ * states[i] in {'M','P'}, sequence_positions[i], signal_positions[i], probabilities[i] and polish_kmers[i], the id of
+ * the polished kmer in the aligner's native order (Aligner::intToKmer, aligner.cpp:222-239, turns it into the
+ * string; RNA pores reverse it).  calc_probabilities = 0 computes Z only.  Returns 0, a dyn_status or -1. */
+int dyn_ntk_align(dyn_aligner*, const float* signal, uint64_t S, const char* seq, uint64_t L, int calc_probabilities,
+	double* Z, uint64_t* n_segments, char* states, uint64_t* sequence_positions, uint64_t* signal_positions,
+	double* probabilities, uint32_t* polish_kmers, uint64_t cap);
 
 /* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
  * last batch call: [0] encode/emission-constant kernel, [1] main DP kernel, [2] number of kernel launches */

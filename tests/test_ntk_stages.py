@@ -28,6 +28,7 @@ class NtkCase:
         if self.has_alignment:
             self.align_Z = float(g("align_Z"))
             self.signal_positions, self.states, self.polishes = g("signal_positions"), g("states"), g("polishes")
+            self.sequence_positions, self.probabilities = g("sequence_positions"), g("probabilities")
 
     @property
     def model_path(self):
@@ -107,8 +108,25 @@ def test_gpu_prepass_matches_reference(case):
     assert inter >= 0.999 * max(r["keys"].size, case.keys.size)
     if rows_tn == 1.0 and rows_tk == 1.0:
         assert np.array_equal(r["keys"], case.keys)
-    with pytest.raises(RuntimeError, match="only the pre-pass stages are built"):
-        al.align(case.signal, case.sequence, True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in load_ntk() if c.has_alignment], ids=lambda c: c.name)
+def test_gpu_ntk_alignment_matches_repaired_reference(case):
+    """End to end: pre-passes + sparse 5-state forward / backward / MAP / traceback on the GPU (dyn_ntk_align) against
+    the reference with the two-line repair of logF / logB (SURVEY.md F2): same segments, states and polish kmers;
+    Z to 1e-9 relative; probabilities to 1e-4 (north_star tolerance)."""
+    from dynamont_b200 import Aligner
+    al = Aligner(case.model_path, case.pore, mode="resquiggle")
+    r = al.align(case.signal, case.sequence, True)
+    assert abs(r["Z"] - case.align_Z) <= 1e-9 * max(1.0, abs(case.align_Z))
+    assert r["states"] == case.states.tolist()
+    assert r["polishes"] == case.polishes.tolist()
+    assert np.array_equal(r["signal_positions"], case.signal_positions)
+    assert np.array_equal(r["sequence_positions"], case.sequence_positions)
+    assert np.abs(r["probabilities"] - case.probabilities).max() <= 1e-4
+    z = al.align(case.signal, case.sequence, False)
+    assert z["Z"] == r["Z"] and len(z["states"]) == 0
 
 
 @pytest.mark.gpu
