@@ -139,3 +139,38 @@ def test_gpu_prepass_input_errors():
                           (x[:6], "ACGTACGTACGT", "Signal too short compared to sequence"), (x, "ACGTNACGTA", "Invalid nucleotide")]:
         with pytest.raises(RuntimeError, match=msg):
             al.ntk_prepass(sig, seq)
+
+
+@pytest.mark.gpu
+def test_gpu_ntk_vs_live_repaired_reference_seeded():
+    """Seeded reads (not in the golden file) against the repaired reference run live on the same box."""
+    import time
+    from oracle import Reference, _build
+    if _build.build_reference_ntkfix() is None:
+        pytest.skip("oracle/_ref/libdynamont_ref_ntkfix.so not available")
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import materialize_model, native_model, synth_read
+    path = materialize_model("rna004_5mer", MODELS_DIR)
+    nm, ns = native_model(path, "dna_r9")
+    ref = Reference(path, "dna_r9", mode="resquiggle", ntk_fix=True)
+    al = Aligner(path, "dna_r9", mode="resquiggle")
+    rng = np.random.default_rng(31)
+    t_ref = t_gpu = 0.0
+    n_seg = n_same = 0
+    for L, spb in ((40, 6), (150, 7), (90, 12)):
+        s, q, _ = synth_read(rng, nm, ns, 5, L, spb)
+        t0 = time.perf_counter()
+        o = ref.align(s, q, True)
+        t1 = time.perf_counter()
+        r = al.align(s, q, True)
+        t2 = time.perf_counter()
+        t_ref += t1 - t0
+        t_gpu += t2 - t1
+        assert abs(r["Z"] - o["Z"]) <= 1e-9 * max(1.0, abs(o["Z"]))
+        assert r["states"] == o["states"] and r["polishes"] == o["polishes"]
+        same = r["signal_positions"] == o["signal_positions"]
+        n_seg += same.size
+        n_same += int(same.sum())
+        assert np.abs(r["probabilities"] - o["probabilities"]).max() <= 1e-4
+    assert n_same >= 0.999 * n_seg
+    print("NTK 3 reads: reference %.2f s, GPU first path %.2f s" % (t_ref, t_gpu))
