@@ -122,6 +122,38 @@ class Aligner:
             raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
         return res, seqpos, sigpos, prob
 
+    # ---- front-end stages either side of the DP ------------------------------------------
+    def preprocess_batch(self, raws, shifts, scales, window: int = 3, n_sigmas: float = 3.0):
+        """(raw - shift) / scale + Hampel filter (utils.py:16-43, segment.py:151-153) on the GPU; returns float32 arrays."""
+        sig, sig_off, _, _ = self._pack(raws, [""] * len(raws), np.float32)
+        sh = np.ascontiguousarray(shifts, dtype=np.float64)
+        sc = np.ascontiguousarray(scales, dtype=np.float64)
+        out = np.empty_like(sig)
+        rc = self._lib.dyn_preprocess_batch(self._h, C.c_void_p(sig.ctypes.data), sig_off.ctypes.data_as(u64p), len(raws),
+                                            sh.ctypes.data_as(f64p), sc.ctypes.data_as(f64p), int(window), float(n_sigmas),
+                                            C.c_void_p(out.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        return [out[int(sig_off[i]):int(sig_off[i + 1])] for i in range(len(raws))]
+
+    def format_segments(self, result: dict, readid: str, signalid: str, sig_offset: int, last_index: int, read: str) -> bytes:
+        """utils.segmentation_to_string (utils.py:193-232) for one alignment result of this aligner."""
+        n = len(result["sequence_positions"])
+        seqpos = np.ascontiguousarray(result["sequence_positions"], dtype=np.uint64)
+        sigpos = np.ascontiguousarray(result["signal_positions"], dtype=np.uint64)
+        prob = np.ascontiguousarray(result["probabilities"], dtype=np.float64)
+        states = "".join(result["states"]).encode("ascii")
+        pol = result.get("polishes")
+        arr = None
+        if pol is not None:
+            arr = (C.c_char_p * max(n, 1))(*[p.encode("ascii") for p in pol])
+        args = [readid.encode(), signalid.encode(), int(sig_offset), int(last_index), read.encode("latin-1"), self.kmer_size,
+                int(self.rna), n, seqpos.ctypes.data_as(u64p), sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p), states, arr]
+        need = self._lib.dyn_format_segments(*args, None, 0)
+        buf = C.create_string_buffer(max(int(need), 1))
+        self._lib.dyn_format_segments(*args, buf, need)
+        return buf.raw[:need]
+
     # ---- resquiggle (NTK) mode: pre-pass stages (reference NTK_aligner_api.cpp:120-441) ---------------------
     def ntk_transitions(self) -> dict:
         t = np.zeros(18)

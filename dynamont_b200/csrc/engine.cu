@@ -274,7 +274,73 @@ DYN_DEV void fold_read(const FoldArgs& a, uint32_t r, int lane)
 	}
 }
 
+// Signal preprocessing of the front end, the step right before the DP: z-normalisation with the
+// basecaller's shift / scale (segment.py:151-152, train.py:168-169) and the Hampel outlier filter
+// (utils.py:16-43; window 3 / 3 sigma for segmentation, 7 / 5 sigma for training) — float64 like the numpy code,
+// rounded to FP32 (what the DP consumes) at the very end.
+struct PreprocArgs
+{
+	const float* raw;        // concatenated raw samples
+	const uint64_t* sig_off; // [n_reads + 1]
+	uint32_t n_reads;
+	const double* shift;     // [n_reads]
+	const double* scale;     // [n_reads]
+	int window;              // <= 15
+	double n_sigmas;
+	float* out;              // concatenated, same offsets
+};
+
+DYN_DEV double small_median(double* v, int m)
+{
+	for (int i = 1; i < m; ++i)
+	{
+		const double x = v[i];
+		int j = i;
+		while (j > 0 && v[j - 1] > x)
+		{
+			v[j] = v[j - 1];
+			--j;
+		}
+		v[j] = x;
+	}
+	return (m & 1) ? v[m / 2] : (v[m / 2 - 1] + v[m / 2]) / 2.0;  // numpy.median
+}
+
+DYN_DEV void preprocess_sample(const PreprocArgs& a, uint64_t g)
+{
+	// read of sample g: largest r with sig_off[r] <= g
+	uint32_t lo = 0, hi = a.n_reads;
+	while (hi - lo > 1)
+	{
+		const uint32_t mid = (lo + hi) / 2;
+		if (a.sig_off[mid] <= g) lo = mid;
+		else hi = mid;
+	}
+	const uint64_t base = a.sig_off[lo], n = a.sig_off[lo + 1] - base, i = g - base;
+	const double sh = a.shift[lo], sc = a.scale[lo];
+	const float* raw = a.raw + base;
+	const int W = a.window, h = W / 2;
+	double v = ((double)raw[i] - sh) / sc;
+	// utils.py:26-40: centres original[W//2 : n - W//2 - 1], window j = original[j : j + W]
+	if (n > (uint64_t)W && i >= (uint64_t)h && i + h + 1 < n)
+	{
+		double w[16], d[16];
+		for (int q = 0; q < W; ++q) w[q] = ((double)raw[i - h + q] - sh) / sc;
+		for (int q = 0; q < W; ++q) d[q] = w[q];
+		const double med = small_median(d, W);
+		for (int q = 0; q < W; ++q) d[q] = fabs(w[q] - med);
+		const double sigma = 1.4826 * small_median(d, W);
+		if (fabs(v - med) > a.n_sigmas * sigma) v = med;
+	}
+	a.out[g] = (float)v;
+}
+
 #ifndef DYN_HOST_EMU
+__global__ void k_preprocess(PreprocArgs a, uint64_t total)
+{
+	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x)
+		preprocess_sample(a, g);
+}
 __global__ void __launch_bounds__(32) k_encode(EncodeArgs a)
 {
 	for (uint32_t r = blockIdx.x; r < a.n_reads; r += gridDim.x) encode_read(a, r, threadIdx.x);
@@ -1206,6 +1272,88 @@ int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off
 		A->last_error = e.what();
 		return -1;
 	}
+}
+
+int dyn_preprocess_batch(dyn_aligner* A, const float* raw, const uint64_t* sig_off, uint32_t n_reads, const double* shift,
+	const double* scale, int window, double n_sigmas, float* out)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	try
+	{
+		if (window < 1 || window > 15) throw std::runtime_error("dyn_preprocess_batch: window must be in [1, 15]");
+		Rt& rt = A->rt;
+		rt.bind();
+		const uint64_t total = n_reads ? sig_off[n_reads] : 0;
+		if (!total) return 0;
+		DevBuf b_raw, b_off, b_sh, b_sc, b_out;
+		PreprocArgs pa;
+		float* d_raw = (float*)b_raw.get(rt, total * 4);
+		uint64_t* d_off = (uint64_t*)b_off.get(rt, ((size_t)n_reads + 1) * 8);
+		double* d_sh = (double*)b_sh.get(rt, (size_t)n_reads * 8);
+		double* d_sc = (double*)b_sc.get(rt, (size_t)n_reads * 8);
+		float* d_out = (float*)b_out.get(rt, total * 4);
+		rt.h2d(d_raw, raw, total * 4);
+		rt.h2d(d_off, sig_off, ((size_t)n_reads + 1) * 8);
+		rt.h2d(d_sh, shift, (size_t)n_reads * 8);
+		rt.h2d(d_sc, scale, (size_t)n_reads * 8);
+		pa.raw = d_raw; pa.sig_off = d_off; pa.n_reads = n_reads; pa.shift = d_sh; pa.scale = d_sc;
+		pa.window = window; pa.n_sigmas = n_sigmas; pa.out = d_out;
+#ifndef DYN_HOST_EMU
+		const unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)rt.sms * 32);
+		k_preprocess<<<grid, 256, 0, rt.stream>>>(pa, total);
+		CK_CUDA(cudaGetLastError());
+#else
+		for (uint64_t i = 0; i < total; ++i) preprocess_sample(pa, i);
+#endif
+		rt.d2h(out, d_out, total * 4);
+		rt.sync();
+		for (DevBuf* b : {&b_raw, &b_off, &b_sh, &b_sc, &b_out}) b->release(rt);
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		A->last_error = e.what();
+		return -1;
+	}
+}
+
+// utils.segmentation_to_string (utils.py:193-232): one CSV line per segment,
+//   readid,signalid,start,end,basepos,base,motif,state,probability(.6f),polish
+// start = signal_position + sigOffset, end = next segment's start (lastIndex for the last one); for RNA reads the motif
+// is reversed and basepos counted from the other end; polish "NA" when empty.  Host-side formatting.
+int64_t dyn_format_segments(const char* readid, const char* signalid, int64_t sig_offset, int64_t last_index, const char* read,
+	int kmer_size, int rna, uint64_t n_segments, const uint64_t* sequence_positions, const uint64_t* signal_positions,
+	const double* probabilities, const char* states, const char* const* polishes, char* out, uint64_t out_cap)
+{
+	const std::string rd(read);
+	std::string buf;
+	buf.reserve(n_segments * 96);
+	char num[64];
+	for (uint64_t i = 0; i < n_segments; ++i)
+	{
+		int64_t basepos = (int64_t)sequence_positions[i];
+		const int64_t start = (int64_t)signal_positions[i] + sig_offset;
+		const int64_t end = (i + 1 < n_segments) ? (int64_t)signal_positions[i + 1] + sig_offset : last_index;
+		const int64_t m0 = std::max<int64_t>(0, basepos - kmer_size / 2);
+		const int64_t m1 = std::min<int64_t>((int64_t)rd.size(), basepos + kmer_size / 2 + 1);
+		std::string motif = m1 > m0 ? rd.substr((size_t)m0, (size_t)(m1 - m0)) : std::string();
+		const char base = rd[(size_t)basepos];
+		if (rna)
+		{
+			std::reverse(motif.begin(), motif.end());
+			basepos = (int64_t)rd.size() - basepos - 1;
+		}
+		buf += readid; buf += ','; buf += signalid; buf += ',';
+		buf += std::to_string(start); buf += ','; buf += std::to_string(end); buf += ','; buf += std::to_string(basepos); buf += ',';
+		buf += base; buf += ','; buf += motif; buf += ','; buf += states[i]; buf += ',';
+		snprintf(num, sizeof num, "%.6f", probabilities[i]);
+		buf += num; buf += ',';
+		const char* pol = polishes ? polishes[i] : nullptr;
+		buf += (pol && pol[0]) ? pol : "NA";
+		buf += '\n';
+	}
+	if (out && buf.size() <= out_cap) std::memcpy(out, buf.data(), buf.size());
+	return (int64_t)buf.size();
 }
 
 void dyn_ntk_transitions(const dyn_aligner* A, double* out18) { std::memcpy(out18, A->ntk_trans, sizeof(A->ntk_trans)); }

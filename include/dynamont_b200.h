@@ -123,6 +123,19 @@ const char* dyn_status_message(int status);
 /* message of the last runtime failure on this handle */
 const char* dyn_last_error(const dyn_aligner*);
 
+/* ---- front-end stages either side of the DP ------------------------------------------------
+ * dyn_preprocess_batch: (raw - shift) / scale followed by the Hampel outlier filter (utils.py:16-43; segment.py:151-153
+ *   uses window 3 / 3 sigma, train.py:168-170 window 7 / 5 sigma), computed on the GPU in float64 like the numpy code
+ *   and rounded to FP32, the sample type the DP entry points take.  raw / out: concatenated samples with sig_off[n+1].
+ * dyn_format_segments: utils.segmentation_to_string (utils.py:193-232) — the CSV lines of one read
+ *   "readid,signalid,start,end,basepos,base,motif,state,prob(.6f),polish\n"; polishes may be NULL (basic mode: "NA").
+ *   Returns the byte length (the text is written when it fits out_cap). */
+int dyn_preprocess_batch(dyn_aligner*, const float* raw, const uint64_t* sig_off, uint32_t n_reads, const double* shift,
+	const double* scale, int window, double n_sigmas, float* out);
+int64_t dyn_format_segments(const char* readid, const char* signalid, int64_t sig_offset, int64_t last_index, const char* read,
+	int kmer_size, int rna, uint64_t n_segments, const uint64_t* sequence_positions, const uint64_t* signal_positions,
+	const double* probabilities, const char* states, const char* const* polishes, char* out, uint64_t out_cap);
+
 /* ---- resquiggle ("NTK") mode, pre-pass stages (reference NTK_aligner_api.cpp:120-441; rows B1-B6 of SURVEY.md 8a).
  * A handle created with mode "resquiggle"/"ntk" is served by dyn_ntk_align (one read per call: the reference's
  * NTKAligner::align, NTK:881-927) and by the stage entry points below; the batched basic-mode entry points fail on it.
