@@ -1440,7 +1440,7 @@ int ntk_prepass_device(dyn_aligner* A, const float* signal, uint64_t S, const ch
 	pa.c.m = A->ntk_trans[14]; pa.c.e = A->ntk_trans[15];
 	pa.fM = d_lat; pa.fE = d_lat + (size_t)T * N; pa.bM = d_lat + (size_t)2 * T * N; pa.bE = d_lat + (size_t)3 * T * N;
 	pa.LP = d_lat + (size_t)4 * T * N; pa.z = d_z;
-	k_tn_fill<<<1, 1024, 0, rt.stream>>>(pa);
+	k_tn_fill<<<2, 1024, 0, rt.stream>>>(pa);
 	CK_CUDA(cudaGetLastError());
 	rt.d2h(z, d_z, 16);
 	rt.sync();
@@ -1453,7 +1453,7 @@ int ntk_prepass_device(dyn_aligner* A, const float* signal, uint64_t S, const ch
 	pa.c.m = A->ntk_trans[16]; pa.c.e = A->ntk_trans[17];
 	pa.fM = d_lat; pa.fE = d_lat + (size_t)T * K; pa.bM = d_lat + (size_t)2 * T * K; pa.bE = d_lat + (size_t)3 * T * K;
 	pa.LP = d_lat + (size_t)4 * T * K; pa.z = d_z + 2;
-	k_tk_fill<<<1, 1024, 0, rt.stream>>>(pa);
+	k_tk_fill<<<2, 1024, 0, rt.stream>>>(pa);
 	CK_CUDA(cudaGetLastError());
 	rt.d2h(z + 2, d_z + 2, 16);
 	rt.sync();
@@ -1570,6 +1570,7 @@ int dyn_ntk_align(dyn_aligner* A, const float* signal, uint64_t S, const char* s
 			sa.seg_state = (char*)(d_seg + o_state); sa.seg_seqpos = (uint64_t*)(d_seg + o_seq); sa.seg_sigpos = (uint64_t*)(d_seg + o_sig);
 			sa.seg_prob = (double*)(d_seg + o_pr); sa.seg_kmer = (uint32_t*)(d_seg + o_km); sa.prob_buf = (double*)(d_seg + o_buf);
 			sa.calc_prob = calc_probabilities;
+			k_ntk_sparse_fb<<<2, 32, 0, rt.stream>>>(sa);
 			k_ntk_sparse<<<1, 32, 0, rt.stream>>>(sa);
 			CK_CUDA(cudaGetLastError());
 			std::vector<unsigned char> h(o);

@@ -69,24 +69,25 @@ struct PrepassArgs
 };
 
 // ---- TN pre-pass (ppForTN / ppBackTN, NTK:197-251): dense T x N, no band ------------------------------------
+// grid = 2 CTAs: block 0 runs the forward recurrence, block 1 the backward one (they are independent)
 __global__ void __launch_bounds__(1024) k_tn_fill(PrepassArgs a)
 {
 	const uint32_t T = a.T, N = a.N;
 	const double NI = neg_inf();
-	for (size_t i = threadIdx.x; i < (size_t)T * N; i += blockDim.x)
+	const bool fwd = (blockIdx.x == 0);
 	{
-		a.fM[i] = NI;
-		a.fE[i] = NI;
-		a.bM[i] = NI;
-		a.bE[i] = NI;
+		double* M = fwd ? a.fM : a.bM;
+		double* E = fwd ? a.fE : a.bE;
+		for (size_t i = threadIdx.x; i < (size_t)T * N; i += blockDim.x)
+		{
+			M[i] = NI;
+			E[i] = NI;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) E[fwd ? 0 : (size_t)T * N - 1] = 0.0;
+		__syncthreads();
 	}
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		a.fE[0] = 0.0;
-		a.bE[(size_t)T * N - 1] = 0.0;
-	}
-	__syncthreads();
+	if (fwd)
 	for (uint32_t t = 1; t < T; ++t)
 	{
 		const double x = a.signal[t - 1];
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(1024) k_tn_fill(PrepassArgs a)
 		}
 		__syncthreads();
 	}
+	else
 	for (uint32_t t = T - 1; t-- > 0;)
 	{
 		const double x = a.signal[t];
@@ -125,30 +127,31 @@ __global__ void __launch_bounds__(1024) k_tn_fill(PrepassArgs a)
 	}
 	if (threadIdx.x == 0)
 	{
-		a.z[0] = a.fE[(size_t)T * N - 1];  // Zf (NTK:328)
-		a.z[1] = a.bE[0];                  // Zb (NTK:329)
+		if (fwd) a.z[0] = a.fE[(size_t)T * N - 1];  // Zf (NTK:328)
+		else a.z[1] = a.bE[0];                      // Zb (NTK:329)
 	}
 }
 
 // ---- TK pre-pass (ppForTK / ppBackTK, NTK:253-313): two-state HMM over the de-Bruijn graph of all K kmers ----
+// grid = 2 CTAs: block 0 forward, block 1 backward
 __global__ void __launch_bounds__(1024) k_tk_fill(PrepassArgs a)
 {
 	const uint32_t T = a.T, K = a.K, hp = a.hp;
 	const double NI = neg_inf();
-	for (size_t i = threadIdx.x; i < (size_t)T * K; i += blockDim.x)
+	const bool fwd = (blockIdx.x == 0);
 	{
-		a.fM[i] = NI;
-		a.fE[i] = NI;
-		a.bM[i] = NI;
-		a.bE[i] = NI;
+		double* M = fwd ? a.fM : a.bM;
+		double* E = fwd ? a.fE : a.bE;
+		for (size_t i = threadIdx.x; i < (size_t)T * K; i += blockDim.x)
+		{
+			M[i] = NI;
+			E[i] = NI;
+		}
+		__syncthreads();
+		for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) E[(fwd ? 0 : (size_t)(T - 1) * K) + k] = 0.0;
+		__syncthreads();
 	}
-	__syncthreads();
-	for (uint32_t k = threadIdx.x; k < K; k += blockDim.x)
-	{
-		a.fE[k] = 0.0;
-		a.bE[(size_t)(T - 1) * K + k] = 0.0;
-	}
-	__syncthreads();
+	if (fwd)
 	for (uint32_t t = 1; t < T; ++t)
 	{
 		const double x = a.signal[t - 1];
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(1024) k_tk_fill(PrepassArgs a)
 		}
 		__syncthreads();
 	}
+	else
 	for (uint32_t t = T - 1; t-- > 0;)
 	{
 		const double x = a.signal[t];
@@ -187,15 +191,10 @@ __global__ void __launch_bounds__(1024) k_tk_fill(PrepassArgs a)
 	if (threadIdx.x == 0)
 	{
 		// sequential log-sum-exp in the reference's order (NTK:372-376)
-		double Zf = NI, Zb = NI;
+		double Z = NI;
 		const size_t TK = (size_t)T * K;
-		for (uint32_t k = 0; k < K; ++k)
-		{
-			Zf = log_plus(Zf, a.fE[TK - 1 - k]);
-			Zb = log_plus(Zb, a.bE[k]);
-		}
-		a.z[0] = Zf;
-		a.z[1] = Zb;
+		for (uint32_t k = 0; k < K; ++k) Z = log_plus(Z, fwd ? a.fE[TK - 1 - k] : a.bE[k]);
+		a.z[fwd ? 0 : 1] = Z;
 	}
 }
 
@@ -704,13 +703,17 @@ __device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_
 	return 0;
 }
 
+// logF and logB are independent: grid = 2 single-warp CTAs
+__global__ void __launch_bounds__(32) k_ntk_sparse_fb(SparseArgs a)
+{
+	if (blockIdx.x == 0) sp_forward<false>(a, threadIdx.x);
+	else sp_backward(a, threadIdx.x);
+}
+
 __global__ void __launch_bounds__(32) k_ntk_sparse(SparseArgs a)
 {
 	const int lane = threadIdx.x;
 	const double NI = neg_inf();
-	sp_forward<false>(a, lane);
-	sp_backward(a, lane);
-	__syncwarp();
 	// Zf, Zb (NTK:897-918): sequential log-sum-exp over q of the E state of (T-1, N-1, q) / (0, 0, q)
 	double Zf = NI, Zb = NI;
 	if (lane == 0)
