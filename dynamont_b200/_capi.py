@@ -32,7 +32,7 @@ EXPORTS = [
     "dyn_create", "dyn_destroy", "dyn_kmer_size", "dyn_num_kmers", "dyn_is_rna", "dyn_model", "dyn_set_model",
     "dyn_transitions", "dyn_count_segments", "dyn_read_cells", "dyn_batch_cells", "dyn_align_batch", "dyn_align_batch_f64",
     "dyn_align_batch_device", "dyn_train_batch", "dyn_status_message", "dyn_last_error", "dyn_last_timing",
-    "dyn_last_fallbacks", "dyn_ntk_transitions", "dyn_ntk_prepass", "dyn_ntk_align", "dyn_preprocess_batch", "dyn_format_segments", "dyn_set_option", "dyn_set_stream",
+    "dyn_last_fallbacks", "dyn_ntk_transitions", "dyn_ntk_prepass", "dyn_ntk_align", "dyn_ntk_align_batch", "dyn_preprocess_batch", "dyn_format_segments", "dyn_set_option", "dyn_set_stream",
 ]
 
 _libs: dict = {}
@@ -83,6 +83,8 @@ def load(path: str | None = None) -> C.CDLL:
                                     C.c_uint64, u64p, f64p]
     lib.dyn_ntk_align.argtypes = [vp, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_int, C.POINTER(C.c_double), u64p,
                                   C.c_char_p, u64p, u64p, f64p, C.c_void_p, C.c_uint64]
+    lib.dyn_ntk_align_batch.argtypes = [vp, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint32, C.c_int, C.c_void_p, f64p, u64p, u64p,
+                                        C.c_void_p, u64p, u64p, f64p, C.c_void_p, C.c_int]
     lib.dyn_preprocess_batch.argtypes = [vp, C.c_void_p, u64p, C.c_uint32, f64p, f64p, C.c_int, C.c_double, C.c_void_p]
     lib.dyn_format_segments.restype = C.c_int64
     lib.dyn_format_segments.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.c_char_p, C.c_int, C.c_int, C.c_uint64,

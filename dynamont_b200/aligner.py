@@ -226,6 +226,8 @@ class Aligner:
         reads the reference would have thrown on (``raise_errors`` re-raises the first)."""
         n = len(signals)
         assert len(sequences) == n
+        if self._ntk:
+            return self._ntk_align_batch(signals, sequences, calc_probabilities, raise_errors)
         dtype = np.float64 if any(np.asarray(s).dtype == np.float64 for s in signals) else np.float32
         sig, sig_off, seq, seq_off = self._pack(signals, sequences, dtype)
         res = (ReadResult * max(n, 1))()
@@ -269,6 +271,45 @@ class Aligner:
             return self._ntk_align(sig, sequence, calc_probabilities)
         return self.align_batch([np.ascontiguousarray(sig, dtype=np.float64)], [sequence], calc_probabilities,
                                 raise_errors=True)[0]
+
+    def _ntk_align_batch(self, signals, sequences, calc_probabilities: bool, raise_errors: bool, concurrency: int = 0):
+        """dyn_ntk_align_batch: independent reads on a pool of CUDA streams."""
+        n = len(signals)
+        sig, sig_off, seq, seq_off = self._pack(signals, sequences, np.float32)
+        caps = (np.diff(sig_off.astype(np.int64)) + np.diff(seq_off.astype(np.int64)) + 16).astype(np.uint64)
+        out_off = np.concatenate(([0], np.cumsum(caps))).astype(np.uint64)
+        tot = int(out_off[-1])
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        Z = np.zeros(max(n, 1))
+        ns = np.zeros(max(n, 1), dtype=np.uint64)
+        states = np.zeros(max(tot, 1), dtype=np.uint8)
+        seqpos = np.zeros(max(tot, 1), dtype=np.uint64)
+        sigpos = np.zeros(max(tot, 1), dtype=np.uint64)
+        prob = np.zeros(max(tot, 1))
+        pk = np.zeros(max(tot, 1), dtype=np.uint32)
+        rc = self._lib.dyn_ntk_align_batch(
+            self._h, C.c_void_p(sig.ctypes.data), sig_off.ctypes.data_as(u64p), C.cast(C.c_char_p(seq), C.c_void_p),
+            seq_off.ctypes.data_as(u64p), n, int(calc_probabilities), C.c_void_p(status.ctypes.data), Z.ctypes.data_as(f64p),
+            ns.ctypes.data_as(u64p), out_off.ctypes.data_as(u64p), C.c_void_p(states.ctypes.data), seqpos.ctypes.data_as(u64p),
+            sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p), C.c_void_p(pk.ctypes.data), int(concurrency))
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        out = []
+        for i in range(n):
+            if status[i] != 0:
+                msg = self._lib.dyn_status_message(int(status[i])).decode()
+                if status[i] == 4:
+                    msg += next((ch for ch in sequences[i] if ch not in "ACGTUacgtu"), "?")
+                e = RuntimeError(msg)
+                if raise_errors:
+                    raise e
+                out.append(e)
+                continue
+            a, b = int(out_off[i]), int(out_off[i]) + int(ns[i])
+            out.append({"Z": float(Z[i]), "sequence_positions": seqpos[a:b].copy(), "signal_positions": sigpos[a:b].copy(),
+                        "probabilities": prob[a:b].copy(), "states": [chr(c) for c in states[a:b]],
+                        "polishes": [self._int_to_kmer(int(q)) for q in pk[a:b]]})
+        return out
 
     def _int_to_kmer(self, q: int) -> str:
         """Aligner::intToKmer (aligner.cpp:222-239): base-4 digits, most significant first; reversed for RNA pores."""

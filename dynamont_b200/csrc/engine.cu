@@ -10,6 +10,7 @@
 #include "ntk_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -18,6 +19,8 @@
 #include <numeric>
 #include <set>
 #include <sstream>
+#include <thread>
+#include <atomic>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -74,13 +77,19 @@ struct Rt
 			if (v) cudaEventDestroy(v);
 	}
 	void bind() { CK_CUDA(cudaSetDevice(device)); }
+	bool async_alloc = false;  // stream-ordered allocation: no device-wide synchronisation (worker pools)
 	void* dmalloc(size_t n)
 	{
 		void* p = nullptr;
-		CK_CUDA(cudaMalloc(&p, n ? n : 1));
+		if (async_alloc) CK_CUDA(cudaMallocAsync(&p, n ? n : 1, stream));
+		else CK_CUDA(cudaMalloc(&p, n ? n : 1));
 		return p;
 	}
-	void dfree(void* p) { cudaFree(p); }
+	void dfree(void* p)
+	{
+		if (async_alloc) cudaFreeAsync(p, stream);
+		else cudaFree(p);
+	}
 	void h2d(void* d, const void* h, size_t n) { CK_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream)); }
 	void d2h(void* h, const void* d, size_t n) { CK_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream)); }
 	void zero(void* d, size_t n) { CK_CUDA(cudaMemsetAsync(d, 0, n, stream)); }
@@ -106,6 +115,7 @@ struct Rt
 {
 	int device = 0;
 	int sms = 2;
+	bool async_alloc = false;
 	size_t smem_optin = 227 * 1024;
 	double tm[6] = {0, 0, 0, 0, 0, 0};
 	void init(int) {}
@@ -430,8 +440,9 @@ struct DevBuf
 			if (p) rt.dfree(p);
 			p = nullptr;
 			cap = 0;
-			p = rt.dmalloc(n);
-			cap = n;
+			const size_t want = rt.async_alloc ? n + n / 2 : n;  // worker pools see varying sizes: grow with slack
+			p = rt.dmalloc(want);
+			cap = want;
 		}
 		return p;
 	}
@@ -1379,10 +1390,9 @@ struct NtkRun
 
 // validation + kmer encoding + TN / TK pre-passes + row masks + keys (NTK_aligner_api.cpp:197-441), all on the device.
 // Returns a dyn_status; throws on CUDA errors.
-int ntk_prepass_device(dyn_aligner* A, const float* signal, uint64_t S, const char* seq, uint64_t L, NtkRun& R)
+int ntk_prepass_device(dyn_aligner* A, Rt& rt, const float* signal, uint64_t S, const char* seq, uint64_t L, NtkRun& R)
 {
 	using namespace dyn::ntk;
-	Rt& rt = A->rt;
 	rt.bind();
 	// Aligner::validateInput (aligner.cpp:145-164) and sequenceToKmers (:166-205)
 	if (S < 1) return DYN_SIGNAL_EMPTY;
@@ -1504,7 +1514,7 @@ int dyn_ntk_prepass(dyn_aligner* A, const float* signal, uint64_t S, const char*
 	NtkRun R;
 	try
 	{
-		const int st = ntk_prepass_device(A, signal, S, seq, L, R);
+		const int st = ntk_prepass_device(A, A->rt, signal, S, seq, L, R);
 		if (st == 0)
 		{
 			Rt& rt = A->rt;
@@ -1527,6 +1537,85 @@ int dyn_ntk_prepass(dyn_aligner* A, const float* signal, uint64_t S, const char*
 #endif
 }
 
+#ifndef DYN_HOST_EMU
+namespace
+{
+
+// NTKAligner::align for one read on the stream of `rt`, with the (reusable) device buffers of R.  Returns a dyn_status;
+// throws on CUDA errors.
+int ntk_align_one(dyn_aligner* A, Rt& rt, NtkRun& R, const float* signal, uint64_t S, const char* seq, uint64_t L,
+	int calc_probabilities, double* Z, uint64_t* n_segments, char* states, uint64_t* sequence_positions,
+	uint64_t* signal_positions, double* probabilities, uint32_t* polish_kmers, uint64_t cap)
+{
+	using namespace dyn::ntk;
+	if (n_segments) *n_segments = 0;
+	static const bool trace = getenv("DYN_NTK_TRACE") != nullptr;
+	const auto c0 = std::chrono::steady_clock::now();
+	int st = ntk_prepass_device(A, rt, signal, S, seq, L, R);
+	if (st != 0) return st;
+	const auto c1 = std::chrono::steady_clock::now();
+	const uint64_t nk = std::max<uint64_t>(R.total, 1);
+	const uint32_t T = R.T, N = R.N;
+	// F, B, LP, V [nk][5] doubles; Z[2]; status; segment arrays [T + N]
+	const size_t segcap = (size_t)T + N + 8;
+	const size_t sparse_bytes = nk * 5 * 8 * 4;
+	double* d_sparse = (double*)R.b_sparse.get(rt, sparse_bytes);
+	size_t o = 0;
+	auto carve = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 16); return at; };
+	const size_t o_z = carve(16), o_st = carve(4), o_ns = carve(4), o_state = carve(segcap), o_seq = carve(segcap * 8),
+				 o_sig = carve(segcap * 8), o_pr = carve(segcap * 8), o_km = carve(segcap * 4), o_buf = carve(segcap * 8);
+	unsigned char* d_seg = (unsigned char*)R.b_seg.get(rt, o);
+	rt.zero(d_seg, o);
+	SparseArgs sa;
+	sa.signal = (const double*)R.b_sig.p; sa.kmers = (const int32_t*)R.b_kmers.p;
+	sa.keys = (const uint64_t*)R.b_keys.p; sa.rowptr = (const uint64_t*)R.b_cnt.p; sa.nk = R.total;
+	sa.T = T; sa.N = N; sa.K = R.K; sa.hp = R.hp; sa.k = (uint32_t)A->k;
+	sa.c = R.consts;
+	for (int i = 0; i < 14; ++i) sa.tr[i] = A->ntk_trans[i];
+	sa.F = d_sparse; sa.B = d_sparse + nk * 5; sa.LP = d_sparse + nk * 10; sa.V = d_sparse + nk * 15;
+	sa.out_z = (double*)(d_seg + o_z); sa.out_status = (int32_t*)(d_seg + o_st); sa.seg_n = (uint32_t*)(d_seg + o_ns);
+	sa.seg_state = (char*)(d_seg + o_state); sa.seg_seqpos = (uint64_t*)(d_seg + o_seq); sa.seg_sigpos = (uint64_t*)(d_seg + o_sig);
+	sa.seg_prob = (double*)(d_seg + o_pr); sa.seg_kmer = (uint32_t*)(d_seg + o_km); sa.prob_buf = (double*)(d_seg + o_buf);
+	sa.calc_prob = calc_probabilities;
+	k_ntk_sparse_fb<<<2, 32, 0, rt.stream>>>(sa);
+	k_ntk_sparse<<<1, 32, 0, rt.stream>>>(sa);
+	CK_CUDA(cudaGetLastError());
+	std::vector<unsigned char> h(o);
+	rt.d2h(h.data(), d_seg, o);
+	rt.sync();
+	if (trace)
+	{
+		const auto c2 = std::chrono::steady_clock::now();
+		fprintf(stderr, "ntk read T=%u keys=%llu: prepass %.1f ms, sparse %.1f ms\n", T, (unsigned long long)R.total,
+			std::chrono::duration<double, std::milli>(c1 - c0).count(), std::chrono::duration<double, std::milli>(c2 - c1).count());
+	}
+	const double* hz = (const double*)(h.data() + o_z);
+	const int32_t kst = *(const int32_t*)(h.data() + o_st);
+	if (kst == 1) return DYN_NTK_ALIGN_FAILED;  // NTK:913-918
+	if (kst != 0) return DYN_INTERNAL;
+	if (Z) *Z = hz[1];  // result.Z = Zb (NTK:920)
+	const uint32_t ns = *(const uint32_t*)(h.data() + o_ns);
+	if (calc_probabilities)
+	{
+		if (ns > cap) return DYN_INTERNAL;
+		// the traceback emits segments from the end of the read: reverse (NTK:800)
+		for (uint32_t i = 0; i < ns; ++i)
+		{
+			const uint32_t j = ns - 1 - i;
+			states[i] = ((const char*)(h.data() + o_state))[j];
+			sequence_positions[i] = ((const uint64_t*)(h.data() + o_seq))[j];
+			signal_positions[i] = ((const uint64_t*)(h.data() + o_sig))[j];
+			probabilities[i] = ((const double*)(h.data() + o_pr))[j];
+			polish_kmers[i] = ((const uint32_t*)(h.data() + o_km))[j];
+		}
+		if (n_segments) *n_segments = ns;
+	}
+	return 0;
+}
+
+} // namespace
+#endif
+
 int dyn_ntk_align(dyn_aligner* A, const float* signal, uint64_t S, const char* seq, uint64_t L, int calc_probabilities,
 	double* Z, uint64_t* n_segments, char* states, uint64_t* sequence_positions, uint64_t* signal_positions,
 	double* probabilities, uint32_t* polish_kmers, uint64_t cap)
@@ -1541,75 +1630,79 @@ int dyn_ntk_align(dyn_aligner* A, const float* signal, uint64_t S, const char* s
 	NtkRun R;
 	try
 	{
-		using namespace dyn::ntk;
-		Rt& rt = A->rt;
-		if (n_segments) *n_segments = 0;
-		int st = ntk_prepass_device(A, signal, S, seq, L, R);
-		if (st == 0)
-		{
-			const uint64_t nk = std::max<uint64_t>(R.total, 1);
-			const uint32_t T = R.T, N = R.N;
-			// F, B, LP, V [nk][5] doubles; Z[2]; status; segment arrays [T + N]
-			const size_t segcap = (size_t)T + N + 8;
-			const size_t sparse_bytes = nk * 5 * 8 * 4;
-			double* d_sparse = (double*)R.b_sparse.get(rt, sparse_bytes);
-			size_t o = 0;
-			auto carve = [&](size_t bytes) { const size_t at = o; o = align_up(o + bytes, 16); return at; };
-			const size_t o_z = carve(16), o_st = carve(4), o_ns = carve(4), o_state = carve(segcap), o_seq = carve(segcap * 8),
-						 o_sig = carve(segcap * 8), o_pr = carve(segcap * 8), o_km = carve(segcap * 4), o_buf = carve(segcap * 8);
-			unsigned char* d_seg = (unsigned char*)R.b_seg.get(rt, o);
-			rt.zero(d_seg, o);
-			SparseArgs sa;
-			sa.signal = (const double*)R.b_sig.p; sa.kmers = (const int32_t*)R.b_kmers.p;
-			sa.keys = (const uint64_t*)R.b_keys.p; sa.rowptr = (const uint64_t*)R.b_cnt.p; sa.nk = R.total;
-			sa.T = T; sa.N = N; sa.K = R.K; sa.hp = R.hp; sa.k = (uint32_t)A->k;
-			sa.c = R.consts;
-			for (int i = 0; i < 14; ++i) sa.tr[i] = A->ntk_trans[i];
-			sa.F = d_sparse; sa.B = d_sparse + nk * 5; sa.LP = d_sparse + nk * 10; sa.V = d_sparse + nk * 15;
-			sa.out_z = (double*)(d_seg + o_z); sa.out_status = (int32_t*)(d_seg + o_st); sa.seg_n = (uint32_t*)(d_seg + o_ns);
-			sa.seg_state = (char*)(d_seg + o_state); sa.seg_seqpos = (uint64_t*)(d_seg + o_seq); sa.seg_sigpos = (uint64_t*)(d_seg + o_sig);
-			sa.seg_prob = (double*)(d_seg + o_pr); sa.seg_kmer = (uint32_t*)(d_seg + o_km); sa.prob_buf = (double*)(d_seg + o_buf);
-			sa.calc_prob = calc_probabilities;
-			k_ntk_sparse_fb<<<2, 32, 0, rt.stream>>>(sa);
-			k_ntk_sparse<<<1, 32, 0, rt.stream>>>(sa);
-			CK_CUDA(cudaGetLastError());
-			std::vector<unsigned char> h(o);
-			rt.d2h(h.data(), d_seg, o);
-			rt.sync();
-			const double* hz = (const double*)(h.data() + o_z);
-			const int32_t kst = *(const int32_t*)(h.data() + o_st);
-			if (kst == 1) st = DYN_NTK_ALIGN_FAILED;  // NTK:913-918
-			else if (kst != 0) st = DYN_INTERNAL;
-			else
-			{
-				if (Z) *Z = hz[1];  // result.Z = Zb (NTK:920)
-				const uint32_t ns = *(const uint32_t*)(h.data() + o_ns);
-				if (calc_probabilities)
-				{
-					if (ns > cap) st = DYN_INTERNAL;
-					else
-					{
-						// the traceback emits segments from the end of the read: reverse (NTK:800)
-						for (uint32_t i = 0; i < ns; ++i)
-						{
-							const uint32_t j = ns - 1 - i;
-							states[i] = ((const char*)(h.data() + o_state))[j];
-							sequence_positions[i] = ((const uint64_t*)(h.data() + o_seq))[j];
-							signal_positions[i] = ((const uint64_t*)(h.data() + o_sig))[j];
-							probabilities[i] = ((const double*)(h.data() + o_pr))[j];
-							polish_kmers[i] = ((const uint32_t*)(h.data() + o_km))[j];
-						}
-						if (n_segments) *n_segments = ns;
-					}
-				}
-			}
-		}
+		const int st = ntk_align_one(A, A->rt, R, signal, S, seq, L, calc_probabilities, Z, n_segments, states,
+			sequence_positions, signal_positions, probabilities, polish_kmers, cap);
 		R.release(A->rt);
 		return st;
 	}
 	catch (const std::exception& e)
 	{
 		R.release(A->rt);
+		A->last_error = e.what();
+		return -1;
+	}
+#endif
+}
+
+int dyn_ntk_align_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
+	uint32_t n_reads, int calc_probabilities, int32_t* status, double* Z, uint64_t* n_segments, const uint64_t* out_off,
+	char* states, uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities, uint32_t* polish_kmers,
+	int concurrency)
+{
+#ifdef DYN_HOST_EMU
+	(void)signal; (void)sig_off; (void)seq; (void)seq_off; (void)n_reads; (void)calc_probabilities; (void)status; (void)Z;
+	(void)n_segments; (void)out_off; (void)states; (void)sequence_positions; (void)signal_positions; (void)probabilities;
+	(void)polish_kmers; (void)concurrency;
+	A->last_error = "dyn_ntk_align_batch: not available in the emulator build";
+	return -1;
+#else
+	std::lock_guard<std::mutex> g(A->mu);
+	try
+	{
+		// Reads are independent: a pool of host threads, each with its own CUDA stream and its own (reused) device
+		// buffers, pulls reads from a queue, so that the small per-read grids of many reads overlap on the device.
+		const int workers = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(concurrency > 0 ? concurrency : 32), n_reads));
+		std::atomic<uint32_t> next(0);
+		std::vector<std::string> errors(workers);
+		auto work = [&](int wi) {
+			Rt rt = A->rt;  // same device; own stream, own events unused
+			NtkRun R;
+			try
+			{
+				CK_CUDA(cudaSetDevice(rt.device));
+				CK_CUDA(cudaStreamCreateWithFlags(&rt.stream, cudaStreamNonBlocking));
+				rt.async_alloc = true;
+				while (true)
+				{
+					const uint32_t r = next.fetch_add(1);
+					if (r >= n_reads) break;
+					const uint64_t S = sig_off[r + 1] - sig_off[r], L = seq_off[r + 1] - seq_off[r];
+					const uint64_t o = out_off[r], cap = out_off[r + 1] - out_off[r];
+					status[r] = ntk_align_one(A, rt, R, signal + sig_off[r], S, seq + seq_off[r], L, calc_probabilities, Z + r,
+						n_segments + r, states + o, sequence_positions + o, signal_positions + o, probabilities + o,
+						polish_kmers + o, cap);
+				}
+			}
+			catch (const std::exception& e)
+			{
+				errors[wi] = e.what();
+			}
+			R.release(rt);
+			if (rt.stream)
+			{
+				cudaStreamSynchronize(rt.stream);
+				cudaStreamDestroy(rt.stream);
+			}
+		};
+		std::vector<std::thread> pool;
+		for (int wi = 0; wi < workers; ++wi) pool.emplace_back(work, wi);
+		for (auto& th : pool) th.join();
+		for (const std::string& e : errors)
+			if (!e.empty()) throw std::runtime_error(e);
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
 		A->last_error = e.what();
 		return -1;
 	}

@@ -160,6 +160,14 @@ int dyn_ntk_prepass(dyn_aligner*, const float* signal, uint64_t S, const char* s
 int dyn_ntk_align(dyn_aligner*, const float* signal, uint64_t S, const char* seq, uint64_t L, int calc_probabilities,
 	double* Z, uint64_t* n_segments, char* states, uint64_t* sequence_positions, uint64_t* signal_positions,
 	double* probabilities, uint32_t* polish_kmers, uint64_t cap);
+/* The same for a batch of independent reads (inputs laid out like dyn_align_batch): read r writes status[r], Z[r],
+ * n_segments[r] and its segments at [out_off[r], out_off[r+1]) of the output arrays (out_off[r+1] - out_off[r] >=
+ * S_r + L_r + 16).  `concurrency` host threads (0 = 32), each with its own CUDA stream and device buffers, process
+ * the reads so that their small grids overlap on the device.  Returns 0, or -1 on a CUDA/runtime error. */
+int dyn_ntk_align_batch(dyn_aligner*, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
+	uint32_t n_reads, int calc_probabilities, int32_t* status, double* Z, uint64_t* n_segments, const uint64_t* out_off,
+	char* states, uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities, uint32_t* polish_kmers,
+	int concurrency);
 
 /* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
  * last batch call: [0] encode/emission-constant kernel, [1] main DP kernel, [2] number of kernel launches */

@@ -174,3 +174,21 @@ def test_gpu_ntk_vs_live_repaired_reference_seeded():
         assert np.abs(r["probabilities"] - o["probabilities"]).max() <= 1e-4
     assert n_same >= 0.999 * n_seg
     print("NTK 3 reads: reference %.2f s, GPU first path %.2f s" % (t_ref, t_gpu))
+
+
+@pytest.mark.gpu
+def test_gpu_ntk_batch_equals_single_reads():
+    """dyn_ntk_align_batch (pool of CUDA streams) returns exactly what the one-read entry point returns, in input order,
+    and reports per-read errors without failing the batch."""
+    from dynamont_b200 import Aligner
+    cases = [c for c in load_ntk() if c.has_alignment and c.pore == "rna002"]
+    al = Aligner(cases[0].model_path, "rna002", mode="resquiggle")
+    sigs = [c.signal for c in cases] * 3 + [cases[0].signal[:8]]
+    seqs = [c.sequence for c in cases] * 3 + [cases[0].sequence]
+    res = al.align_batch(sigs, seqs, True)
+    assert isinstance(res[-1], RuntimeError) and "Signal too short" in str(res[-1])
+    for i, c in enumerate(cases * 3):
+        r = res[i]
+        assert r["Z"] == al.align(c.signal, c.sequence, False)["Z"]
+        assert r["states"] == c.states.tolist() and r["polishes"] == c.polishes.tolist()
+        assert np.array_equal(r["signal_positions"], c.signal_positions)

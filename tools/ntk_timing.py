@@ -26,9 +26,21 @@ t1 = time.perf_counter()
 ref = Reference(path, "dna_r9", mode="resquiggle", ntk_fix=True)
 o = ref.align(s, q, True)
 t2 = time.perf_counter()
+ref_s = t2 - t1
 T, N, K = s.size + 1, len(q) - 3, 1024
 same = (r["signal_positions"] == o["signal_positions"]).mean() if len(r["states"]) == len(o["states"]) else 0.0
 print("NTK k=5 read: L=%d S=%d  dense cells T*N + T*K = %.3g  GPU %.3f s  reference (1 core) %.3f s  speed-up %.1fx  "
       "Z %.6f vs %.6f  segments %d/%d identical borders %.4f polish identical %s" % (
           L, s.size, T * N + T * K, t1 - t0, t2 - t1, (t2 - t1) / (t1 - t0), r["Z"], o["Z"], len(r["states"]), len(o["states"]),
           same, r["polishes"] == o["polishes"]))
+
+# throughput of the batched entry point: n copies of differently seeded reads of the same length
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+rng = np.random.default_rng(5)
+batch = [synth_read(rng, nm, ns, 5, L, spb) for _ in range(n)]
+t0 = time.perf_counter()
+res = al.align_batch([b[0] for b in batch], [b[1] for b in batch], True)
+t1 = time.perf_counter()
+ok = sum(isinstance(r, dict) for r in res)
+print("NTK batch: %d reads (%d ok) of L=%d in %.2f s = %.1f reads/s  (reference: %.2f reads/s per host core)" % (
+    n, ok, L, t1 - t0, n / (t1 - t0), 1.0 / ref_s))
