@@ -368,8 +368,45 @@ struct SparseArgs
 
 enum { TA1 = 0, TA2, TP1, TP2, TP3, TS1, TS2, TS3, TE1, TE2, TE3, TE4, TI1, TI2 };
 
-__device__ __forceinline__ int64_t sp_find(const SparseArgs& a, uint32_t t, uint32_t n, uint32_t q)
+// The keys of up to three lattice rows, as 32-bit in-row codes n*K + q, staged in shared memory: a predecessor /
+// successor lookup is then a binary search at shared-memory latency.  Rows with more than ROWCACHE keys (rows whose
+// posterior mass is spread over many columns) fall back to the global key list.
+constexpr uint32_t ROWCACHE = 1536;
+struct RowCache
 {
+	uint32_t* code[3];  // shared memory
+	uint32_t row[3];    // lattice row held by slot i (0xffffffff: none)
+	uint32_t cnt[3];
+};
+
+__device__ __forceinline__ void rc_load(const SparseArgs& a, RowCache& rc, int slot, uint32_t t, int lane)
+{
+	rc.row[slot] = 0xffffffffu;
+	if (t >= a.T) return;
+	const uint64_t r0 = a.rowptr[t], r1 = a.rowptr[t + 1];
+	if (r1 - r0 > ROWCACHE || (uint64_t)a.N * a.K > 0xffffffffull) return;
+	const uint64_t tNK = (uint64_t)t * a.N * a.K;
+	for (uint64_t i = r0 + lane; i < r1; i += 32) rc.code[slot][i - r0] = (uint32_t)(a.keys[i] - tNK);
+	rc.row[slot] = t;
+	rc.cnt[slot] = (uint32_t)(r1 - r0);
+}
+
+__device__ __forceinline__ int64_t sp_find(const SparseArgs& a, const RowCache& rc, uint32_t t, uint32_t n, uint32_t q)
+{
+	for (int sl = 0; sl < 3; ++sl)
+		if (rc.row[sl] == t)
+		{
+			const uint32_t code = n * a.K + q;
+			const uint32_t* c = rc.code[sl];
+			uint32_t lo = 0, hi = rc.cnt[sl];
+			while (lo < hi)
+			{
+				const uint32_t mid = (lo + hi) >> 1;
+				if (c[mid] < code) lo = mid + 1;
+				else hi = mid;
+			}
+			return (lo < rc.cnt[sl] && c[lo] == code) ? (int64_t)(a.rowptr[t] + lo) : -1;
+		}
 	const uint64_t key = ((uint64_t)t * a.N + n) * a.K + q;
 	uint64_t lo = a.rowptr[t], hi = a.rowptr[t + 1];
 	while (lo < hi)
@@ -412,12 +449,17 @@ __device__ __forceinline__ void sp_decode(const SparseArgs& a, uint64_t key, uin
 
 // one pass of logF (MAXP = false) or of the MAP fill of decodeMAP (MAXP = true, NTK:814-863) over all rows
 template <bool MAXP>
-__device__ void sp_forward(const SparseArgs& a, int lane)
+__device__ void sp_forward(const SparseArgs& a, RowCache& rc, int lane)
 {
 	const double NI = neg_inf();
 	double* M = MAXP ? a.V : a.F;
+	rc.row[0] = rc.row[1] = rc.row[2] = 0xffffffffu;
 	for (uint32_t t = 0; t < a.T; ++t)
 	{
+		// slot t&1: this row, slot (t+1)&1: the previous one (loaded when it was "this row")
+		__syncwarp();
+		rc_load(a, rc, t & 1, t, lane);
+		__syncwarp();
 		const uint64_t r0 = a.rowptr[t], r1 = a.rowptr[t + 1];
 		for (uint64_t idx = r0 + lane; idx < r1; idx += 32)
 		{
@@ -431,7 +473,7 @@ __device__ void sp_forward(const SparseArgs& a, int lane)
 				const double* lp = a.LP + idx * 5;
 				for (uint32_t pre = q / 4; pre < a.K; pre += a.hp)
 				{
-					const int64_t ia = sp_find(a, t - 1, n - 1, pre), ip = sp_find(a, t - 1, n, pre);
+					const int64_t ia = sp_find(a, rc, t - 1, n - 1, pre), ip = sp_find(a, rc, t - 1, n, pre);
 					if (MAXP)
 					{
 						va = fmax(va, sp_get(M, ia, 3) + lp[0]);
@@ -449,7 +491,7 @@ __device__ void sp_forward(const SparseArgs& a, int lane)
 						vp = log_plus(vp, sp_get(M, ip, 4) + a.tr[TP3] + sc);
 					}
 				}
-				const int64_t is = sp_find(a, t - 1, n - 1, q), ie = sp_find(a, t - 1, n, q);
+				const int64_t is = sp_find(a, rc, t - 1, n - 1, q), ie = sp_find(a, rc, t - 1, n, q);
 				if (MAXP)
 				{
 					vs = fmax(vs, sp_get(M, is, 1) + lp[2]);
@@ -475,43 +517,60 @@ __device__ void sp_forward(const SparseArgs& a, int lane)
 			o[0] = va; o[1] = vp; o[2] = vs; o[3] = ve; o[4] = NI;
 		}
 		__syncwarp();
-		// the I state consumes no sample: (t, n-1, q) of the same row, an earlier key (NTK:503-505, 857-858)
-		if (lane == 0 && t > 0)
+		// The I state consumes no sample: (t, n-1, q) of the same row, an earlier key (NTK:503-505, 857-858).  Every
+		// lane walks the chain of its own key from the first column of the run (t, n0..n, q) upwards — the same
+		// operations in the same order as the sequential evaluation, so the values are identical.
+		if (t > 0)
 		{
-			for (uint64_t idx = r0; idx < r1; ++idx)
+			for (uint64_t idx = r0 + lane; idx < r1; idx += 32)
 			{
 				uint32_t tt, n, q;
 				sp_decode(a, a.keys[idx], tt, n, q);
 				if (n == 0) continue;
-				const int64_t ii = sp_find(a, t, n - 1, q);
-				double vi = NI;
-				if (MAXP)
+				uint32_t n0 = n;
+				while (n0 > 1 && sp_find(a, rc, t, n0 - 1, q) >= 0) --n0;
+				double vi = NI;  // I of (t, n0-1, q): absent or column 0
+				int64_t prev = (n0 >= 1) ? sp_find(a, rc, t, n0 - 1, q) : -1;
+				for (uint32_t m = n0; m <= n; ++m)
 				{
-					const double l4 = a.LP[idx * 5 + 4];
-					vi = fmax(vi, sp_get(M, ii, 3) + l4);
-					vi = fmax(vi, sp_get(M, ii, 4) + l4);
-				}
-				else
-				{
-					const double sc = sp_score(a, a.signal[t - 1], (uint32_t)a.kmers[n - 1], q);
-					vi = log_plus(vi, sp_get(M, ii, 3) + a.tr[TI1] + sc);
-					vi = log_plus(vi, sp_get(M, ii, 4) + a.tr[TI2] + sc);
+					const int64_t cur = (m == n) ? (int64_t)idx : sp_find(a, rc, t, m, q);
+					const double pe = sp_get(M, prev, 3);
+					const double pi = (m == n0) ? sp_get(M, prev, 4) : vi;
+					double x = NI;
+					if (MAXP)
+					{
+						const double l4 = a.LP[cur * 5 + 4];
+						x = fmax(x, pe + l4);
+						x = fmax(x, pi + l4);
+					}
+					else
+					{
+						const double sc = sp_score(a, a.signal[t - 1], (uint32_t)a.kmers[m - 1], q);
+						x = log_plus(x, pe + a.tr[TI1] + sc);
+						x = log_plus(x, pi + a.tr[TI2] + sc);
+					}
+					vi = x;
+					prev = cur;
 				}
 				M[idx * 5 + 4] = vi;
 			}
 		}
-		__syncwarp();
 	}
+	__syncwarp();
 }
 
 // logB (NTK:517-607)
-__device__ void sp_backward(const SparseArgs& a, int lane)
+__device__ void sp_backward(const SparseArgs& a, RowCache& rc, int lane)
 {
 	const double NI = neg_inf();
 	double* M = a.B;
 	const uint32_t T = a.T, N = a.N;
+	rc.row[0] = rc.row[1] = rc.row[2] = 0xffffffffu;
 	for (uint32_t t = T; t-- > 0;)
 	{
+		__syncwarp();
+		rc_load(a, rc, t & 1, t, lane);  // the other slot still holds row t+1
+		__syncwarp();
 		const uint64_t r0 = a.rowptr[t], r1 = a.rowptr[t + 1];
 		for (uint64_t idx = r0 + lane; idx < r1; idx += 32)
 		{
@@ -527,7 +586,7 @@ __device__ void sp_backward(const SparseArgs& a, int lane)
 				{
 					const uint32_t kn = (uint32_t)a.kmers[n - 1];
 					double sc = sp_score(a, x, kn, q);
-					const int64_t ie = sp_find(a, t + 1, n, q);
+					const int64_t ie = sp_find(a, rc, t + 1, n, q);
 					const double fe = sp_get(M, ie, 3);
 					va = log_plus(va, fe + sc);
 					vp = log_plus(vp, fe + a.tr[TE2] + sc);
@@ -536,7 +595,7 @@ __device__ void sp_backward(const SparseArgs& a, int lane)
 					for (uint32_t suc = s0; suc < s0 + 4; ++suc)
 					{
 						sc = sp_score(a, x, kn, suc);
-						const double fp = sp_get(M, sp_find(a, t + 1, n, suc), 1);
+						const double fp = sp_get(M, sp_find(a, rc, t + 1, n, suc), 1);
 						vs = log_plus(vs, fp + a.tr[TP1] + sc);
 						ve = log_plus(ve, fp + a.tr[TP2] + sc);
 						vi = log_plus(vi, fp + a.tr[TP3] + sc);
@@ -546,14 +605,14 @@ __device__ void sp_backward(const SparseArgs& a, int lane)
 				{
 					const uint32_t kn = (uint32_t)a.kmers[n];
 					double sc = sp_score(a, x, kn, q);
-					const double fs = sp_get(M, sp_find(a, t + 1, n + 1, q), 2);
+					const double fs = sp_get(M, sp_find(a, rc, t + 1, n + 1, q), 2);
 					vp = log_plus(vp, fs + a.tr[TS1] + sc);
 					ve = log_plus(ve, fs + a.tr[TS2] + sc);
 					vi = log_plus(vi, fs + a.tr[TS3] + sc);
 					for (uint32_t suc = s0; suc < s0 + 4; ++suc)
 					{
 						sc = sp_score(a, x, kn, suc);
-						const double fa = sp_get(M, sp_find(a, t + 1, n + 1, suc), 0);
+						const double fa = sp_get(M, sp_find(a, rc, t + 1, n + 1, suc), 0);
 						ve = log_plus(ve, fa + a.tr[TA1] + sc);
 						vi = log_plus(vi, fa + a.tr[TA2] + sc);
 					}
@@ -561,25 +620,57 @@ __device__ void sp_backward(const SparseArgs& a, int lane)
 			}
 			double* o = M + idx * 5;
 			o[0] = va; o[1] = vp; o[2] = vs; o[3] = ve; o[4] = vi;
+			a.LP[idx * 5 + 2] = 0.0;  // LP doubles as scratch for the same-row update below
 		}
 		__syncwarp();
-		// the I move into (t, n+1, q) of the same row, a later key: descending key order (NTK:592-598)
-		if (lane == 0 && t > 0)
+		// The I move into (t, n+1, q) of the same row, a later key (NTK:592-598): only the I component of the successor
+		// enters, so every lane walks its own chain from the last column of the run (t, n..n1, q) downwards, adding
+		// the same terms in the same order as the sequential (descending key order) evaluation.
+		if (t > 0)
 		{
-			for (uint64_t idx = r1; idx-- > r0;)
+			for (uint64_t idx = r0 + lane; idx < r1; idx += 32)
 			{
 				uint32_t tt, n, q;
 				sp_decode(a, a.keys[idx], tt, n, q);
 				if (n >= N - 1) continue;
+				uint32_t n1 = n;
+				while (n1 + 1 <= N - 1 && sp_find(a, rc, t, n1 + 1, q) >= 0) ++n1;
+				if (n1 == n) continue;  // successor absent: the terms are -inf, log_plus leaves e and i unchanged
+				// I of (t, m, q) for m = n1 down to n+1, each including its own same-row term
+				double fi = 0.0;
+				for (uint32_t m = n1; m > n; --m)
+				{
+					const int64_t cur = sp_find(a, rc, t, m, q);
+					double im = M[cur * 5 + 4];  // phase-1 value (terms of row t+1 only)
+					if (m < n1 && m < N - 1)
+					{
+						const double sc = sp_score(a, a.signal[t - 1], (uint32_t)a.kmers[m], q);
+						im = log_plus(im, fi + a.tr[TI2] + sc);
+					}
+					fi = im;
+				}
 				const double sc = sp_score(a, a.signal[t - 1], (uint32_t)a.kmers[n], q);
-				const double fi = sp_get(M, sp_find(a, t, n + 1, q), 4);
 				double* o = M + idx * 5;
-				o[3] = log_plus(o[3], fi + a.tr[TI1] + sc);
-				o[4] = log_plus(o[4], fi + a.tr[TI2] + sc);
+				const double e_new = log_plus(o[3], fi + a.tr[TI1] + sc);
+				const double i_new = log_plus(o[4], fi + a.tr[TI2] + sc);
+				// written to separate outputs after all lanes have read the phase-1 I values
+				a.LP[idx * 5 + 0] = e_new;
+				a.LP[idx * 5 + 1] = i_new;
+				a.LP[idx * 5 + 2] = 1.0;  // marker
+			}
+			__syncwarp();
+			for (uint64_t idx = r0 + lane; idx < r1; idx += 32)
+			{
+				if (a.LP[idx * 5 + 2] == 1.0)
+				{
+					M[idx * 5 + 3] = a.LP[idx * 5 + 0];
+					M[idx * 5 + 4] = a.LP[idx * 5 + 1];
+					a.LP[idx * 5 + 2] = 0.0;
+				}
 			}
 		}
-		__syncwarp();
 	}
+	__syncwarp();
 }
 
 // formattedMedian (aligner.cpp:247-263) of v[0..m); sorts v in place
@@ -615,12 +706,14 @@ __device__ void sp_push_segment(const SparseArgs& a, uint32_t& ns, char state, u
 // NTKAligner::traceback (NTK:628-801), one thread
 __device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_t q)
 {
+	RowCache rc;
+	rc.row[0] = rc.row[1] = rc.row[2] = 0xffffffffu;
 	const double* V = a.V;
 	const double* LP = a.LP;
 	double* prob = a.prob_buf;
 	uint32_t np = 0, ns = 0;
 	int state = 3;
-	int64_t cur = sp_find(a, t, n, q);
+	int64_t cur = sp_find(a, rc, t, n, q);
 	const uint32_t half = a.k / 2;
 	uint64_t guard = (uint64_t)a.T + a.N + 8;
 	while (t)
@@ -633,7 +726,7 @@ __device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_
 				sp_push_segment(a, ns, 'M', half, 0, prob, np, q);
 				break;
 			}
-			const int64_t prev = sp_find(a, t - 1, n, q);
+			const int64_t prev = sp_find(a, rc, t - 1, n, q);
 			const double sc = sp_get(V, cur, 3), ls = sp_get(LP, cur, 3);
 			prob[np++] = exp(ls);
 			if (sc == sp_get(V, prev, 3) + ls) state = 3;
@@ -656,7 +749,7 @@ __device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_
 			bool moved = false;
 			for (uint32_t pre = q / 4; pre < a.K && !moved; pre += a.hp)
 			{
-				const int64_t prev = sp_find(a, t - 1, isA ? n - 1 : n, pre);
+				const int64_t prev = sp_find(a, rc, t - 1, isA ? n - 1 : n, pre);
 				int nstate = -1;
 				if (sc == sp_get(V, prev, 3) + ls) nstate = 3;
 				else if (!isA && sc == sp_get(V, prev, 2) + ls) nstate = 2;
@@ -677,7 +770,7 @@ __device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_
 		else if (state == 2)
 		{
 			if (t == 1 && n == 1) break;
-			const int64_t prev = sp_find(a, t - 1, n - 1, q);
+			const int64_t prev = sp_find(a, rc, t - 1, n - 1, q);
 			const double sc = sp_get(V, cur, 2), ls = sp_get(LP, cur, 2);
 			prob[np++] = exp(ls);
 			if (sc == sp_get(V, prev, 3) + ls) state = 3;
@@ -690,7 +783,7 @@ __device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_
 		else
 		{
 			if (n == 1) break;
-			const int64_t prev = sp_find(a, t, n - 1, q);
+			const int64_t prev = sp_find(a, rc, t, n - 1, q);
 			const double sc = sp_get(V, cur, 4), ls = sp_get(LP, cur, 4);
 			prob[np++] = exp(ls);
 			if (sc == sp_get(V, prev, 4) + ls) state = 4;
@@ -706,14 +799,24 @@ __device__ int sp_traceback(const SparseArgs& a, uint32_t t, uint32_t n, uint32_
 // logF and logB are independent: grid = 2 single-warp CTAs
 __global__ void __launch_bounds__(32) k_ntk_sparse_fb(SparseArgs a)
 {
-	if (blockIdx.x == 0) sp_forward<false>(a, threadIdx.x);
-	else sp_backward(a, threadIdx.x);
+	__shared__ uint32_t codes[2][ROWCACHE];
+	RowCache rc;
+	rc.code[0] = codes[0];
+	rc.code[1] = codes[1];
+	rc.code[2] = codes[0];
+	if (blockIdx.x == 0) sp_forward<false>(a, rc, threadIdx.x);
+	else sp_backward(a, rc, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(32) k_ntk_sparse(SparseArgs a)
 {
 	const int lane = threadIdx.x;
 	const double NI = neg_inf();
+	__shared__ uint32_t codes[2][ROWCACHE];
+	RowCache rc;
+	rc.code[0] = codes[0];
+	rc.code[1] = codes[1];
+	rc.code[2] = codes[0];
 	// Zf, Zb (NTK:897-918): sequential log-sum-exp over q of the E state of (T-1, N-1, q) / (0, 0, q)
 	double Zf = NI, Zb = NI;
 	if (lane == 0)
@@ -746,7 +849,7 @@ __global__ void __launch_bounds__(32) k_ntk_sparse(SparseArgs a)
 	// sparse logP (NTK:159-177)
 	for (uint64_t i = lane; i < a.nk * 5; i += 32) a.LP[i] = a.F[i] + a.B[i] - Zb;
 	__syncwarp();
-	sp_forward<true>(a, lane);
+	sp_forward<true>(a, rc, lane);
 	__syncwarp();
 	if (lane == 0)
 	{
