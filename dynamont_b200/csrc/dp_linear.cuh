@@ -31,6 +31,13 @@
 
 #include "dp_kernels.cuh"
 
+#ifndef DYN_FWD_UNROLL
+#define DYN_FWD_UNROLL 0
+#endif
+#ifndef DYN_RCP_UNROLL
+#define DYN_RCP_UNROLL 1
+#endif
+
 namespace dyn
 {
 namespace lin
@@ -277,19 +284,35 @@ DYN_DEV double backward_pass(Warp<CFG>& w, const SlotScratch& sc, float m1, floa
 		const uint32_t base = (uint32_t)t & ~31u;
 		const Chunk cur = nxt;
 		if (base >= 32) nxt = chunk_load<CFG>(w, base - 32);
-		float x = __shfl_sync(FULL, cur.xv, t - (int)base);
+		int i = t - (int)base;
 #pragma unroll 1
-		for (int i = t - (int)base; i >= 0; --i)
+		while (i >= 0)
 		{
+			if (CFG::RN == 4 && (i & 3) == 3 && ((cur.smask >> (i - 3)) & 0xfu) == 0u)
+			{
+				// four rows without a band slide in one basic block: no branches between the rows, so the emissions of
+				// the next row (which do not depend on the recurrence) overlap the tail of the previous one
+				const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i - 1);
+				const float x2 = __shfl_sync(FULL, cur.xv, i - 2), x3 = __shfl_sync(FULL, cur.xv, i - 3);
+				bwd_row<CFG>(w, b, x0, m1, e2);
+				bwd_row<CFG>(w, b, x1, m1, e2);
+				bwd_row<CFG>(w, b, x2, m1, e2);
+				bwd_row<CFG>(w, b, x3, m1, e2);
+				const uint32_t tt = base + i - 3;
+				bwd_renorm<CFG>(w, b);
+				if (STORE && (tt & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
+				i -= 4;
+				continue;
+			}
 			const uint32_t tt = base + i;
-			const float xn = __shfl_sync(FULL, cur.xv, (i - 1) & 31);
+			const float x = __shfl_sync(FULL, cur.xv, i);
 			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid, m1, e2);
-			x = xn;
 			if ((tt & (CFG::RN - 1)) == 0)
 			{
 				bwd_renorm<CFG>(w, b);
 				if (STORE && (tt & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
 			}
+			--i;
 		}
 		t = (int)base - 1;
 	}
@@ -391,7 +414,7 @@ DYN_DEV void vit_renorm(Warp<CFG>& w, FwdL<CFG::CPL>& f)
 template <class CFG, bool DO_V, bool DO_STEP>
 DYN_DEV void fwd_row(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, RecSink& rs, float thr, uint32_t t, float x,
 	bool slide, int& mid_f, float (&bc)[CFG::CPL], float (&bn)[CFG::CPL], const float* pf, bool has_pf, float kapE, float kapM,
-	float m1, float e2)
+	float m1, float e2, bool maybe_vit = true)
 {
 	constexpr int CPL = CFG::CPL;
 	const int lane = w.lane;
@@ -428,7 +451,7 @@ DYN_DEV void fwd_row(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, Rec
 			f.VE[j] = vmx * PE[j];
 			lmax = max3f(lmax, PM[j], PE[j]);
 		}
-		if ((t & (CFG::RV - 1)) == 0) vit_renorm<CFG>(w, f);
+		if (maybe_vit && (t & (CFG::RV - 1)) == 0) vit_renorm<CFG>(w, f);
 		sc.bits[(size_t)t * 32 + lane] = (uint16_t)acc;
 
 		// sparse posterior records (linear posteriors); a NaN/inf lane is recorded too so that the mass check sees it
@@ -553,22 +576,47 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 			for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
 			sm.OB[((src_row - t_lo + RN - 1) / RN) * 32 + lane] = b.OB;
 		}
-		float xb = __shfl_sync(FULL, cur.xv, ((int)src_row - 1) & 31);
-#pragma unroll 1
-		for (int tt = (int)src_row - 1; tt >= (int)t_lo; --tt)
 		{
-			const int i = tt & 31;
-			const float x = xb;
-			xb = __shfl_sync(FULL, cur.xv, (i - 1) & 31);
-			bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid_b, m1, e2);
-			float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
-			if ((tt & (RN - 1)) == 0)
+			int tt = (int)src_row - 1;
+#pragma unroll 1
+			while (tt >= (int)t_lo)
 			{
-				bwd_renorm<CFG>(w, b);
-				sm.OB[((tt - (int)t_lo) / RN) * 32 + lane] = b.OB;
-			}
+				const int i = tt & 31;
+				if (DYN_RCP_UNROLL && RN == 4 && (i & 3) == 3 && ((cur.smask >> (i - 3)) & 0xfu) == 0u)
+				{
+					// four rows without a band slide in one basic block (see backward_pass)
+					const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i - 1);
+					const float x2 = __shfl_sync(FULL, cur.xv, i - 2), x3 = __shfl_sync(FULL, cur.xv, i - 3);
+					float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
+					bwd_row<CFG>(w, b, x0, m1, e2);
 #pragma unroll
-			for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
+					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
+					bwd_row<CFG>(w, b, x1, m1, e2);
+#pragma unroll
+					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane - ROWF] = b.bE[j];
+					bwd_row<CFG>(w, b, x2, m1, e2);
+#pragma unroll
+					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane - 2 * ROWF] = b.bE[j];
+					bwd_row<CFG>(w, b, x3, m1, e2);
+					bwd_renorm<CFG>(w, b);
+					sm.OB[((tt - 3 - (int)t_lo) / RN) * 32 + lane] = b.OB;
+#pragma unroll
+					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane - 3 * ROWF] = b.bE[j];
+					tt -= 4;
+					continue;
+				}
+				const float x = __shfl_sync(FULL, cur.xv, i);
+				bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid_b, m1, e2);
+				float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
+				if ((tt & (RN - 1)) == 0)
+				{
+					bwd_renorm<CFG>(w, b);
+					sm.OB[((tt - (int)t_lo) / RN) * 32 + lane] = b.OB;
+				}
+#pragma unroll
+				for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
+				--tt;
+			}
 		}
 		__syncwarp();
 
@@ -615,22 +663,36 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 				bn[j] = row[ROWF + j * 32 + lane];
 			}
 		}
-		float x = __shfl_sync(FULL, cur.xv, t & 31);
 #pragma unroll 1
-		for (; t < t_end; ++t)
+		while (t < t_end)
 		{
 			const int i = t & 31;
 			const uint32_t r = t - t_lo;
+			if (DYN_FWD_UNROLL && RN == 4 && (t & 1u) == 0 && t + 1 < t_end && ((cur.smask >> i) & 0x3u) == 0u)
+			{
+				// two rows without a band slide in one basic block: the emissions of the second row overlap the tail of
+				// the first one
+				const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i + 1);
+				const bool rn0 = (t & 3u) == 0;
+				const float kapN = rn0 ? kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0) : f.kap;
+				const float* rows = sm.bE + (size_t)(r + 1) * ROWF;
+				fwd_row<CFG, true, true>(w, f, sc, rs, thr, t, x0, false, mid_f, bc, bn, rows, true, f.kap, kapN, m1, e2, true);
+				fwd_row<CFG, true, true>(w, f, sc, rs, thr, t + 1, x1, false, mid_f, bc, bn, rows + ROWF, t + 2 < t_end, kapN, kapN, m1, e2, false);
+				f.kap = kapN;
+				if (((t + 2) & 3u) == 0) fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 2) / RN) * 32 + lane], Z2i, c0);
+				t += 2;
+				continue;
+			}
 			const bool rn_row = (t & (RN - 1)) == 0;
 			// on a renormalisation row bM[t] = bE[t+1] * p lives in the offsets of the next rows
 			const float kapN = rn_row ? kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0) : f.kap;
-			const float xn = __shfl_sync(FULL, cur.xv, (i + 1) & 31);
+			const float x = __shfl_sync(FULL, cur.xv, i);
 			fwd_row<CFG, true, true>(w, f, sc, rs, thr, t, x, (cur.smask >> i) & 1u, mid_f, bc, bn,
 				sm.bE + (size_t)(r + 1) * ROWF, t + 1 < t_end, f.kap, kapN, m1, e2);
 			f.kap = kapN;
 			// the forward values are now those of row t+1 (bc: the backward row t+1, or still row t at a block end)
 			if (((t + 1) & (RN - 1)) == 0) fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 1) / RN) * 32 + lane], Z2i, c0);
-			x = xn;
+			++t;
 		}
 		__syncwarp();
 	}
