@@ -48,7 +48,7 @@ constexpr int E0V = 20;                // exponent of the lane maximum after a p
 constexpr float LIN_MASS_TOL = 1e-3f;  // |recorded posterior mass of a row - 1| above this is a range fault
 constexpr double LIN_Z_TOL = 3e-3;     // |log2 Zf - log2 Zb| above this is a range fault
 constexpr int LIN_GUARD_BITS = 70;     // see the header comment
-constexpr int KAPPA_MAX_EXP = 100;     // the posterior factor 2^(OF + OB - Z2) is clamped here (sb * kappa must stay finite)
+constexpr int KAPPA_MAX_EXP = 118;     // the posterior factor 2^(OF + OB - Z2) is clamped here (sb * kappa must stay finite)
 
 // 2^e as a float; 0 for e < -126, 2^127 for e > 127
 DYN_DEV float pow2i(int e)

@@ -17,6 +17,7 @@ from fp32_model import LOG2E, bounds, emis, pos_consts
 
 f32 = np.float32
 TINY = f32(2.0 ** -126)
+KAPMAX = int(__import__("os").environ.get("LIN_KAPMAX", "100"))
 
 
 def ftz(a):
@@ -162,7 +163,7 @@ def align_lin(x, kmers, mean, stdev, trans, k, band=400, R=4, RV=8, thr=2.0 ** -
             fM = scale2(fM, shf[lane])
             fE = scale2(fE, shf[lane])
             OF = newO
-        kap = (c0 * np.ldexp(f32(1.0), np.clip(OF + OBat[t] - Z2i, -127, 100).astype(np.int32))).astype(f32)
+        kap = (c0 * np.ldexp(f32(1.0), np.clip(OF + OBat[t] - Z2i, -127, KAPMAX).astype(np.int32))).astype(f32)
         if t % R == 0:
             # guard: F_lane * B_lane / Z bounds the posterior any flushed cell of that lane could have had (times 2^-126)
             fl_ = np.maximum(lane_max(fM, t), lane_max(fE, t)); bl_ = lane_max(bE[t], t)
