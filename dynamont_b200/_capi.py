@@ -39,7 +39,8 @@ _libs: dict = {}
 
 
 def load(path: str | None = None) -> C.CDLL:
-    path = os.path.abspath(path or DEFAULT_LIB)
+    # DYNAMONT_B200_LIB: kernel experiments only (A/B of two builds of the same sources on one GPU box, tools/gpu_ab.sh)
+    path = os.path.abspath(path or os.environ.get("DYNAMONT_B200_LIB") or DEFAULT_LIB)
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

@@ -22,6 +22,7 @@ namespace dyn
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float NEG = -1.0e30f;      // forced value of an impossible / out-of-band cell
 constexpr float CNEG = -1.0e25f;     // emission constant of an inactive ring slot
+constexpr float BIGB = 1.0e18f;      // Cfg::UNI: b constant of an inactive ring slot (z^2 = 1e36 stays finite)
 constexpr float DEADT = -1.0e20f;    // anything below this is "-inf" (real log2-probabilities are > -1e10)
 constexpr double LOG2E = 1.4426950408889634074;
 constexpr double LN2 = 0.69314718055994530942;

@@ -25,9 +25,13 @@
 namespace dyn
 {
 
-template <int CPL_, int CK_, int RN_, int RV_>
+template <int CPL_, int CK_, int RN_, int RV_, bool UNI_ = false>
 struct Cfg
 {
+	// UNI: every kmer of the pore model has the same standard deviation (both shipped 5-mer models and the synthetic
+	// 9-mer models): the emission constants a and c are warp-uniform scalars, only b = mu * a is per column; an inactive
+	// ring slot is gated through b (z = x*a - 1e18 -> 2^-1e36 = 0) instead of c.  26 registers fewer per thread.
+	static constexpr bool UNI = UNI_;
 	static constexpr int CPL = CPL_;         // lattice columns per lane
 	static constexpr int SLOTS = 32 * CPL_;  // ring capacity; needs 2*bw + 2 <= SLOTS
 	static constexpr int CK = CK_;           // checkpoint spacing (rows); divides 32, multiple of RN
@@ -36,7 +40,7 @@ struct Cfg
 	static constexpr int NRN = CK_ / RN_ + 1;
 	static constexpr int CKF = 2 * CPL_ * 32;  // floats per checkpoint
 	static constexpr int ROWF = CPL_ * 32;     // floats per shared-memory row
-	static constexpr size_t SMEM_BYTES = (size_t)(CK_ + 1) * ROWF * 4 + (size_t)NRN * 32 * (8 + 4);
+	static constexpr size_t SMEM_BYTES = (size_t)(CK_ + 2) * ROWF * 4 + (size_t)NRN * 32 * (8 + 4);  // rows t_lo .. t_lo+CK, + 1 row the fast forward row may prefetch past the block
 	static_assert(CK_ % RN_ == 0 && 32 % CK_ == 0, "CK must divide 32 and be a multiple of RN");
 	static_assert((RN_ & (RN_ - 1)) == 0 && (RV_ & (RV_ - 1)) == 0, "RN, RV: powers of two");
 };
@@ -71,6 +75,8 @@ struct BatchArgs
 	float m1_lin, e2_lin;       // the same transitions as plain probabilities (linear-domain kernels)
 	float thr_lin;              // 2^thr2
 	int mode;                   // 0: Z only (backward pass), 1: full alignment, 2: training statistics
+	float uni_a, uni_c;         // Cfg::UNI kernels: the model-wide emission constants (every kmer has the same sigma)
+	int fwd_fast;               // linear-domain pass 2: branch-free row body for groups of rows without a band slide
 	// training (mode 2)
 	double* stat_w;             // [K] pooled sum of gamma              (NT:510)
 	double* stat_x;             // [K] pooled sum of gamma * x          (NT:511)
@@ -206,20 +212,29 @@ struct Warp
 	const float* sig;
 	const PosConst* pc;
 	float m1, e2;
+	float ua, uc;  // UNI: the model-wide emission constants a, c
 	Emis<CPL> em;
 
 	DYN_DEV bool valid_col(int n) const { return n >= 0 && n < (int)N; }
+	// log2 emission of ring slot j (compile-time j) for sample x
+	DYN_DEV float emis(int j, float x) const
+	{
+		return CFG::UNI ? emis2(x, ua, em.b[j], uc) : emis2(x, em.a[j], em.b[j], em.c[j]);
+	}
+	// b constant of a column (UNI: a column that scores no kmer is gated through b)
+	DYN_DEV static float bsel(const PosConst& v) { return (CFG::UNI && v.c < 0.5f * CNEG) ? BIGB : v.b; }
+	DYN_DEV static float b_off() { return CFG::UNI ? BIGB : 0.0f; }
 
 	DYN_DEV void activate(int n)
 	{
 		if (!valid_col(n)) return;
 		const PosConst v = pc[n];  // uniform address: one broadcast transaction
-		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, v.a, v.b, v.c});
+		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, v.a, bsel(v), v.c});
 	}
 	DYN_DEV void deactivate(int n)
 	{
 		if (!valid_col(n)) return;
-		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, 0.0f, 0.0f, CNEG});
+		with_slot<CPL>(lane, pmod(n, SLOTS), SetEmis<CPL>{em, 0.0f, b_off(), CNEG});
 	}
 	// lattice column held by ring slot q when the window starts at column n0 (may be negative)
 	DYN_DEV int col_of_slot(int q, int n0) const { return n0 + pmod(q - n0, SLOTS); }
@@ -237,13 +252,13 @@ struct Warp
 			{
 				const PosConst v = pc[n];
 				em.a[j] = v.a;
-				em.b[j] = v.b;
+				em.b[j] = bsel(v);
 				em.c[j] = v.c;
 			}
 			else
 			{
 				em.a[j] = 0.0f;
-				em.b[j] = 0.0f;
+				em.b[j] = b_off();
 				em.c[j] = CNEG;
 			}
 		}
@@ -297,7 +312,7 @@ DYN_DEV void bwd_row(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x)
 #pragma unroll
 	for (int j = 0; j < CPL; ++j)
 	{
-		s[j] = emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]);
+		s[j] = w.emis(j, x);
 		A[j] = b.bM[j] + (s[j] + w.m1);  // bM[t+1][n] + score(x[t], kmer[n-1]) + m1, consumed by column n-1
 	}
 	const float Ar = __shfl_sync(FULL, A[0], (w.lane + 1) & 31) + b.dR;
@@ -352,7 +367,7 @@ DYN_DEV void bwd_step(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x, bool slide, int& 
 		if (nb >= 0)
 		{
 			const PosConst v = w.pc[nb];
-			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetEmisState<CPL>{w.em, v.a, v.b, v.c, b.bM, b.bE, NEG});
+			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetEmisState<CPL>{w.em, v.a, w.bsel(v), v.c, b.bM, b.bE, NEG});
 		}
 	}
 	bwd_row<CFG>(w, b, x);
@@ -360,7 +375,7 @@ DYN_DEV void bwd_step(Warp<CFG>& w, Bwd<CFG::CPL>& b, float x, bool slide, int& 
 	{
 		const int ntop = mid + w.bw;  // column that was in band(t+1) but is not in band(t)
 		if (ntop < (int)w.N)
-			with_slot<CPL>(w.lane, pmod(ntop, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, b.bM, b.bE, NEG});
+			with_slot<CPL>(w.lane, pmod(ntop, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, w.b_off(), CNEG, b.bM, b.bE, NEG});
 		--mid;
 	}
 }
@@ -565,7 +580,7 @@ DYN_DEV void fwd_row(Warp<CFG>& w, Fwd<CFG::CPL>& f, const SlotScratch& sc, RecS
 #pragma unroll
 	for (int j = 0; j < CPL; ++j)
 	{
-		s[j] = emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]);
+		s[j] = w.emis(j, x);
 		if (DO_V)
 		{
 			LPE[j] = f.fE[j] + bc[j];
@@ -662,7 +677,7 @@ DYN_DEV void fwd_row(Warp<CFG>& w, Fwd<CFG::CPL>& f, const SlotScratch& sc, RecS
 		{
 			const int nold = mid_f - w.bw;  // column of band(t) that is not in band(t+1)
 			if (nold >= 0)
-				with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, f.fM, f.fE, NEG});
+				with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, w.b_off(), CNEG, f.fM, f.fE, NEG});
 			++mid_f;
 		}
 	}
@@ -873,20 +888,29 @@ DYN_DEV bool trace_decisions(Warp<CFG>& w, const SlotScratch& sc, const BatchArg
 	int t = (int)T - 1, n = (int)N - 1;
 	int inM = 0;
 	bool done = false;
+	// the decision words of the chunk below the current one are fetched while the current one is walked
+	uint4 nb[4];
+	{
+		const uint32_t r = ((uint32_t)t & ~31u) + lane;
+		const uint4* src = reinterpret_cast<const uint4*>(sc.bits + (size_t)r * 32);
+#pragma unroll
+		for (int q = 0; q < 4; ++q) nb[q] = (r < T) ? src[q] : make_uint4(0u, 0u, 0u, 0u);
+	}
 	while (!done)
 	{
 		const int cbase = t & ~31;
 		{
-			const uint32_t r = (uint32_t)cbase + lane;
-			const uint4* src = reinterpret_cast<const uint4*>(sc.bits + (size_t)r * 32);
 			uint4* dst = reinterpret_cast<uint4*>(sbits + lane * 32);
-			if (r < T)
-			{
 #pragma unroll
-				for (int q = 0; q < 4; ++q) dst[q] = src[q];
-			}
+			for (int q = 0; q < 4; ++q) dst[q] = nb[q];
 		}
 		__syncwarp();
+		if (cbase >= 32)
+		{
+			const uint4* src = reinterpret_cast<const uint4*>(sc.bits + (size_t)(cbase - 32 + lane) * 32);
+#pragma unroll
+			for (int q = 0; q < 4; ++q) nb[q] = src[q];
+		}
 		while (t >= cbase)
 		{
 			if (t == 0 || n == 0)
@@ -1085,6 +1109,8 @@ DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx
 	w.pc = args.pc + rd.pc_off;
 	w.m1 = args.m1;
 	w.e2 = args.e2;
+	w.ua = args.uni_a;
+	w.uc = args.uni_c;
 
 	ReadOut out;
 	out.Z = 0.0;

@@ -37,6 +37,18 @@
 #ifndef DYN_RCP_UNROLL
 #define DYN_RCP_UNROLL 1
 #endif
+#ifndef DYN_FWD_FAST
+#define DYN_FWD_FAST 1
+#endif
+// the slide-free 4-row groups of the backward passes: 0 = four rows unrolled into one basic block, 1 = a loop over a
+// one-row body (a quarter of the code: the recomputation alternates with the forward rows every CK rows, and the two
+// loops together have to stay resident in the instruction cache)
+#ifndef DYN_BWD_ROLL_P1
+#define DYN_BWD_ROLL_P1 1
+#endif
+#ifndef DYN_BWD_ROLL_RCP
+#define DYN_BWD_ROLL_RCP 1
+#endif
 
 namespace dyn
 {
@@ -49,6 +61,9 @@ constexpr float LIN_MASS_TOL = 1e-3f;  // |recorded posterior mass of a row - 1|
 constexpr double LIN_Z_TOL = 3e-3;     // |log2 Zf - log2 Zb| above this is a range fault
 constexpr int LIN_GUARD_BITS = 70;     // see the header comment
 constexpr int KAPPA_MAX_EXP = 118;     // the posterior factor 2^(OF + OB - Z2) is clamped here (sb * kappa must stay finite)
+
+// component c (compile-time after unrolling) of a float4 held in registers
+DYN_DEV float f4_get(const float4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
 
 // 2^e as a float; 0 for e < -126, 2^127 for e > 127
 DYN_DEV float pow2i(int e)
@@ -84,7 +99,7 @@ template <class CFG>
 DYN_DEV void emis_lin(const Warp<CFG>& w, float x, float (&p)[CFG::CPL])
 {
 #pragma unroll
-	for (int j = 0; j < CFG::CPL; ++j) p[j] = ex2(emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]));
+	for (int j = 0; j < CFG::CPL; ++j) p[j] = ex2(w.emis(j, x));
 }
 
 // New integer offset of this lane after a renormalisation.
@@ -132,11 +147,11 @@ DYN_DEV void bwd_row(Warp<CFG>& w, BwdL<CFG::CPL>& b, float x, float m1, float e
 	float p[CPL], A[CPL];
 	// A[n] = bM[t+1][n] * p(t,n) * m1 is consumed by column n-1.  Slot 0 goes first: A[0] is what the left lane needs,
 	// and the shuffle that carries it then has the rest of the row to complete.
-	p[0] = ex2(emis2(x, w.em.a[0], w.em.b[0], w.em.c[0]));
+	p[0] = ex2(w.emis(0, x));
 	A[0] = b.bM[0] * (p[0] * m1);
 	const float Araw = __shfl_sync(FULL, A[0], (w.lane + 1) & 31);
 #pragma unroll
-	for (int j = 1; j < CPL; ++j) p[j] = ex2(emis2(x, w.em.a[j], w.em.b[j], w.em.c[j]));
+	for (int j = 1; j < CPL; ++j) p[j] = ex2(w.emis(j, x));
 #pragma unroll
 	for (int j = 1; j < CPL; ++j) A[j] = b.bM[j] * (p[j] * m1);
 #pragma unroll
@@ -186,7 +201,7 @@ DYN_DEV void bwd_step(Warp<CFG>& w, BwdL<CFG::CPL>& b, float x, bool slide, int&
 		if (nb >= 0)
 		{
 			const PosConst v = w.pc[nb];
-			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetEmisState<CPL>{w.em, v.a, v.b, v.c, b.bM, b.bE, 0.0f});
+			with_slot<CPL>(w.lane, pmod(nb, CFG::SLOTS), SetEmisState<CPL>{w.em, v.a, w.bsel(v), v.c, b.bM, b.bE, 0.0f});
 		}
 	}
 	bwd_row<CFG>(w, b, x, m1, e2);
@@ -194,7 +209,7 @@ DYN_DEV void bwd_step(Warp<CFG>& w, BwdL<CFG::CPL>& b, float x, bool slide, int&
 	{
 		const int ntop = mid + w.bw;
 		if (ntop < (int)w.N)
-			with_slot<CPL>(w.lane, pmod(ntop, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, b.bM, b.bE, 0.0f});
+			with_slot<CPL>(w.lane, pmod(ntop, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, w.b_off(), CNEG, b.bM, b.bE, 0.0f});
 		--mid;
 	}
 }
@@ -292,12 +307,17 @@ DYN_DEV double backward_pass(Warp<CFG>& w, const SlotScratch& sc, float m1, floa
 			{
 				// four rows without a band slide in one basic block: no branches between the rows, so the emissions of
 				// the next row (which do not depend on the recurrence) overlap the tail of the previous one
+#if DYN_BWD_ROLL_P1
+#pragma unroll 1
+				for (int q = 0; q < 4; ++q) bwd_row<CFG>(w, b, __shfl_sync(FULL, cur.xv, i - q), m1, e2);
+#else
 				const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i - 1);
 				const float x2 = __shfl_sync(FULL, cur.xv, i - 2), x3 = __shfl_sync(FULL, cur.xv, i - 3);
 				bwd_row<CFG>(w, b, x0, m1, e2);
 				bwd_row<CFG>(w, b, x1, m1, e2);
 				bwd_row<CFG>(w, b, x2, m1, e2);
 				bwd_row<CFG>(w, b, x3, m1, e2);
+#endif
 				const uint32_t tt = base + i - 3;
 				bwd_renorm<CFG>(w, b);
 				if (STORE && (tt & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
@@ -510,9 +530,103 @@ DYN_DEV void fwd_row(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, Rec
 		{
 			const int nold = mid_f - w.bw;
 			if (nold >= 0)
-				with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, 0.0f, CNEG, f.fM, f.fE, 0.0f});
+				with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, w.b_off(), CNEG, f.fM, f.fE, 0.0f});
 			++mid_f;
 		}
+	}
+}
+
+// 16-byte global store under a predicate: keeps the sparse-record write of the fast row free of divergent regions
+DYN_DEV void st_v4_if(bool on, float* dst, float a, float b, float c, float d)
+{
+#ifndef DYN_HOST_EMU
+	asm volatile(
+		"{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %0, 0;\n\t@p st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"((int)on),
+		"l"(__cvta_generic_to_global(dst)), "f"(a), "f"(b), "f"(c), "f"(d)
+		: "memory");
+#else
+	if (on)
+	{
+		dst[0] = a;
+		dst[1] = b;
+		dst[2] = c;
+		dst[3] = d;
+	}
+#endif
+}
+
+// fwd_row<CFG, true, true> for a row that (a) does not slide the band, (b) has both neighbouring backward rows in shared
+// memory and (c) is not a renormalisation row of the posterior-Viterbi scores: ONE basic block.  The generic row spends
+// about a quarter of its time at the boundaries of its nine conditional regions (nothing is scheduled across them);
+// groups of RN rows without a slide (87 % at 30 samples per base) run through this body instead.
+template <class CFG>
+DYN_DEV void fwd_row_fast(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc, RecSink& rs, float thr, uint32_t t, float x,
+	float (&bc)[CFG::CPL], float (&bn)[CFG::CPL], const float* pf, float kapE, float kapM, float m1, float e2)
+{
+	constexpr int CPL = CFG::CPL;
+	typedef LaneRec<CPL> Rec;
+	const int lane = w.lane;
+	const float vlraw = __shfl_sync(FULL, f.VE[CPL - 1], (lane + 31) & 31);
+	const float flraw = __shfl_sync(FULL, f.fE[CPL - 1], (lane + 31) & 31);
+	float p[CPL], PM[CPL], PE[CPL];
+	emis_lin<CFG>(w, x, p);
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		PE[j] = f.fE[j] * (bc[j] * kapE);
+		PM[j] = f.fM[j] * ((bn[j] * p[j]) * kapM);  // bM[t][n] = bE[t+1][n] * p(t,n) (NT:200)
+	}
+	const float vl = (vlraw * f.sV1) * f.sV2;
+	unsigned acc = 0;
+	float lmax = 0.0f;
+#pragma unroll
+	for (int j = CPL - 1; j >= 0; --j)
+	{
+		const float vmx = fmaxf(f.VM[j], f.VE[j]);
+		acc = __funnelshift_l(__float_as_uint(f.VM[j] - f.VE[j]), acc, 1);
+		const float left = (j > 0) ? f.VE[j - 1] : vl;
+		f.VM[j] = left * PM[j];
+		f.VE[j] = vmx * PE[j];
+		lmax = max3f(lmax, PM[j], PE[j]);
+	}
+	sc.bits[(size_t)t * 32 + lane] = (uint16_t)acc;
+	if (lane == 0) sc.rowptr[t] = rs.n;
+	{
+		const bool hot = !(lmax <= thr);
+		const unsigned hm = __ballot_sync(FULL, hot);
+		const uint32_t pos = rs.n + __popc(hm & ((1u << lane) - 1u));
+		const bool wr = hot && pos < rs.cap;
+		float* dst = static_cast<Rec*>(rs.recs)[wr ? pos : 0u].v;
+		float tmp[Rec::NF];
+#pragma unroll
+		for (int j = 0; j < CPL; ++j)
+		{
+			tmp[j] = PM[j];
+			tmp[CPL + j] = PE[j];
+		}
+		tmp[2 * CPL] = __int_as_float(lane);
+#pragma unroll
+		for (int q = 2 * CPL + 1; q < Rec::NF; ++q) tmp[q] = 0.0f;
+#pragma unroll
+		for (int q = 0; q < Rec::NF / 4; ++q) st_v4_if(wr, dst + 4 * q, tmp[4 * q], tmp[4 * q + 1], tmp[4 * q + 2], tmp[4 * q + 3]);
+		const uint32_t nn = rs.n + __popc(hm);
+		rs.overflow = rs.overflow || (nn > rs.cap);
+		rs.n = (nn > rs.cap) ? (uint32_t)rs.cap : nn;
+	}
+	const float fl = (flraw * f.sL1) * f.sL2;
+#pragma unroll
+	for (int j = 0; j < CPL; ++j)
+	{
+		bc[j] = bn[j];
+		bn[j] = pf[CFG::ROWF + j * 32 + lane];
+	}
+#pragma unroll
+	for (int j = CPL - 1; j >= 0; --j)
+	{
+		const float left = (j > 0) ? f.fE[j - 1] : fl;
+		const float ne = fmaf(f.fE[j], e2, f.fM[j]) * p[j];  // (fM + fE*e2) * p    (NT:146-150, e1 = 1)
+		f.fM[j] = left * (p[j] * m1);                        // fE[t][n-1] * p * m1  (NT:143)
+		f.fE[j] = ne;
 	}
 }
 
@@ -585,6 +699,24 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 				if (DYN_RCP_UNROLL && RN == 4 && (i & 3) == 3 && ((cur.smask >> (i - 3)) & 0xfu) == 0u)
 				{
 					// four rows without a band slide in one basic block (see backward_pass)
+#if DYN_BWD_ROLL_RCP
+					float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF + lane;
+#pragma unroll 1
+					for (int q = 0; q < 3; ++q)
+					{
+						bwd_row<CFG>(w, b, __shfl_sync(FULL, cur.xv, i - q), m1, e2);
+#pragma unroll
+						for (int j = 0; j < CPL; ++j) dst[j * 32] = b.bE[j];
+						dst -= ROWF;
+					}
+					bwd_row<CFG>(w, b, __shfl_sync(FULL, cur.xv, i - 3), m1, e2);
+					bwd_renorm<CFG>(w, b);
+					sm.OB[((tt - 3 - (int)t_lo) / RN) * 32 + lane] = b.OB;
+#pragma unroll
+					for (int j = 0; j < CPL; ++j) dst[j * 32] = b.bE[j];
+					tt -= 4;
+					continue;
+#else
 					const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i - 1);
 					const float x2 = __shfl_sync(FULL, cur.xv, i - 2), x3 = __shfl_sync(FULL, cur.xv, i - 3);
 					float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
@@ -604,9 +736,23 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane - 3 * ROWF] = b.bE[j];
 					tt -= 4;
 					continue;
+#endif
 				}
 				const float x = __shfl_sync(FULL, cur.xv, i);
-				bwd_step<CFG>(w, b, x, (cur.smask >> i) & 1u, mid_b, m1, e2);
+				const bool sl = (cur.smask >> i) & 1u;
+				if (sl)
+				{
+					// the column that enters the band at row tt: (tt+1, n) is out of band, but its slot kept computing the
+					// ungated M-transition term (see bwd_step); zero it in the stored row tt+1 so that the forward pass
+					// gets bM[tt][n] = bE[tt+1][n] * p = 0 without a special case
+					const int nb = mid_b - 1 - w.bw;
+					if (nb >= 0)
+					{
+						const int q = pmod(nb, CFG::SLOTS);
+						if (lane == q / CPL) sm.bE[(size_t)(tt + 1 - (int)t_lo) * ROWF + (q % CPL) * 32 + lane] = 0.0f;
+					}
+				}
+				bwd_step<CFG>(w, b, x, sl, mid_b, m1, e2);
 				float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
 				if ((tt & (RN - 1)) == 0)
 				{
@@ -668,6 +814,53 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 		{
 			const int i = t & 31;
 			const uint32_t r = t - t_lo;
+			if (DYN_FWD_FAST && args.fwd_fast && RN == 4 && (t & 3u) == 0 && t + 4 <= t_end)
+			{
+				// an aligned group of RN rows inside the block: the branch-free row body (see fwd_row_fast)
+				const unsigned sl4 = (cur.smask >> i) & 0xfu;
+				const float kapN = kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0);
+				if ((t & (CFG::RV - 1)) == 0) vit_renorm<CFG>(w, f);
+				float kapE = f.kap;
+				const float* pf = sm.bE + (size_t)(r + 1) * ROWF;
+				if (sl4 == 0u)
+				{
+#pragma unroll 1
+					for (int q = 0; q < 4; ++q)
+					{
+						const float x = __shfl_sync(FULL, cur.xv, i + q);
+						fwd_row_fast<CFG>(w, f, sc, rs, thr, t + q, x, bc, bn, pf, kapE, kapN, m1, e2);
+						kapE = kapN;
+						pf += ROWF;
+					}
+				}
+				else
+				{
+					// a band slide between rows t+q and t+q+1: the column entering band(t+q+1) is activated before the row,
+					// the column leaving is retired after it; the match posterior of the leaving column is forced through
+					// the zero the recomputation wrote into the backward row t+q+1 (see step a)
+#pragma unroll 1
+					for (int q = 0; q < 4; ++q)
+					{
+						const bool sl = (sl4 >> q) & 1u;
+						const float x = __shfl_sync(FULL, cur.xv, i + q);
+						if (sl) w.activate(mid_f + 1 + w.bw);
+						fwd_row_fast<CFG>(w, f, sc, rs, thr, t + q, x, bc, bn, pf, kapE, kapN, m1, e2);
+						if (sl)
+						{
+							const int nold = mid_f - w.bw;
+							if (nold >= 0)
+								with_slot<CPL>(lane, pmod(nold, CFG::SLOTS), SetEmisState<CPL>{w.em, 0.0f, w.b_off(), CNEG, f.fM, f.fE, 0.0f});
+							++mid_f;
+						}
+						kapE = kapN;
+						pf += ROWF;
+					}
+				}
+				f.kap = kapN;
+				fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 4) / RN) * 32 + lane], Z2i, c0);
+				t += 4;
+				continue;
+			}
 			if (DYN_FWD_UNROLL && RN == 4 && (t & 1u) == 0 && t + 1 < t_end && ((cur.smask >> i) & 0x3u) == 0u)
 			{
 				// two rows without a band slide in one basic block: the emissions of the second row overlap the tail of
@@ -734,23 +927,65 @@ DYN_DEV int traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs&
 
 	const Rec* recs = static_cast<const Rec*>(sc.recs);
 	bool bad = false;
-	for (uint32_t r = t_first + lane; r < T; r += 32)
+	// NR rows per lane and iteration: the row's path cell, its record range and its first record (vector loads) are
+	// fetched for all NR rows before anything is consumed, so a lane has NR independent chains of dependent loads in
+	// flight instead of one (the records of a long read come from DRAM)
+	constexpr int NR = 4;
+	constexpr int NV = Rec::NF / 4;
+	for (uint32_t rb = t_first; rb < T; rb += 32 * NR)
 	{
-		const uint32_t v = sc.pn[r];
-		const uint32_t col = v & 0x7fffffffu;
-		const bool isM = (v >> 31) != 0;
-		const int q = (int)(col % SLOTS);
-		const int ql = q / CPL, j = q - ql * CPL;
-		const uint32_t r0 = sc.rowptr[r], r1 = sc.rowptr[r + 1];
-		float mass = 0.0f, lp = 0.0f;
-		for (uint32_t i = r0; i < r1; ++i)
+		uint32_t pv[NR], r0[NR], r1[NR];
+#pragma unroll
+		for (int q = 0; q < NR; ++q)
 		{
-			const float* f = recs[i].v;
-			for (int c = 0; c < 2 * CPL; ++c) mass += f[c];
-			if (__float_as_int(f[2 * CPL]) == ql) lp = f[(isM ? 0 : CPL) + j];
+			const uint32_t r = rb + q * 32 + lane;
+			const bool in = r < T;
+			pv[q] = in ? sc.pn[r] : 0u;
+			r0[q] = in ? sc.rowptr[r] : 0u;
+			r1[q] = in ? sc.rowptr[r + 1] : 0u;
 		}
-		if (!(fabsf(mass - 1.0f) <= LIN_MASS_TOL)) bad = true;
-		sc.pp[r] = lp / mass;
+		float4 rv[NR][NV];
+#pragma unroll
+		for (int q = 0; q < NR; ++q)
+		{
+			const float4* src = reinterpret_cast<const float4*>(recs + r0[q]);
+			const bool has = r1[q] > r0[q];
+#pragma unroll
+			for (int k = 0; k < NV; ++k) rv[q][k] = has ? src[k] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		}
+#pragma unroll
+		for (int q = 0; q < NR; ++q)
+		{
+			const uint32_t r = rb + q * 32 + lane;
+			if (r >= T) continue;
+			const uint32_t col = pv[q] & 0x7fffffffu;
+			const bool isM = (pv[q] >> 31) != 0;
+			const int sl = (int)(col % SLOTS);
+			const int ql = sl / CPL, j = sl - ql * CPL;
+			const int want = (isM ? 0 : CPL) + j;
+			float mass = 0.0f, lp = 0.0f;
+			if (r1[q] > r0[q])
+			{
+				// first record, from registers: same summation order as the loop below
+				float pick = 0.0f;
+#pragma unroll
+				for (int c = 0; c < 2 * CPL; ++c)
+				{
+					const float fc = f4_get(rv[q][c >> 2], c & 3);
+					mass += fc;
+					pick = (c == want) ? fc : pick;
+				}
+				if (__float_as_int(f4_get(rv[q][(2 * CPL) >> 2], (2 * CPL) & 3)) == ql) lp = pick;
+			}
+			for (uint32_t i = r0[q] + 1; i < r1[q]; ++i)
+			{
+				const float* f = recs[i].v;
+				for (int c = 0; c < 2 * CPL; ++c) mass += f[c];
+				if (__float_as_int(f[2 * CPL]) == ql) lp = f[want];
+			}
+			if (!(fabsf(mass - 1.0f) <= LIN_MASS_TOL)) bad = true;
+			sc.pp[r] = lp / mass;
+		}
 	}
 	// rows before the first path row (t_first > 1 never happens for a complete path, which starts at row 1)
 	if (__any_sync(FULL, bad)) return 2;
@@ -841,6 +1076,8 @@ DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx
 	w.pc = args.pc + rd.pc_off;
 	w.m1 = args.m1;
 	w.e2 = args.e2;
+	w.ua = args.uni_a;
+	w.uc = args.uni_c;
 	const float m1 = args.m1_lin, e2 = args.e2_lin;
 
 	ReadOut out;

@@ -148,9 +148,23 @@ namespace
 //   variant 1: CK =  8, 10 CTAs/SM (<= 200 registers, 16 KB smem)     scratch 448 B/row
 //   variant 2: CK =  8, 12 CTAs/SM (<= 168 registers, 16 KB smem)     scratch 448 B/row
 //   variant 3: CK =  8, 8 CTAs/SM (<= 255 registers, 16 KB smem)      scratch 448 B/row
+//   variants 4 .. 8: the uniform-sigma linear-domain kernels (Cfg::UNI) at 8 / 9 / 10 / 11 / 12 CTAs/SM (255 / 224 / 200 /
+//                    184 / 168 registers); chosen only when every kmer of the model has the same sigma, otherwise they
+//                    map to the general variants 3 / 9 / 1 / 1 / 2.  The log2-domain re-run of faulted reads uses the
+//                    general kernels of variant 3.
+//   variant 9: CK = 8, 9 CTAs/SM (<= 224 registers), general kernels
 using Cfg16 = Cfg<13, 16, 4, 8>;
 using Cfg8 = Cfg<13, 8, 4, 8>;
-constexpr int N_VARIANTS = 4;
+using Cfg8U = Cfg<13, 8, 4, 8, true>;
+constexpr int N_VARIANTS = 10;
+// experiment builds: -DDYN_ONLY_VARIANT=n compiles the kernels of one variant only (seconds instead of minutes)
+#ifdef DYN_ONLY_VARIANT
+#define DYN_HAS(n) ((n) == DYN_ONLY_VARIANT)
+#else
+#define DYN_HAS(n) 1
+#endif
+constexpr int DEFAULT_VARIANT = 3;      // measured fastest on B200
+constexpr int DEFAULT_VARIANT_UNI = 4;  // uniform-sigma models
 
 struct EncodeArgs
 {
@@ -355,8 +369,11 @@ __global__ void __launch_bounds__(32) k_encode(EncodeArgs a)
 {
 	for (uint32_t r = blockIdx.x; r < a.n_reads; r += gridDim.x) encode_read(a, r, threadIdx.x);
 }
+// register budget for MINB resident single-warp CTAs per SM (64 K registers, allocation granularity 8 per thread).
+// __launch_bounds__(32, MINB) makes ptxas fall to 168 registers for every MINB > 8; __maxnreg__ gives the exact budget.
+constexpr int max_regs(int minb) { return (65536 / (32 * minb) / 8 * 8) > 255 ? 255 : (65536 / (32 * minb) / 8 * 8); }
 template <class CFG, int MODE, int MINB, bool LIN>
-__global__ void __launch_bounds__(32, MINB) k_align(BatchArgs args)
+__global__ void __launch_bounds__(32) __maxnreg__(max_regs(MINB)) k_align(BatchArgs args)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	align_worker<CFG, MODE, LIN>(args, smem_raw, threadIdx.x, blockIdx.x);
@@ -406,11 +423,11 @@ void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 }
 
 // lin: the linear-domain kernels (dp_linear.cuh); otherwise the log2-domain kernels (dp_kernels.cuh)
-template <class CFG, int MINB>
+template <class CFG, int MINB, class CFGLIN, int MINB_FB>
 void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode, bool lin)
 {
-	if (lin) launch_align_t<CFG, MINB, true>(rt, args, grid, mode);
-	else launch_align_t<CFG, MINB, false>(rt, args, grid, mode);
+	if (lin) launch_align_t<CFGLIN, MINB, true>(rt, args, grid, mode);
+	else launch_align_t<CFG, MINB_FB, false>(rt, args, grid, mode);
 }
 
 void launch_fold(Rt& rt, const FoldArgs& a)
@@ -476,7 +493,10 @@ struct dyn_aligner
 	std::vector<double> mean, stdev;
 	// tuning
 	int warps_per_sm = 0;  // 0 = the variant's own occupancy
-	int variant = 3;  // measured fastest on B200
+	int variant = -1;  // -1: DEFAULT_VARIANT / DEFAULT_VARIANT_UNI (measured fastest on B200)
+	int fwd_fast = 1;  // linear-domain pass 2: branch-free row body for groups of rows without a band slide
+	bool uniform = false;  // every kmer has the same sigma (set by upload_table): the Cfg::UNI kernels apply
+	float uni_a = 0.0f, uni_c = 0.0f;
 	bool ntk = false; // resquiggle (NTK) mode: only the pre-pass stages are built (dyn_ntk_prepass)
 	double ntk_trans[18] = {0};  // log a1,a2,p1-3,s1-3,e1-4,i1,i2, then log ntMatch/ntExtend for TN and TK (NTK:35-104)
 	int arith = 0;    // 0: linear-domain kernels, reads with an FP32 range fault re-run in the log2 domain; 1: log2 domain only
@@ -583,6 +603,10 @@ void dyn_aligner::upload_table()
 		t[q].c = (float)(-std::log2(sd) - 0.5 * std::log2(2.0 * M_PI));
 		t[q].pad = 0.0f;
 	}
+	uniform = K > 0;
+	for (uint64_t q = 1; q < K && uniform; ++q) uniform = (t[q].a == t[0].a && t[q].c == t[0].c);
+	uni_a = K ? t[0].a : 0.0f;
+	uni_c = K ? t[0].c : 0.0f;
 	void* d = d_table.get(rt, K * sizeof(PosConst));
 	rt.h2d(d, t.data(), K * sizeof(PosConst));
 	rt.sync();
@@ -616,7 +640,7 @@ struct BatchResult
 };
 
 // mode: 0 Z only, 1 align, 2 train.  sigpos/prob (host) receive the segment arrays for mode 1.
-template <class CFG, int MINB>
+template <class CFG, int MINB, class CFGLIN = CFG, int MINB_FB = MINB>
 void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
 	double* pooled, double* per_read_w)
 {
@@ -790,6 +814,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	ba.e2_lin = (float)std::exp(A.trans[2]);
 	ba.thr_lin = (float)std::exp2(A.thr2);
 	ba.mode = mode;
+	ba.uni_a = A.uni_a;
+	ba.uni_c = A.uni_c;
+	ba.fwd_fast = A.fwd_fast;
 	ba.kmers = d_kmers;
 	if (mode == 2)
 	{
@@ -811,7 +838,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	const bool lin = (A.arith == 0);
 	A.n_fallback = 0;
 	rt.mark(2);
-	launch_align<CFG, MINB>(rt, ba, grid, mode, lin);
+	launch_align<CFG, MINB, CFGLIN, MINB_FB>(rt, ba, grid, mode, lin);
 	rt.mark(3);
 	int launches = 2;
 	double fallback_ms = 0.0;
@@ -830,7 +857,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			rt.zero(d_queue, 64);
 			ba.n_reads = (uint32_t)again.size();
 			rt.mark(4);
-			launch_align<CFG, MINB>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode, false);
+			launch_align<CFG, MINB, CFGLIN, MINB_FB>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode, false);
 			rt.mark(5);
 			rt.sync();
 			fallback_ms = rt.elapsed(4, 5);
@@ -881,12 +908,47 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
 	double* pooled, double* per_read_w)
 {
-	switch (A.variant)
+	int v = A.variant;
+	if (v < 0) v = A.uniform ? DEFAULT_VARIANT_UNI : DEFAULT_VARIANT;
+	if (v >= 4 && v <= 8 && !A.uniform)
 	{
+		static const int general[5] = {3, 9, 1, 1, 2};
+		v = general[v - 4];
+	}
+	switch (v)
+	{
+#if DYN_HAS(4)
+	case 4: run_batch_t<Cfg8, 8, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(5)
+	case 5: run_batch_t<Cfg8, 9, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(6)
+	case 6: run_batch_t<Cfg8, 10, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(7)
+	case 7: run_batch_t<Cfg8, 11, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(8)
+	case 8: run_batch_t<Cfg8, 12, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(9)
+	case 9: run_batch_t<Cfg8, 9, Cfg8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(1)
 	case 1: run_batch_t<Cfg8, 10>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(2)
 	case 2: run_batch_t<Cfg8, 12>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(3)
 	case 3: run_batch_t<Cfg8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(0)
 	default: run_batch_t<Cfg16, 7>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#else
+	default: throw std::runtime_error("dynamont_b200: kernel variant not built (DYN_ONLY_VARIANT)");
+#endif
 	}
 }
 
@@ -1756,7 +1818,8 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	const std::string k(key);
 	if (k == "warps_per_sm") A->warps_per_sm = std::max(0, (int)value);
 	else if (k == "arith") A->arith = std::min(1, std::max(0, (int)value));
-	else if (k == "variant") A->variant = std::min(N_VARIANTS - 1, std::max(0, (int)value));
+	else if (k == "variant") A->variant = std::min(N_VARIANTS - 1, std::max(-1, (int)value));
+	else if (k == "fwd_fast") A->fwd_fast = value != 0.0 ? 1 : 0;
 	else if (k == "thr2") A->thr2 = value;
 	else if (k == "recs_per_row") A->recs_per_row = value;
 	else if (k == "mem_fraction") A->mem_fraction = value;

@@ -36,6 +36,7 @@ struct uint4
 {
 	unsigned x, y, z, w;
 };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 struct dim3e
 {
 	unsigned x = 1, y = 1, z = 1;

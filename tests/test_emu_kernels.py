@@ -74,12 +74,55 @@ def test_emulated_range_fault_falls_back(emu_lib):
     np.testing.assert_allclose(pooled_lin["w"], pooled_log["w"], rtol=1e-12)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 8, 9, -1])
 def test_emulated_variants(variant, emu_lib):
+    """build variants: general kernels (0-3, 9), uniform-sigma kernels (4-8), library default (-1)"""
     case = [c for c in load_golden() if c.name == "rna002_band"][0]
     al = _aligner(emu_lib, case, variant)
     r = al.align(case.signal, case.sequence, True)
     check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    assert al.last_timing()["log2_fallback_reads"] == 0
+
+
+@pytest.mark.parametrize("variant", [3, 4])
+def test_emulated_generic_forward_rows(variant, emu_lib):
+    """pass 2 with the branch-free row body switched off must give the same alignment as with it"""
+    case = [c for c in load_golden() if c.name == "rna002_dinuc"][0]
+    al = _aligner(emu_lib, case, variant)
+    al.set_option("fwd_fast", 0)
+    r = al.align(case.signal, case.sequence, True)
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    al.set_option("fwd_fast", 1)
+    r1 = al.align(case.signal, case.sequence, True)
+    assert np.array_equal(r["signal_positions"], r1["signal_positions"])
+    np.testing.assert_allclose(r["probabilities"], r1["probabilities"], atol=2e-6)
+
+
+def test_emulated_nonuniform_model_uses_general_kernels(emu_lib):
+    """a trained model (per-kmer sigma) asked for a uniform-sigma variant runs the general kernels"""
+    case = [c for c in load_golden() if c.name == "rna002_trained"][0]
+    al = _aligner(emu_lib, case, 6)
+    r = al.align(case.signal, case.sequence, True)
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+
+
+def test_emulated_uniform_training_and_narrow_band(emu_lib):
+    """uniform-sigma kernels: training statistics and a band narrow enough to slide every other row"""
+    from dynamont_b200 import Aligner
+    from oracle import Oracle
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    al = _aligner(emu_lib, case, 5)
+    per_read, pooled = al.train_batch([case.signal], [case.sequence], per_read_model=True)
+    tp = per_read[0]["transition_params"]
+    np.testing.assert_allclose([tp["m1"], tp["e1"], tp["e2"]], case.train_trans, rtol=TRAIN_RTOL)
+    heavy = case.stat_w > 1e-3
+    np.testing.assert_allclose(pooled["w"][case.train_kmers][heavy], case.stat_w[heavy], rtol=TRAIN_RTOL)
+    case = [c for c in load_golden() if c.name == "rna002_min_dwell"][0]
+    al = Aligner(case.model_path, case.pore, band=40, _lib_path=emu_lib)
+    al.set_option("variant", 4)
+    o = Oracle(case.model_path, case.pore, band=40).align(case.signal, case.sequence, True)
+    check_alignment(al.align(case.signal, case.sequence, True), o["signal_positions"], o["sequence_positions"],
+                    o["probabilities"], o["Z"])
 
 
 def test_emulated_training(emu_lib):
