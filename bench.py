@@ -36,6 +36,20 @@ CONFIGS = {
 MODELS_DIR = os.path.join(ROOT, "tests", "golden", "_models")
 
 
+# k_align template instances of the build variants (csrc/engine.cu): (Cfg, resident single-warp CTAs per SM)
+VARIANT_KERNELS = {0: ("Cfg<13,16,4,8>", 7), 1: ("Cfg<13,8,4,8>", 10), 2: ("Cfg<13,8,4,8>", 12), 3: ("Cfg<13,8,4,8>", 8),
+                   4: ("Cfg<13,8,4,8,UNI>", 8), 5: ("Cfg<13,8,4,8,UNI>", 9), 6: ("Cfg<13,8,4,8,UNI>", 10),
+                   7: ("Cfg<13,8,4,8,UNI>", 11), 8: ("Cfg<13,8,4,8,UNI>", 12), 9: ("Cfg<13,8,4,8>", 9)}
+
+
+def kernel_label(variant, lin):
+    cfg, minb = VARIANT_KERNELS.get(variant, ("Cfg<?>", 0))
+    if not lin:
+        return f"k_align<{cfg.replace(',UNI', '')},1,{minb},LIN=0> (log2-domain FP32, 2 MUFU per cell-update)"
+    uni = " uniform-sigma emission constants," if "UNI" in cfg else ""
+    return f"k_align<{cfg},1,{minb},LIN=1> (linear-domain FP32,{uni} 1 MUFU per cell-update)"
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -426,8 +440,7 @@ def main():
     hbm_bytes = n_samples * 4.0 + n_bases * 17.0 + (n_samples / 8.0) * 3584 * 2 + n_samples * 64.0 * 2 + n_samples * 125.0 * 2
     roofline = {
         "bound": "sfu",
-        "kernel": ("k_align<Cfg<13,8,4,8>,1,8,LIN=1> (linear-domain FP32, 1 MUFU per cell-update)" if lin else
-                   "k_align<Cfg<13,8,4,8>,1,8,LIN=0> (log2-domain FP32, 2 MUFU per cell-update)"),
+        "kernel": kernel_label(al.last_timing()["variant"], lin),
         "achieved": alg_mufu, "peak": mufu_peak, "unit": "G MUFU op/s", "frac": alg_mufu / mufu_peak,
         "achieved_definition": "algorithmic: 4 MUFU per lattice cell (log-space forward + backward, SURVEY 8d) x cells / kernel time",
         "executed": exe_mufu, "executed_frac": exe_mufu / mufu_peak,
@@ -435,7 +448,7 @@ def main():
         "cell_updates_per_s": 3.0 * cells / dp_s, "kernel_ms": dp_ms_all,
         "log2_fallback_reads": int(fallbacks),
         "traffic": None,
-        "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1d_k_align_lin_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
+        "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1i_k_align_uni_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
         "hbm": {"achieved": hbm_bytes / dp_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "note": "algorithmic signal + constants + checkpoint/decision-bit/record spill per launch"},
     }

@@ -197,7 +197,8 @@ class Aligner:
         t = np.zeros(3)
         self._lib.dyn_last_timing(self._h, t.ctypes.data_as(f64p))
         return {"encode_ms": t[0], "dp_ms": t[1], "launches": int(t[2]),
-                "log2_fallback_reads": int(self._lib.dyn_last_fallbacks(self._h))}
+                "log2_fallback_reads": int(self._lib.dyn_last_fallbacks(self._h)),
+                "variant": int(self._lib.dyn_last_variant(self._h))}
 
     @staticmethod
     def _pack(signals, sequences, dtype):

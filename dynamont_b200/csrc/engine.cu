@@ -501,6 +501,7 @@ struct dyn_aligner
 	double ntk_trans[18] = {0};  // log a1,a2,p1-3,s1-3,e1-4,i1,i2, then log ntMatch/ntExtend for TN and TK (NTK:35-104)
 	int arith = 0;    // 0: linear-domain kernels, reads with an FP32 range fault re-run in the log2 domain; 1: log2 domain only
 	uint64_t n_fallback = 0;  // reads of the last batch that were re-run in the log2 domain
+	int last_variant = -1;    // resolved build variant of the last batch
 	double thr2 = -22.0;
 	double recs_per_row = 2.0;  // lane records per row (typical use: ~1.1)
 	double mem_fraction = 0.85;
@@ -915,6 +916,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 		static const int general[5] = {3, 9, 1, 1, 2};
 		v = general[v - 4];
 	}
+	A.last_variant = v;
 	switch (v)
 	{
 #if DYN_HAS(4)
@@ -1793,6 +1795,7 @@ const char* dyn_status_message(int status)
 const char* dyn_last_error(const dyn_aligner* A) { return A->last_error.c_str(); }
 
 uint64_t dyn_last_fallbacks(const dyn_aligner* A) { return A->n_fallback; }
+int dyn_last_variant(const dyn_aligner* A) { return A->last_variant; }
 
 void dyn_last_timing(const dyn_aligner* A, double* out3)
 {

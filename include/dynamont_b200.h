@@ -175,6 +175,9 @@ void dyn_last_timing(const dyn_aligner*, double* out3);
 /* number of reads of the last batch call that the FP32 linear-domain kernels could not represent and that were
  * re-run by the log2-domain kernels (same GPU); results are identical either way */
 uint64_t dyn_last_fallbacks(const dyn_aligner*);
+/* kernel build variant the last batch call ran (csrc/engine.cu: 3 = general kernels at 8 CTAs/SM, 4 = uniform-sigma
+ * kernels at 8 CTAs/SM, ...); -1 before the first call */
+int dyn_last_variant(const dyn_aligner*);
 /* run all work of this handle on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
  * of the handle's own stream, so that the caller's CUDA events bracket it */
 int dyn_set_stream(dyn_aligner*, void* cuda_stream);
