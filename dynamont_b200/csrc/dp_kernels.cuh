@@ -837,20 +837,52 @@ DYN_DEV float forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const 
 // ------------------------------------------------------------------------------------------------------
 // pass 3: traceback (NT:383-456), path posteriors, per-segment medians (aligner.cpp:247-263)
 // ------------------------------------------------------------------------------------------------------
-// median of d <= 32 values (one per lane; lanes >= d hold +inf) by ranking: the lane whose value has rank k owns
-// the k-th smallest.  Returns (k-th smallest, (k-1)-th smallest) broadcast to all lanes.
+// median of d <= 32 values (one per lane; lanes >= d hold a value above every real one) by ranking: the lane whose
+// value has rank k owns the k-th smallest.  Returns (k-th smallest, (k-1)-th smallest) broadcast to all lanes.  The 32
+// shuffles are independent of each other (fully unrolled), so they pipeline instead of paying their latency 32 times.
 DYN_DEV void rank_select(float v, uint32_t d, uint32_t k, int lane, float& kth, float& prev)
 {
 	uint32_t rank = 0;
-	for (uint32_t s = 0; s < d; ++s)
+#pragma unroll
+	for (int s = 0; s < 32; ++s)
 	{
-		const float o = __shfl_sync(FULL, v, (int)s);
-		rank += (o < v || (o == v && (int)s < lane)) ? 1u : 0u;
+		const float o = __shfl_sync(FULL, v, s);
+		rank += (o < v || (o == v && s < lane)) ? 1u : 0u;
 	}
 	const unsigned mk = __ballot_sync(FULL, lane < (int)d && rank == k);
 	const unsigned mp = __ballot_sync(FULL, lane < (int)d && rank + 1 == k);
 	kth = __shfl_sync(FULL, v, __ffs(mk) - 1);
 	prev = mp ? __shfl_sync(FULL, v, __ffs(mp) - 1) : kth;
+}
+
+// the same for d <= 32*NV non-negative values held in registers (value i in lane i % 32, slot i / 32; unused slots hold
+// a value above every real one): bisection on the bit pattern, one vote per slot and step.  prev = (k-1)-th smallest.
+template <int NV>
+DYN_DEV void reg_select(const float (&v)[NV], uint32_t k, int lane, float& kth, float& prev)
+{
+	uint32_t lo = 0u, hi = 0x7f800000u;
+	while (lo < hi)
+	{
+		const uint32_t midv = lo + (hi - lo) / 2;
+		uint32_t cnt = 0;
+#pragma unroll
+		for (int q = 0; q < NV; ++q) cnt += __popc(__ballot_sync(FULL, __float_as_uint(v[q]) <= midv));
+		if (cnt >= k + 1) hi = midv;
+		else lo = midv + 1;
+	}
+	kth = __uint_as_float(lo);
+	// sorted s[k] = kth.  s[k-1] = kth when fewer than k values lie strictly below it, else the largest of those
+	uint32_t below = 0, mx = 0;
+#pragma unroll
+	for (int q = 0; q < NV; ++q)
+	{
+		const uint32_t bits = __float_as_uint(v[q]);
+		const bool lt = bits < lo;
+		below += __popc(__ballot_sync(FULL, lt));
+		mx = max(mx, lt ? bits : 0u);
+	}
+	for (int o = 16; o; o >>= 1) mx = max(mx, (uint32_t)__shfl_sync(FULL, (int)mx, (lane + o) & 31));
+	prev = (below == k && k > 0) ? __uint_as_float(mx) : kth;
 }
 
 // k-th smallest (0-based) of d non-negative floats at v[0..d) (global memory), all lanes cooperating: binary
@@ -1008,30 +1040,66 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 template <class CFG>
 DYN_DEV void segment_medians(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd)
 {
+	constexpr int NV = 4;           // register path: dwells up to 32 * NV samples
+	constexpr float PAD = 3.0e38f;  // above every posterior
 	const int lane = w.lane;
 	const uint32_t T = w.T, N = w.N;
 	const uint32_t* border = args.out_sigpos + rd.out_off;
 	double* prob = args.out_prob + rd.out_off;
 	const uint32_t Kc = N - 1;
-	uint32_t rs_ = border[0] + 1;
-	for (uint32_t sgm = 0; sgm < Kc; ++sgm)
+	// segment s covers rows border[s] + 1 .. ext(s + 1), ext(s) = border[s] for s < Kc, T - 1 for s = Kc.
+	// Borders are fetched 32 segments at a time and the path posteriors of the NEXT segment are requested before the
+	// current one is ranked, so the dependent loads (border -> posteriors) are off the critical path.
+	for (uint32_t s0 = 0; s0 < Kc; s0 += 32)
 	{
-		const uint32_t re = (sgm + 1 < Kc) ? border[sgm + 1] : (T - 1);  // inclusive
-		const uint32_t d = re - rs_ + 1;
-		const float* v = sc.pp + rs_;
-		float up, dn;
-		if (d <= 32)
+		const uint32_t mine = (s0 + lane < Kc) ? border[s0 + lane] : (T - 1);
+		const uint32_t last = (s0 + 32 < Kc) ? border[s0 + 32] : (T - 1);
+		const uint32_t ns = min(32u, Kc - s0);
+		// ext(s0 + j), j = 0 .. 32
+		auto ext_at = [&](uint32_t j) -> uint32_t {
+			const uint32_t e = __shfl_sync(FULL, mine, (int)(j & 31u));
+			return (j < 32u) ? e : last;
+		};
+		float cur[NV], nxt[NV];
+		uint32_t c_rs = ext_at(0) + 1, c_re = ext_at(1);
+#pragma unroll
+		for (int q = 0; q < NV; ++q)
 		{
-			const float mine = ((uint32_t)lane < d) ? v[lane] : 3.0e38f;
-			rank_select(mine, d, d / 2, lane, up, dn);
+			const uint32_t idx = c_rs + q * 32 + lane;
+			cur[q] = (idx <= c_re) ? sc.pp[idx] : PAD;
 		}
-		else
+		for (uint32_t j = 0; j < ns; ++j)
 		{
-			up = coop_select(v, d, d / 2, lane);
-			dn = (d & 1u) ? up : coop_select(v, d, d / 2 - 1, lane);
+			uint32_t n_rs = 0, n_re = 0;
+#pragma unroll
+			for (int q = 0; q < NV; ++q) nxt[q] = PAD;
+			if (j + 1 < ns)
+			{
+				n_rs = ext_at(j + 1) + 1;
+				n_re = ext_at(j + 2);
+#pragma unroll
+				for (int q = 0; q < NV; ++q)
+				{
+					const uint32_t idx = n_rs + q * 32 + lane;
+					nxt[q] = (idx <= n_re) ? sc.pp[idx] : PAD;
+				}
+			}
+			const uint32_t d = c_re - c_rs + 1;
+			float up, dn;
+			if (d <= 32) rank_select(cur[0], d, d / 2, lane, up, dn);
+			else if (d <= 32 * NV) reg_select<NV>(cur, d / 2, lane, up, dn);
+			else
+			{
+				const float* v = sc.pp + c_rs;
+				up = coop_select(v, d, d / 2, lane);
+				dn = (d & 1u) ? up : coop_select(v, d, d / 2 - 1, lane);
+			}
+			if (lane == 0) prob[s0 + j] = (d & 1u) ? (double)up : ((double)dn + (double)up) / 2.0;
+			c_rs = n_rs;
+			c_re = n_re;
+#pragma unroll
+			for (int q = 0; q < NV; ++q) cur[q] = nxt[q];
 		}
-		if (lane == 0) prob[sgm] = (d & 1u) ? (double)up : ((double)dn + (double)up) / 2.0;
-		rs_ = re + 1;
 	}
 }
 
