@@ -90,6 +90,13 @@ struct Rt
 		if (async_alloc) cudaFreeAsync(p, stream);
 		else cudaFree(p);
 	}
+	void* hmalloc(size_t n)
+	{
+		void* p = nullptr;
+		CK_CUDA(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault));  // pinned: device-to-host copies at link speed
+		return p;
+	}
+	void hfree(void* p) { cudaFreeHost(p); }
 	void h2d(void* d, const void* h, size_t n) { CK_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, stream)); }
 	void d2h(void* h, const void* d, size_t n) { CK_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, stream)); }
 	void zero(void* d, size_t n) { CK_CUDA(cudaMemsetAsync(d, 0, n, stream)); }
@@ -124,6 +131,8 @@ struct Rt
 	void bind() {}
 	void* dmalloc(size_t n) { return malloc(n ? n : 1); }
 	void dfree(void* p) { free(p); }
+	void* hmalloc(size_t n) { return malloc(n ? n : 1); }
+	void hfree(void* p) { free(p); }
 	void h2d(void* d, const void* h, size_t n) { memcpy(d, h, n); }
 	void d2h(void* h, const void* d, size_t n) { memcpy(h, d, n); }
 	void zero(void* d, size_t n) { memset(d, 0, n); }
@@ -471,7 +480,77 @@ struct DevBuf
 	}
 };
 
+// pinned host staging buffer that only ever grows (results of a batch land here before they are fanned out into the
+// caller's arrays by a few host threads)
+struct HostBuf
+{
+	void* p = nullptr;
+	size_t cap = 0;
+	void* get(Rt& rt, size_t n)
+	{
+		if (n > cap)
+		{
+			if (p) rt.hfree(p);
+			p = nullptr;
+			cap = 0;
+			const size_t want = n + n / 4;
+			p = rt.hmalloc(want);
+			cap = want;
+		}
+		return p;
+	}
+	void release(Rt& rt)
+	{
+		if (p) rt.hfree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// host phases of a batch call, printed to stderr when DYN_TIMING is set (bench.py reports the kernel time separately)
+struct HostTimer
+{
+	bool on;
+	std::chrono::steady_clock::time_point t0;
+	std::string log;
+	HostTimer() : on(getenv("DYN_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+	void lap(const char* what)
+	{
+		if (!on) return;
+		const auto t1 = std::chrono::steady_clock::now();
+		char b[96];
+		snprintf(b, sizeof(b), " %s=%.1fms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+		log += b;
+		t0 = t1;
+	}
+	~HostTimer()
+	{
+		if (on && !log.empty()) fprintf(stderr, "[dyn timing]%s\n", log.c_str());
+	}
+};
+
+// fn(begin, end) over [0, n) on up to 8 host threads (memory-bound fan-out of results; first-touch page faults of the
+// caller's arrays are spread over the threads too)
+template <class F>
+void parallel_ranges(uint32_t n, uint64_t work, F fn)
+{
+	unsigned nt = std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+	if (work < (1u << 20) || n < 2 * nt) nt = 1;
+	if (nt == 1)
+	{
+		fn(0u, n);
+		return;
+	}
+	std::vector<std::thread> th;
+	for (unsigned i = 0; i < nt; ++i)
+	{
+		const uint32_t a = (uint32_t)((uint64_t)n * i / nt), b = (uint32_t)((uint64_t)n * (i + 1) / nt);
+		th.emplace_back([=]() { fn(a, b); });
+	}
+	for (auto& t : th) t.join();
+}
 
 } // namespace
 
@@ -508,6 +587,7 @@ struct dyn_aligner
 	// device state
 	DevBuf d_table, d_sig, d_seq, d_seqoff, d_desc, d_order, d_pc, d_kmers, d_bad, d_out, d_sigpos, d_prob, d_scratch,
 		d_slots, d_queue, d_rw, d_rx, d_rxx, d_sw, d_sx, d_sxx;
+	HostBuf h_sigpos, h_prob;  // pinned staging of a batch's segment borders / probabilities
 	bool table_dirty = true;
 	double timing[3] = {0, 0, 0};
 
@@ -647,6 +727,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 {
 	Rt& rt = A.rt;
 	rt.bind();
+	HostTimer tm;
 	if (A.table_dirty) A.upload_table();
 	const uint32_t n = io.n;
 	res.out.assign(n, ReadOut{});
@@ -702,6 +783,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	for (uint32_t r = 0; r < n; ++r)
 		if (res.desc[r].status != ST_OK) res.out[r].status = res.desc[r].status;
 	if (order.empty()) return;
+	tm.lap("host_prep");
 
 	// ---- device inputs --------------------------------------------------------------------------------------------
 	const uint64_t sig_total = io.sig_off[n];
@@ -838,6 +920,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	// ---- K2..K5: the DP kernel ------------------------------------------------------------------------------------
 	const bool lin = (A.arith == 0);
 	A.n_fallback = 0;
+	tm.lap("enqueue");
 	rt.mark(2);
 	launch_align<CFG, MINB, CFGLIN, MINB_FB>(rt, ba, grid, mode, lin);
 	rt.mark(3);
@@ -848,6 +931,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		// reads the FP32 linear arithmetic could not represent (ST_LIN_FAULT) are re-run in the log2 domain
 		rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
 		rt.sync();
+		tm.lap("kernels");
 		std::vector<uint32_t> again;
 		for (uint32_t r : order)
 			if (res.out[r].status == ST_LIN_FAULT) again.push_back(r);
@@ -896,6 +980,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		rt.d2h(per_read_w + 2 * pc_total, ba.read_xx, pc_total * 8);
 	}
 	rt.sync();
+	tm.lap("results_d2h");
 	A.timing[0] = rt.elapsed(0, 1);
 	A.timing[1] = rt.elapsed(2, 3) + fallback_ms;
 	A.timing[2] = launches;
@@ -1037,6 +1122,8 @@ void dyn_destroy(dyn_aligner* A)
 				 &A->d_bad, &A->d_out, &A->d_sigpos, &A->d_prob, &A->d_scratch, &A->d_slots, &A->d_queue, &A->d_rw,
 				 &A->d_rx, &A->d_rxx, &A->d_sw, &A->d_sx, &A->d_sxx})
 			b->release(A->rt);
+		A->h_sigpos.release(A->rt);
+		A->h_prob.release(A->rt);
 		A->rt.fini();
 	}
 	catch (...)
@@ -1137,10 +1224,16 @@ static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilitie
 	try
 	{
 		if (A->ntk) throw std::runtime_error(NTK_PARTIAL);
+		HostTimer tm;
 		BatchResult res;
 		const uint64_t seg_total = dyn_count_segments(A, io.seq_off, io.n);
-		std::vector<uint32_t> sigpos(calc_probabilities ? seg_total : 0);
-		run_batch(*A, io, calc_probabilities ? 1 : 0, res, sigpos.data(), probabilities, nullptr, nullptr);
+		// device results land in pinned staging buffers and are fanned out into the caller's arrays below
+		A->rt.bind();
+		uint32_t* sigpos = (uint32_t*)A->h_sigpos.get(A->rt, (calc_probabilities ? seg_total : 0) * 4 + 4);
+		double* prob_st = (double*)A->h_prob.get(A->rt, (calc_probabilities ? seg_total : 0) * 8 + 8);
+		tm.lap("setup");
+		run_batch(*A, io, calc_probabilities ? 1 : 0, res, sigpos, prob_st, nullptr, nullptr);
+		tm.lap("run_batch");
 
 		// retry reads whose sparse posterior buffer overflowed, one by one with a full-size buffer
 		std::vector<uint32_t> retry;
@@ -1176,8 +1269,8 @@ static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilitie
 				if (io.seq_dev) sh.seq_dev = io.seq_dev + qo[0];
 				run_batch(*A, sh, 1, r1, sp.data(), pr.data(), nullptr, nullptr);
 				res.out[r] = r1.out[0];
-				std::copy(sp.begin(), sp.end(), sigpos.begin() + res.seg_off[r]);
-				std::copy(pr.begin(), pr.end(), probabilities + res.seg_off[r]);
+				std::copy(sp.begin(), sp.end(), sigpos + res.seg_off[r]);
+				std::copy(pr.begin(), pr.end(), prob_st + res.seg_off[r]);
 			}
 			A->recs_per_row = saved;
 		}
@@ -1199,17 +1292,27 @@ static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilitie
 					A->rt.sync();
 				}
 			}
-			if (o.status == ST_OK && calc_probabilities)
-			{
-				const uint64_t kc = res.seg_off[r + 1] - res.seg_off[r];
-				o.n_segments = kc;
-				for (uint64_t i = 0; i < kc; ++i)
-				{
-					sequence_positions[o.seg_offset + i] = i + (uint64_t)A->k / 2;  // n - 1 + k/2 (NT:421)
-					signal_positions[o.seg_offset + i] = sigpos[o.seg_offset + i];
-				}
-			}
+			if (o.status == ST_OK && calc_probabilities) o.n_segments = res.seg_off[r + 1] - res.seg_off[r];
 		}
+		if (calc_probabilities)
+		{
+			const uint64_t half_k = (uint64_t)A->k / 2;
+			parallel_ranges(io.n, seg_total, [&](uint32_t r_lo, uint32_t r_hi) {
+				for (uint32_t r = r_lo; r < r_hi; ++r)
+				{
+					const dyn_read_result& o = results[r];
+					if (o.status != ST_OK) continue;
+					const uint64_t off = o.seg_offset, kc = o.n_segments;
+					for (uint64_t i = 0; i < kc; ++i)
+					{
+						sequence_positions[off + i] = i + half_k;  // n - 1 + k/2 (NT:421)
+						signal_positions[off + i] = sigpos[off + i];
+					}
+					std::memcpy(probabilities + off, prob_st + off, kc * sizeof(double));
+				}
+			});
+		}
+		tm.lap("fan_out");
 		return 0;
 	}
 	catch (const std::exception& e)
