@@ -39,7 +39,8 @@ MODELS_DIR = os.path.join(ROOT, "tests", "golden", "_models")
 # k_align template instances of the build variants (csrc/engine.cu): (Cfg, resident single-warp CTAs per SM)
 VARIANT_KERNELS = {0: ("Cfg<13,16,4,8>", 7), 1: ("Cfg<13,8,4,8>", 10), 2: ("Cfg<13,8,4,8>", 12), 3: ("Cfg<13,8,4,8>", 8),
                    4: ("Cfg<13,8,4,8,UNI>", 8), 5: ("Cfg<13,8,4,8,UNI>", 9), 6: ("Cfg<13,8,4,8,UNI>", 10),
-                   7: ("Cfg<13,8,4,8,UNI>", 11), 8: ("Cfg<13,8,4,8,UNI>", 12), 9: ("Cfg<13,8,4,8>", 9)}
+                   7: ("Cfg<13,8,4,8,UNI>", 11), 8: ("Cfg<13,8,4,8,UNI>", 12), 9: ("Cfg<13,8,4,8>", 9),
+                   10: ("Cfg<13,8,8,8,UNI>", 8), 11: ("Cfg<13,8,8,8>", 8)}
 
 
 def kernel_label(variant, lin):

@@ -31,23 +31,11 @@
 
 #include "dp_kernels.cuh"
 
-#ifndef DYN_FWD_UNROLL
-#define DYN_FWD_UNROLL 0
-#endif
 #ifndef DYN_RCP_UNROLL
 #define DYN_RCP_UNROLL 1
 #endif
 #ifndef DYN_FWD_FAST
 #define DYN_FWD_FAST 1
-#endif
-// the slide-free 4-row groups of the backward passes: 0 = four rows unrolled into one basic block, 1 = a loop over a
-// one-row body (a quarter of the code: the recomputation alternates with the forward rows every CK rows, and the two
-// loops together have to stay resident in the instruction cache)
-#ifndef DYN_BWD_ROLL_P1
-#define DYN_BWD_ROLL_P1 1
-#endif
-#ifndef DYN_BWD_ROLL_RCP
-#define DYN_BWD_ROLL_RCP 1
 #endif
 
 namespace dyn
@@ -303,24 +291,19 @@ DYN_DEV double backward_pass(Warp<CFG>& w, const SlotScratch& sc, float m1, floa
 #pragma unroll 1
 		while (i >= 0)
 		{
-			if (CFG::RN == 4 && (i & 3) == 3 && ((cur.smask >> (i - 3)) & 0xfu) == 0u)
+			if (CFG::RN % 4 == 0 && (i & 3) == 3 && ((cur.smask >> (i - 3)) & 0xfu) == 0u)
 			{
-				// four rows without a band slide in one basic block: no branches between the rows, so the emissions of
-				// the next row (which do not depend on the recurrence) overlap the tail of the previous one
-#if DYN_BWD_ROLL_P1
+				// an aligned group of four rows without a band slide: a loop over the bare row (one copy of the code; the
+				// fully unrolled version of round 1 overlapped the rows a little better but evicted the forward loop from
+				// the instruction cache every CK rows)
 #pragma unroll 1
 				for (int q = 0; q < 4; ++q) bwd_row<CFG>(w, b, __shfl_sync(FULL, cur.xv, i - q), m1, e2);
-#else
-				const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i - 1);
-				const float x2 = __shfl_sync(FULL, cur.xv, i - 2), x3 = __shfl_sync(FULL, cur.xv, i - 3);
-				bwd_row<CFG>(w, b, x0, m1, e2);
-				bwd_row<CFG>(w, b, x1, m1, e2);
-				bwd_row<CFG>(w, b, x2, m1, e2);
-				bwd_row<CFG>(w, b, x3, m1, e2);
-#endif
 				const uint32_t tt = base + i - 3;
-				bwd_renorm<CFG>(w, b);
-				if (STORE && (tt & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
+				if ((tt & (CFG::RN - 1)) == 0)
+				{
+					bwd_renorm<CFG>(w, b);
+					if (STORE && (tt & (CFG::CK - 1)) == 0) ckpt_store<CFG>(sc, tt / CFG::CK, w.lane, b);
+				}
 				i -= 4;
 				continue;
 			}
@@ -696,10 +679,9 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 			while (tt >= (int)t_lo)
 			{
 				const int i = tt & 31;
-				if (DYN_RCP_UNROLL && RN == 4 && (i & 3) == 3 && ((cur.smask >> (i - 3)) & 0xfu) == 0u)
+				if (DYN_RCP_UNROLL && RN % 4 == 0 && (i & 3) == 3 && ((cur.smask >> (i - 3)) & 0xfu) == 0u)
 				{
-					// four rows without a band slide in one basic block (see backward_pass)
-#if DYN_BWD_ROLL_RCP
+					// an aligned group of four rows without a band slide (see backward_pass)
 					float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF + lane;
 #pragma unroll 1
 					for (int q = 0; q < 3; ++q)
@@ -710,33 +692,15 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 						dst -= ROWF;
 					}
 					bwd_row<CFG>(w, b, __shfl_sync(FULL, cur.xv, i - 3), m1, e2);
-					bwd_renorm<CFG>(w, b);
-					sm.OB[((tt - 3 - (int)t_lo) / RN) * 32 + lane] = b.OB;
+					if (((tt - 3) & (RN - 1)) == 0)
+					{
+						bwd_renorm<CFG>(w, b);
+						sm.OB[((tt - 3 - (int)t_lo) / RN) * 32 + lane] = b.OB;
+					}
 #pragma unroll
 					for (int j = 0; j < CPL; ++j) dst[j * 32] = b.bE[j];
 					tt -= 4;
 					continue;
-#else
-					const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i - 1);
-					const float x2 = __shfl_sync(FULL, cur.xv, i - 2), x3 = __shfl_sync(FULL, cur.xv, i - 3);
-					float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF;
-					bwd_row<CFG>(w, b, x0, m1, e2);
-#pragma unroll
-					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane] = b.bE[j];
-					bwd_row<CFG>(w, b, x1, m1, e2);
-#pragma unroll
-					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane - ROWF] = b.bE[j];
-					bwd_row<CFG>(w, b, x2, m1, e2);
-#pragma unroll
-					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane - 2 * ROWF] = b.bE[j];
-					bwd_row<CFG>(w, b, x3, m1, e2);
-					bwd_renorm<CFG>(w, b);
-					sm.OB[((tt - 3 - (int)t_lo) / RN) * 32 + lane] = b.OB;
-#pragma unroll
-					for (int j = 0; j < CPL; ++j) dst[j * 32 + lane - 3 * ROWF] = b.bE[j];
-					tt -= 4;
-					continue;
-#endif
 				}
 				const float x = __shfl_sync(FULL, cur.xv, i);
 				const bool sl = (cur.smask >> i) & 1u;
@@ -814,11 +778,12 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 		{
 			const int i = t & 31;
 			const uint32_t r = t - t_lo;
-			if (DYN_FWD_FAST && args.fwd_fast && RN == 4 && (t & 3u) == 0 && t + 4 <= t_end)
+			if (DYN_FWD_FAST && args.fwd_fast && RN % 4 == 0 && (t & 3u) == 0 && t + 4 <= t_end)
 			{
 				// an aligned group of RN rows inside the block: the branch-free row body (see fwd_row_fast)
 				const unsigned sl4 = (cur.smask >> i) & 0xfu;
-				const float kapN = kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0);
+				// on a renormalisation row bM[t] = bE[t+1] * p lives in the offsets of the next rows
+				const float kapN = ((t & (RN - 1)) == 0) ? kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0) : f.kap;
 				if ((t & (CFG::RV - 1)) == 0) vit_renorm<CFG>(w, f);
 				float kapE = f.kap;
 				const float* pf = sm.bE + (size_t)(r + 1) * ROWF;
@@ -857,23 +822,8 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 					}
 				}
 				f.kap = kapN;
-				fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 4) / RN) * 32 + lane], Z2i, c0);
+				if (((t + 4) & (RN - 1)) == 0) fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 4) / RN) * 32 + lane], Z2i, c0);
 				t += 4;
-				continue;
-			}
-			if (DYN_FWD_UNROLL && RN == 4 && (t & 1u) == 0 && t + 1 < t_end && ((cur.smask >> i) & 0x3u) == 0u)
-			{
-				// two rows without a band slide in one basic block: the emissions of the second row overlap the tail of
-				// the first one
-				const float x0 = __shfl_sync(FULL, cur.xv, i), x1 = __shfl_sync(FULL, cur.xv, i + 1);
-				const bool rn0 = (t & 3u) == 0;
-				const float kapN = rn0 ? kappa(f.OF, sm.OB[(r / RN + 1) * 32 + lane], Z2i, c0) : f.kap;
-				const float* rows = sm.bE + (size_t)(r + 1) * ROWF;
-				fwd_row<CFG, true, true>(w, f, sc, rs, thr, t, x0, false, mid_f, bc, bn, rows, true, f.kap, kapN, m1, e2, true);
-				fwd_row<CFG, true, true>(w, f, sc, rs, thr, t + 1, x1, false, mid_f, bc, bn, rows + ROWF, t + 2 < t_end, kapN, kapN, m1, e2, false);
-				f.kap = kapN;
-				if (((t + 2) & 3u) == 0) fwd_renorm<CFG>(w, f, bc, sm.OB[((r + 2) / RN) * 32 + lane], Z2i, c0);
-				t += 2;
 				continue;
 			}
 			const bool rn_row = (t & (RN - 1)) == 0;

@@ -165,7 +165,11 @@ namespace
 using Cfg16 = Cfg<13, 16, 4, 8>;
 using Cfg8 = Cfg<13, 8, 4, 8>;
 using Cfg8U = Cfg<13, 8, 4, 8, true>;
-constexpr int N_VARIANTS = 10;
+//   variants 10 / 11: renormalisation of the forward / backward values every 8 rows instead of 4 (uniform-sigma / general
+//                     kernels at 8 CTAs/SM); the log2-domain re-run uses the kernels of variant 3
+using Cfg8R8 = Cfg<13, 8, 8, 8>;
+using Cfg8UR8 = Cfg<13, 8, 8, 8, true>;
+constexpr int N_VARIANTS = 12;
 // experiment builds: -DDYN_ONLY_VARIANT=n compiles the kernels of one variant only (seconds instead of minutes)
 #ifdef DYN_ONLY_VARIANT
 #define DYN_HAS(n) ((n) == DYN_ONLY_VARIANT)
@@ -1001,6 +1005,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 		static const int general[5] = {3, 9, 1, 1, 2};
 		v = general[v - 4];
 	}
+	if (v == 10 && !A.uniform) v = 11;
 	A.last_variant = v;
 	switch (v)
 	{
@@ -1018,6 +1023,12 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 #endif
 #if DYN_HAS(8)
 	case 8: run_batch_t<Cfg8, 12, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(10)
+	case 10: run_batch_t<Cfg8, 8, Cfg8UR8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(11)
+	case 11: run_batch_t<Cfg8, 8, Cfg8R8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(9)
 	case 9: run_batch_t<Cfg8, 9, Cfg8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;

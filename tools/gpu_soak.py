@@ -1,6 +1,6 @@
 """Soak test on the GPU box: many seeded reads of different kinds through the C ABI against the CPU oracle (plain-C
 restatement, bit-exact with the reference).  Reports border identity, |dp|, Z error and how many reads took the log2-domain
-fallback.  usage: python tools/gpu_soak.py [reads_per_kind]"""
+fallback.  usage: [DYN_SOAK_VARIANT=n] python tools/gpu_soak.py [reads_per_kind]"""
 import os
 import sys
 import time
@@ -35,6 +35,8 @@ for name, pore, model, (lo, hi), spb, dwell, sds, kind, outl in KINDS:
     k = PORE_INFO[pore][1]
     orc = Oracle(path, pore)
     al = Aligner(path, pore)
+    if os.environ.get("DYN_SOAK_VARIANT"):
+        al.set_option("variant", int(os.environ["DYN_SOAK_VARIANT"]))  # kernel build variant (csrc/engine.cu)
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     sigs, seqs = [], []
     for _ in range(n_per):
