@@ -335,7 +335,7 @@ def main():
 
     def step_device():
         """One step: every batch through the C ABI with device-resident inputs.  Returns (#ok reads, kernel ms, launches)."""
-        ok, kms, nl, fb = 0, 0.0, 0, 0
+        ok, kms, nl, fb, rl = 0, 0.0, 0, 0, 0
         for b in batches:
             res, _, _, _ = al.align_packed(b["sig"].data_ptr(), b["sig_off"], b["bases"].data_ptr(), b["seq_off"],
                                            not args.z_only, device=True)
@@ -343,10 +343,11 @@ def main():
             kms += tm["dp_ms"]
             nl += tm["launches"]
             fb += tm["log2_fallback_reads"]
+            rl += tm["lin_retry_reads"]
             ok += sum(1 for i in range(b["sig_off"].size - 1) if res[i].status == 0)
-        return ok, kms, nl, fb
+        return ok, kms, nl, fb, rl
 
-    dp_ms, launches, fallbacks = [], 0, 0
+    dp_ms, launches, fallbacks, lin_retries = [], 0, 0, 0
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local_rank)
@@ -356,7 +357,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        n_ok, kms, nl, fb = step_device()
+        n_ok, kms, nl, fb, rl_ = step_device()
+        lin_retries += rl_
         dp_ms.append(kms)
         launches += nl
         fallbacks += fb
@@ -447,7 +449,7 @@ def main():
         "executed": exe_mufu, "executed_frac": exe_mufu / mufu_peak,
         "peak_at_max_clock": mufu_peak_max, "peak_source": "16 MUFU/clk/SM x SMs x SM clock sampled by nvidia-smi during the timed region",
         "cell_updates_per_s": 3.0 * cells / dp_s, "kernel_ms": dp_ms_all,
-        "log2_fallback_reads": int(fallbacks),
+        "log2_fallback_reads": int(fallbacks), "lin_retry_reads": int(lin_retries),
         "traffic": None,
         "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1i_k_align_uni_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
         "hbm": {"achieved": hbm_bytes / dp_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

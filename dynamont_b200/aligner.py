@@ -198,6 +198,7 @@ class Aligner:
         self._lib.dyn_last_timing(self._h, t.ctypes.data_as(f64p))
         return {"encode_ms": t[0], "dp_ms": t[1], "launches": int(t[2]),
                 "log2_fallback_reads": int(self._lib.dyn_last_fallbacks(self._h)),
+                "lin_retry_reads": int(self._lib.dyn_last_lin_retries(self._h)),
                 "variant": int(self._lib.dyn_last_variant(self._h))}
 
     @staticmethod

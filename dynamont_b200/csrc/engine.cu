@@ -20,6 +20,7 @@
 #include <set>
 #include <sstream>
 #include <thread>
+#include <type_traits>
 #include <atomic>
 #include <stdexcept>
 #include <string>
@@ -166,7 +167,9 @@ using Cfg16 = Cfg<13, 16, 4, 8>;
 using Cfg8 = Cfg<13, 8, 4, 8>;
 using Cfg8U = Cfg<13, 8, 4, 8, true>;
 //   variants 10 / 11: renormalisation of the forward / backward values every 8 rows instead of 4 (uniform-sigma / general
-//                     kernels at 8 CTAs/SM); the log2-domain re-run uses the kernels of variant 3
+//                     kernels at 8 CTAs/SM).  Reads they cannot represent (noisy reads: twice as many as with period 4)
+//                     are re-run by the period-4 linear kernels of variant 4 / 3, and what those cannot represent by the
+//                     log2-domain kernels of variant 3.
 using Cfg8R8 = Cfg<13, 8, 8, 8>;
 using Cfg8UR8 = Cfg<13, 8, 8, 8, true>;
 constexpr int N_VARIANTS = 12;
@@ -176,8 +179,8 @@ constexpr int N_VARIANTS = 12;
 #else
 #define DYN_HAS(n) 1
 #endif
-constexpr int DEFAULT_VARIANT = 3;      // measured fastest on B200
-constexpr int DEFAULT_VARIANT_UNI = 4;  // uniform-sigma models
+constexpr int DEFAULT_VARIANT = 11;      // measured fastest on B200
+constexpr int DEFAULT_VARIANT_UNI = 10;  // uniform-sigma models
 
 struct EncodeArgs
 {
@@ -585,6 +588,7 @@ struct dyn_aligner
 	int arith = 0;    // 0: linear-domain kernels, reads with an FP32 range fault re-run in the log2 domain; 1: log2 domain only
 	uint64_t n_fallback = 0;  // reads of the last batch that were re-run in the log2 domain
 	int last_variant = -1;    // resolved build variant of the last batch
+	uint64_t n_retry_lin = 0; // reads of the last batch that were re-run by the second-tier linear-domain kernels
 	double thr2 = -22.0;
 	double recs_per_row = 2.0;  // lane records per row (typical use: ~1.1)
 	double mem_fraction = 0.85;
@@ -725,7 +729,10 @@ struct BatchResult
 };
 
 // mode: 0 Z only, 1 align, 2 train.  sigpos/prob (host) receive the segment arrays for mode 1.
-template <class CFG, int MINB, class CFGLIN = CFG, int MINB_FB = MINB>
+// CFGLIN: configuration of the linear-domain kernels of the first launch.  CFGLIN2 (optional): linear-domain kernels
+// with a shorter renormalisation period that re-run the reads CFGLIN could not represent; what they cannot represent
+// either goes to the log2-domain kernels (CFG, MINB_FB resident CTAs per SM).  All three share CK, i.e. the scratch.
+template <class CFG, int MINB, class CFGLIN = CFG, int MINB_FB = MINB, class CFGLIN2 = void>
 void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
 	double* pooled, double* per_read_w)
 {
@@ -924,6 +931,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	// ---- K2..K5: the DP kernel ------------------------------------------------------------------------------------
 	const bool lin = (A.arith == 0);
 	A.n_fallback = 0;
+	A.n_retry_lin = 0;
 	tm.lap("enqueue");
 	rt.mark(2);
 	launch_align<CFG, MINB, CFGLIN, MINB_FB>(rt, ba, grid, mode, lin);
@@ -939,6 +947,28 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		std::vector<uint32_t> again;
 		for (uint32_t r : order)
 			if (res.out[r].status == ST_LIN_FAULT) again.push_back(r);
+		if constexpr (!std::is_void<CFGLIN2>::value)
+		{
+			if (!again.empty())
+			{
+				// second tier: the linear-domain kernels that renormalise twice as often
+				A.n_retry_lin = again.size();
+				rt.h2d(d_order, again.data(), again.size() * 4);
+				rt.zero(d_queue, 64);
+				ba.n_reads = (uint32_t)again.size();
+				rt.mark(4);
+				launch_align_t<CFGLIN2, MINB_FB, true>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode);
+				rt.mark(5);
+				rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
+				rt.sync();
+				fallback_ms += rt.elapsed(4, 5);
+				++launches;
+				std::vector<uint32_t> still;
+				for (uint32_t r : again)
+					if (res.out[r].status == ST_LIN_FAULT) still.push_back(r);
+				again.swap(still);
+			}
+		}
 		if (!again.empty())
 		{
 			A.n_fallback = again.size();
@@ -949,7 +979,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			launch_align<CFG, MINB, CFGLIN, MINB_FB>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode, false);
 			rt.mark(5);
 			rt.sync();
-			fallback_ms = rt.elapsed(4, 5);
+			fallback_ms += rt.elapsed(4, 5);
 			++launches;
 		}
 	}
@@ -1025,10 +1055,10 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 	case 8: run_batch_t<Cfg8, 12, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(10)
-	case 10: run_batch_t<Cfg8, 8, Cfg8UR8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	case 10: run_batch_t<Cfg8, 8, Cfg8UR8, 8, Cfg8U>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(11)
-	case 11: run_batch_t<Cfg8, 8, Cfg8R8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	case 11: run_batch_t<Cfg8, 8, Cfg8R8, 8, Cfg8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(9)
 	case 9: run_batch_t<Cfg8, 9, Cfg8, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
@@ -1909,6 +1939,7 @@ const char* dyn_status_message(int status)
 const char* dyn_last_error(const dyn_aligner* A) { return A->last_error.c_str(); }
 
 uint64_t dyn_last_fallbacks(const dyn_aligner* A) { return A->n_fallback; }
+uint64_t dyn_last_lin_retries(const dyn_aligner* A) { return A->n_retry_lin; }
 int dyn_last_variant(const dyn_aligner* A) { return A->last_variant; }
 
 void dyn_last_timing(const dyn_aligner* A, double* out3)

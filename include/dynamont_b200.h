@@ -175,6 +175,9 @@ void dyn_last_timing(const dyn_aligner*, double* out3);
 /* number of reads of the last batch call that the FP32 linear-domain kernels could not represent and that were
  * re-run by the log2-domain kernels (same GPU); results are identical either way */
 uint64_t dyn_last_fallbacks(const dyn_aligner*);
+/* number of reads of the last batch call that the first-tier linear-domain kernels (renormalisation every 8 rows) handed
+ * to the second tier (every 4 rows); dyn_last_fallbacks counts what the second tier handed on to the log2 domain */
+uint64_t dyn_last_lin_retries(const dyn_aligner*);
 /* kernel build variant the last batch call ran (csrc/engine.cu: 3 = general kernels at 8 CTAs/SM, 4 = uniform-sigma
  * kernels at 8 CTAs/SM, ...); -1 before the first call */
 int dyn_last_variant(const dyn_aligner*);

@@ -16,6 +16,7 @@ from oracle import Oracle  # noqa: E402
 
 MODELS = os.path.join(ROOT, "tests", "golden", "_models")
 n_per = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+ONLY = os.environ.get("DYN_SOAK_KINDS", "").split()
 KINDS = [  # name, pore, model, (min,max) length, spb, dwell, sd_scale, kind, outlier rate
     ("c1", "rna002", "rna002_5mer", (300, 1000), 30, "geometric", 1.0, "rand", 0.0),
     ("c2", "rna004", "synthetic_rna004_9mer", (500, 1500), 30, "geometric", 1.0, "rand", 0.0),
@@ -30,6 +31,8 @@ KINDS = [  # name, pore, model, (min,max) length, spb, dwell, sd_scale, kind, ou
 tot_seg = tot_same = tot_fb = tot_reads = 0
 worst_dp = worst_z = 0.0
 for name, pore, model, (lo, hi), spb, dwell, sds, kind, outl in KINDS:
+    if ONLY and name not in ONLY:
+        continue
     path = materialize_model(model, MODELS)
     nm, ns = native_model(path, pore)
     k = PORE_INFO[pore][1]
@@ -37,6 +40,8 @@ for name, pore, model, (lo, hi), spb, dwell, sds, kind, outl in KINDS:
     al = Aligner(path, pore)
     if os.environ.get("DYN_SOAK_VARIANT"):
         al.set_option("variant", int(os.environ["DYN_SOAK_VARIANT"]))  # kernel build variant (csrc/engine.cu)
+    for kv in os.environ.get("DYN_SOAK_OPTS", "").split():
+        al.set_option(kv.split("=")[0], float(kv.split("=")[1]))
     rng = np.random.default_rng(zlib.crc32(name.encode()))
     sigs, seqs = [], []
     for _ in range(n_per):
@@ -51,6 +56,7 @@ for name, pore, model, (lo, hi), spb, dwell, sds, kind, outl in KINDS:
     t0 = time.time()
     res = al.align_batch(sigs, seqs, True)
     fb = al.last_timing()["log2_fallback_reads"]
+    rl = al.last_timing()["lin_retry_reads"]
     seg = same = 0
     dpm = zm = 0.0
     bad = 0
@@ -69,8 +75,8 @@ for name, pore, model, (lo, hi), spb, dwell, sds, kind, outl in KINDS:
         bad += int(eq.sum() != eq.size)
         dpm = max(dpm, float(np.abs(r["probabilities"] - o["probabilities"])[ok].max(initial=0.0)))
         zm = max(zm, abs(r["Z"] - o["Z"]) / max(1.0, abs(o["Z"])))
-    print("%-9s %3d reads  borders %d/%d (%d reads with a moved border)  max|dp| %.2e  max dZ/|Z| %.2e  log2 fallback %d  %.1fs" % (
-        name, n_per, same, seg, bad, dpm, zm, fb, time.time() - t0), flush=True)
+    print("%-9s %3d reads  borders %d/%d (%d reads with a moved border)  max|dp| %.2e  max dZ/|Z| %.2e  period-4 retry %d  log2 fallback %d  %.1fs" % (
+        name, n_per, same, seg, bad, dpm, zm, rl, fb, time.time() - t0), flush=True)
     tot_seg += seg; tot_same += same; tot_fb += fb; tot_reads += n_per
     worst_dp = max(worst_dp, dpm); worst_z = max(worst_z, zm)
 print("TOTAL %d reads: borders identical %.5f %%, max|dp| %.2e, max dZ/|Z| %.2e, fallback reads %d" % (
