@@ -174,6 +174,9 @@ using Cfg8R8 = Cfg<13, 8, 8, 8>;
 using Cfg8UR8 = Cfg<13, 8, 8, 8, true>;
 constexpr int N_VARIANTS = 12;
 // experiment builds: -DDYN_ONLY_VARIANT=n compiles the kernels of one variant only (seconds instead of minutes)
+#ifndef DYN_V10_MINB
+#define DYN_V10_MINB 8  // resident CTAs per SM of the default uniform-sigma kernels (experiment builds override it)
+#endif
 #ifdef DYN_ONLY_VARIANT
 #define DYN_HAS(n) ((n) == DYN_ONLY_VARIANT)
 #else
@@ -590,8 +593,8 @@ struct dyn_aligner
 	int last_variant = -1;    // resolved build variant of the last batch
 	uint64_t n_retry_lin = 0; // reads of the last batch that were re-run by the second-tier linear-domain kernels
 	double thr2 = -22.0;
-	double recs_per_row = 2.0;  // lane records per row (typical use: ~1.1)
-	double mem_fraction = 0.85;
+	double recs_per_row = 1.6;  // lane records per row (typical use: ~1.1; a read that overflows is retried alone with a full buffer)
+	double mem_fraction = 0.92;  // share of the free HBM the scratch of the resident warps may take
 	// device state
 	DevBuf d_table, d_sig, d_seq, d_seqoff, d_desc, d_order, d_pc, d_kmers, d_bad, d_out, d_sigpos, d_prob, d_scratch,
 		d_slots, d_queue, d_rw, d_rx, d_rxx, d_sw, d_sx, d_sxx;
@@ -873,6 +876,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		per_slot = o;
 		const size_t budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
 		const size_t fit = std::max<size_t>(1, budget / per_slot);
+		if (tm.on)
+			fprintf(stderr, "[dyn timing] scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit\n",
+				per_slot / 1048576.0, grid, budget / 1073741824.0, fit);
 		grid = (unsigned)std::min<size_t>(grid, fit);
 	}
 	std::vector<SlotScratch> slots(grid);
@@ -1055,7 +1061,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 	case 8: run_batch_t<Cfg8, 12, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(10)
-	case 10: run_batch_t<Cfg8, 8, Cfg8UR8, 8, Cfg8U>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	case 10: run_batch_t<Cfg8, DYN_V10_MINB, Cfg8UR8, 8, Cfg8U>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(11)
 	case 11: run_batch_t<Cfg8, 8, Cfg8R8, 8, Cfg8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
