@@ -1418,18 +1418,49 @@ int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off
 		std::vector<double> cols;
 		const bool want_cols = per_read_mean && per_read_stdev;
 		if (want_cols) cols.assign(3 * pc_total, 0.0);
-		const double saved = A->recs_per_row;
-		A->recs_per_row = 1e9;  // training keeps every significant cell; no overflow retry path
-		try
+		// first pass with the usual sparse-record budget (the scratch of a resident warp then stays small enough for every
+		// warp to be resident); a read whose records overflow has accumulated nothing (the statistics pass runs after the
+		// overflow check) and is re-run alone with a full-size buffer, its statistics added to the batch's
+		run_batch(*A, io, 2, res, nullptr, nullptr, pooled.data(), want_cols ? cols.data() : nullptr);
+		std::vector<uint32_t> retry;
+		for (uint32_t r = 0; r < n_reads; ++r)
+			if (res.out[r].status == ST_REC_OVERFLOW) retry.push_back(r);
+		if (!retry.empty())
 		{
-			run_batch(*A, io, 2, res, nullptr, nullptr, pooled.data(), want_cols ? cols.data() : nullptr);
-		}
-		catch (...)
-		{
+			const double saved = A->recs_per_row;
+			A->recs_per_row = 1e9;  // clamped to the band width inside run_batch
+			try
+			{
+				for (uint32_t r : retry)
+				{
+					BatchIO sh;
+					uint64_t so0[2] = {0, sig_off[r + 1] - sig_off[r]};
+					uint64_t qo0[2] = {0, seq_off[r + 1] - seq_off[r]};
+					sh.sig_host = signal + sig_off[r];
+					sh.seq_host = seq + seq_off[r];
+					sh.sig_off = so0;
+					sh.seq_off = qo0;
+					sh.n = 1;
+					BatchResult r1;
+					std::vector<double> pooled1(3 * K, 0.0), cols1;
+					const uint64_t ncol = res.desc[r].N;
+					if (want_cols) cols1.assign(3 * ncol, 0.0);
+					run_batch(*A, sh, 2, r1, nullptr, nullptr, pooled1.data(), want_cols ? cols1.data() : nullptr);
+					res.out[r] = r1.out[0];
+					for (uint64_t q = 0; q < 3 * K; ++q) pooled[q] += pooled1[q];
+					if (want_cols)
+						for (int a = 0; a < 3; ++a)
+							std::copy(cols1.begin() + a * ncol, cols1.begin() + (a + 1) * ncol,
+								cols.begin() + a * pc_total + res.desc[r].pc_off);
+				}
+			}
+			catch (...)
+			{
+				A->recs_per_row = saved;
+				throw;
+			}
 			A->recs_per_row = saved;
-			throw;
 		}
-		A->recs_per_row = saved;
 		for (uint64_t q = 0; q < K; ++q)
 		{
 			if (pooled_w) pooled_w[q] += pooled[q];

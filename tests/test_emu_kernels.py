@@ -176,3 +176,22 @@ def test_emulated_narrow_band_and_errors(emu_lib):
         Aligner(path + ".missing", "rna002", _lib_path=emu_lib)
     with pytest.raises(RuntimeError, match="Inconsistent kmer size in model"):
         Aligner(path, "rna004", _lib_path=emu_lib)
+
+
+def test_emulated_training_record_overflow_retry(emu_lib):
+    """a read whose sparse posterior records overflow the per-warp buffer is re-run alone with a full buffer; the pooled
+    statistics and the per-read model must come out as without the overflow"""
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    al = _aligner(emu_lib, case, -1)
+    per0, pooled0 = al.train_batch([case.signal, case.signal], [case.sequence, case.sequence], per_read_model=True)
+    al.set_option("recs_per_row", 0.05)
+    per1, pooled1 = al.train_batch([case.signal, case.signal], [case.sequence, case.sequence], per_read_model=True)
+    for k in ("w", "x", "xx"):
+        np.testing.assert_allclose(pooled1[k], pooled0[k], rtol=1e-12, atol=0)
+    for a, b in zip(per0, per1):
+        assert a["Z"] == b["Z"]
+        np.testing.assert_allclose(a["emission_model"]["mean"], b["emission_model"]["mean"], rtol=1e-12)  # atomics: order
+    # the alignment path has had this retry since the first kernels
+    r0 = al.align(case.signal, case.sequence, True)
+    check_alignment(r0, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+
