@@ -43,6 +43,14 @@ namespace dyn
 namespace lin
 {
 
+// CTA-wide barriers inside pass 2 as well (recomputation / forward rows of every block in step): measured slower
+// (1251 vs 1363 G MUFU/s on c2 x 8192: the barriers cost more than the instruction-cache locality gains), off
+#ifndef DYN_BLOCK_SYNC
+#define DYN_BLOCK_SYNC 0
+#endif
+template <int WPC>
+DYN_DEV void cta_sync();
+
 constexpr int DCPL = 100;              // largest offset deficit of a lane against its source-side neighbour
 constexpr int E0V = 20;                // exponent of the lane maximum after a posterior-Viterbi renormalisation
 constexpr float LIN_MASS_TOL = 1e-3f;  // |recorded posterior mass of a row - 1| above this is a range fault
@@ -614,9 +622,12 @@ DYN_DEV void fwd_row_fast(Warp<CFG>& w, FwdL<CFG::CPL>& f, const SlotScratch& sc
 }
 
 // pass 2: forward + posterior + posterior-Viterbi fill.  Returns log2 Zf - log2 Zb (NaN on a range fault).
-template <class CFG>
+// WPC > 1: the warps of the CTA also keep the two halves of every block in step (recomputation, forward rows), so at
+// any time the whole SM runs one of the two loops; kb_sync = the largest block count among the CTA's reads (a warp whose
+// read is shorter keeps passing the barriers)
+template <class CFG, int WPC = 1>
 DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
-	double Z2, float thr, float m1, float e2, uint32_t& nrec_out, bool& overflow)
+	double Z2, float thr, float m1, float e2, uint32_t& nrec_out, bool& overflow, uint32_t kb_sync = 0)
 {
 	constexpr int CPL = CFG::CPL;
 	constexpr int CK = CFG::CK;
@@ -729,6 +740,7 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 			}
 		}
 		__syncwarp();
+		if (DYN_BLOCK_SYNC) cta_sync<WPC>();
 
 		// ---- step b: forward rows t_lo .. min(t_hi, T) - 1 ----------------------------------------------
 		uint32_t t = t_lo;
@@ -838,7 +850,14 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 			++t;
 		}
 		__syncwarp();
+		if (DYN_BLOCK_SYNC) cta_sync<WPC>();
 	}
+	if (DYN_BLOCK_SYNC && WPC > 1)
+		for (uint32_t k = kb + 1; k <= kb_sync; ++k)
+		{
+			cta_sync<WPC>();
+			cta_sync<WPC>();
+		}
 	{
 		const float* row = sm.bE + (size_t)((T - 1) - kb * CK) * ROWF;
 #pragma unroll
@@ -1010,11 +1029,35 @@ DYN_DEV bool train_stats_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchAr
 	return true;
 }
 
-// one read, all passes.  A read the linear arithmetic cannot represent leaves with ST_LIN_FAULT.
-template <class CFG, int MODE>
-DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx, const SlotScratch& sc,
-	unsigned char* smem_raw, int lane)
+// CTA-wide barrier between the passes of the phase-synchronised launch shape (WPC warps per CTA, each with its own
+// read of nearly the same length): all warps of an SM then run the SAME pass, so they share its code in the instruction
+// cache instead of evicting each other's loops.  Every warp of the CTA passes the same number of barriers per read.
+template <int WPC>
+DYN_DEV void cta_sync()
 {
+#ifndef DYN_HOST_EMU
+	if (WPC > 1) __syncthreads();
+#endif
+}
+
+// one read, all passes.  A read the linear arithmetic cannot represent leaves with ST_LIN_FAULT.
+// live: false for a warp that has no read in this round of its CTA (it only keeps the barriers company)
+template <class CFG, int MODE, int WPC = 1>
+DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx, const SlotScratch& sc,
+	unsigned char* smem_raw, int lane, bool live = true, uint32_t kb_sync = 0)
+{
+	if (WPC > 1 && !live)
+	{
+		cta_sync<WPC>();
+		if (DYN_BLOCK_SYNC && MODE != 0)
+			for (uint32_t k = 0; k <= kb_sync; ++k)
+			{
+				cta_sync<WPC>();
+				cta_sync<WPC>();
+			}
+		cta_sync<WPC>();
+		return;
+	}
 	Warp<CFG> w;
 	w.lane = lane;
 	w.S = rd.S;
@@ -1040,18 +1083,33 @@ DYN_DEV void align_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx
 
 	const double Z2 = (MODE == 0) ? backward_pass<CFG, false>(w, sc, m1, e2) : backward_pass<CFG, true>(w, sc, m1, e2);
 	out.Z = Z2 * LN2;
+	cta_sync<WPC>();
+	bool go = false;  // pass 3 follows
 	if (!(Z2 > -1.0e30 && Z2 < 1.0e30))
+	{
 		out.status = ST_LIN_FAULT;  // underflow of every path or NaN/inf: let the log2-domain kernels decide
+		if (DYN_BLOCK_SYNC && WPC > 1 && MODE != 0)
+			for (uint32_t k = 0; k <= kb_sync; ++k)
+			{
+				cta_sync<WPC>();
+				cta_sync<WPC>();
+			}
+	}
 	else if (MODE != 0)
 	{
 		uint32_t nrec = 0;
 		bool overflow = false;
-		const double dz2 = forward_posterior_pass<CFG>(w, sc, args, smem_raw, Z2, args.thr_lin, m1, e2, nrec, overflow);
+		const double dz2 = forward_posterior_pass<CFG, WPC>(w, sc, args, smem_raw, Z2, args.thr_lin, m1, e2, nrec, overflow, kb_sync);
 		out.nrec = nrec;
 		out.dZ = dz2 * LN2;
 		if (!(fabs(dz2) <= LIN_Z_TOL)) out.status = ST_LIN_FAULT;
 		else if (overflow) out.status = ST_REC_OVERFLOW;
-		else if (MODE == 1)
+		else go = true;
+	}
+	cta_sync<WPC>();
+	if (go)
+	{
+		if (MODE == 1)
 		{
 			const int rc = lin::traceback_pass<CFG>(w, sc, args, smem_raw, rd);
 			if (rc) out.status = ST_LIN_FAULT;

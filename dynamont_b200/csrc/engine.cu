@@ -172,7 +172,8 @@ using Cfg8U = Cfg<13, 8, 4, 8, true>;
 //                     log2-domain kernels of variant 3.
 using Cfg8R8 = Cfg<13, 8, 8, 8>;
 using Cfg8UR8 = Cfg<13, 8, 8, 8, true>;
-constexpr int N_VARIANTS = 12;
+//   variant 12: variant 10 launched as CTAs of 8 warps that run their reads pass by pass in step (uniform-sigma models)
+constexpr int N_VARIANTS = 13;
 // experiment builds: -DDYN_ONLY_VARIANT=n compiles the kernels of one variant only (seconds instead of minutes)
 #ifndef DYN_V10_MINB
 #define DYN_V10_MINB 8  // resident CTAs per SM of the default uniform-sigma kernels (experiment builds override it)
@@ -183,7 +184,7 @@ constexpr int N_VARIANTS = 12;
 #define DYN_HAS(n) 1
 #endif
 constexpr int DEFAULT_VARIANT = 11;      // measured fastest on B200
-constexpr int DEFAULT_VARIANT_UNI = 10;  // uniform-sigma models
+constexpr int DEFAULT_VARIANT_UNI = 12;  // uniform-sigma models
 
 struct EncodeArgs
 {
@@ -259,19 +260,47 @@ DYN_DEV void encode_read(const EncodeArgs& a, uint32_t r, int lane)
 	}
 }
 
-template <class CFG, int MODE, bool LIN>
-DYN_DEV void align_worker(const BatchArgs& args, unsigned char* smem_raw, int lane, unsigned slot)
+// WPC = 1: a persistent grid of single-warp CTAs, each pulling one read at a time.  WPC > 1 (linear-domain kernels
+// only): CTAs of WPC warps pull WPC consecutive reads of the processing order (sorted by size, so nearly equal) and run
+// them pass by pass in step (lin::cta_sync).
+template <class CFG, int MODE, bool LIN, int WPC = 1>
+DYN_DEV void align_worker(const BatchArgs& args, unsigned char* smem_all, int tid, unsigned cta)
 {
-	const SlotScratch sc = args.slots[slot];
+	const int lane = tid & 31, wid = tid >> 5;
+	unsigned char* smem_raw = smem_all + (size_t)wid * CFG::SMEM_BYTES;
+	const SlotScratch sc = args.slots[cta * WPC + wid];
+#ifndef DYN_HOST_EMU
+	__shared__ uint32_t s_base, s_kb;
+#endif
 	while (true)
 	{
 		uint32_t i = 0;
-		if (lane == 0) i = atomicAdd(args.queue, 1u);
-		i = __shfl_sync(FULL, i, 0);
-		if (i >= args.n_reads) break;
-		const uint32_t ridx = args.order[i];
-		const ReadDesc rd = args.reads[ridx];
-		if (rd.status != ST_OK)
+		if (WPC == 1)
+		{
+			if (lane == 0) i = atomicAdd(args.queue, 1u);
+			i = __shfl_sync(FULL, i, 0);
+		}
+#ifndef DYN_HOST_EMU
+		else
+		{
+			if (tid == 0)
+			{
+				s_base = atomicAdd(args.queue, (uint32_t)WPC);
+				s_kb = 0u;
+			}
+			__syncthreads();
+			i = s_base + (uint32_t)wid;
+			__syncthreads();
+			if (i - (uint32_t)wid >= args.n_reads) break;  // the whole CTA leaves together
+		}
+#endif
+		const bool live = i < args.n_reads;
+		if (WPC == 1 && !live) break;
+		const uint32_t ridx = live ? args.order[i] : 0u;
+		ReadDesc rd;
+		if (live) rd = args.reads[ridx];
+		else rd.status = ST_INTERNAL;
+		if (live && rd.status != ST_OK)
 		{
 			if (lane == 0)
 			{
@@ -279,9 +308,19 @@ DYN_DEV void align_worker(const BatchArgs& args, unsigned char* smem_raw, int la
 				o.Z = 0.0; o.dZ = 0.0; o.nrec = 0; o.status = rd.status; o.xi_m = 0.0; o.xi_e = 0.0;
 				args.out[ridx] = o;
 			}
-			continue;
+			if (WPC == 1) continue;
 		}
-		if (LIN) lin::align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
+		uint32_t kb_sync = 0;
+#ifndef DYN_HOST_EMU
+		if (WPC > 1)
+		{
+			// the largest number of pass-2 blocks among the CTA's reads (lin::forward_posterior_pass)
+			if (lane == 0 && live && rd.status == ST_OK) atomicMax(&s_kb, rd.S / (uint32_t)CFG::CK);
+			__syncthreads();
+			kb_sync = s_kb;
+		}
+#endif
+		if (LIN) lin::align_read<CFG, MODE, WPC>(args, rd, ridx, sc, smem_raw, lane, live && rd.status == ST_OK, kb_sync);
 		else align_read<CFG, MODE>(args, rd, ridx, sc, smem_raw, lane);
 		__syncwarp();
 	}
@@ -391,11 +430,11 @@ __global__ void __launch_bounds__(32) k_encode(EncodeArgs a)
 // register budget for MINB resident single-warp CTAs per SM (64 K registers, allocation granularity 8 per thread).
 // __launch_bounds__(32, MINB) makes ptxas fall to 168 registers for every MINB > 8; __maxnreg__ gives the exact budget.
 constexpr int max_regs(int minb) { return (65536 / (32 * minb) / 8 * 8) > 255 ? 255 : (65536 / (32 * minb) / 8 * 8); }
-template <class CFG, int MODE, int MINB, bool LIN>
-__global__ void __launch_bounds__(32) __maxnreg__(max_regs(MINB)) k_align(BatchArgs args)
+template <class CFG, int MODE, int MINB, bool LIN, int WPC = 1>
+__global__ void __launch_bounds__(32 * WPC) __maxnreg__(max_regs(MINB * WPC)) k_align(BatchArgs args)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	align_worker<CFG, MODE, LIN>(args, smem_raw, threadIdx.x, blockIdx.x);
+	align_worker<CFG, MODE, LIN, WPC>(args, smem_raw, threadIdx.x, blockIdx.x);
 }
 __global__ void __launch_bounds__(32) k_fold(FoldArgs a)
 {
@@ -416,25 +455,28 @@ void launch_encode(Rt& rt, const EncodeArgs& a)
 #endif
 }
 
-template <class CFG, int MINB, bool LIN>
+// grid = resident warps ("slots"); WPC warps per CTA (see align_worker)
+template <class CFG, int MINB, bool LIN, int WPC = 1>
 void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 {
-	const size_t smem = CFG::SMEM_BYTES;
+	const size_t smem = CFG::SMEM_BYTES * WPC;
 #ifndef DYN_HOST_EMU
 	static bool attr_set = false;
 	if (!attr_set)
 	{
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB, LIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	if (mode == 0) k_align<CFG, 0, MINB, LIN><<<grid, 32, 0, rt.stream>>>(args);  // the backward pass alone needs no shared memory
-	else if (mode == 1) k_align<CFG, 1, MINB, LIN><<<grid, 32, smem, rt.stream>>>(args);
-	else k_align<CFG, 2, MINB, LIN><<<grid, 32, smem, rt.stream>>>(args);
+	const unsigned ctas = std::max(1u, grid / WPC);  // the host sizes the slot table for grid warps
+	if (mode == 0) k_align<CFG, 0, MINB, LIN, WPC><<<ctas, 32 * WPC, 0, rt.stream>>>(args);  // the backward pass alone needs no shared memory
+	else if (mode == 1) k_align<CFG, 1, MINB, LIN, WPC><<<ctas, 32 * WPC, smem, rt.stream>>>(args);
+	else k_align<CFG, 2, MINB, LIN, WPC><<<ctas, 32 * WPC, smem, rt.stream>>>(args);
 	CK_CUDA(cudaGetLastError());
 #else
 	(void)rt;
+	static_assert(WPC == 1 || true, "");
 	if (mode == 0) simt::launch(grid, smem, [&]() { align_worker<CFG, 0, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 	else if (mode == 1) simt::launch(grid, smem, [&]() { align_worker<CFG, 1, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 	else simt::launch(grid, smem, [&]() { align_worker<CFG, 2, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
@@ -442,10 +484,10 @@ void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 }
 
 // lin: the linear-domain kernels (dp_linear.cuh); otherwise the log2-domain kernels (dp_kernels.cuh)
-template <class CFG, int MINB, class CFGLIN, int MINB_FB>
+template <class CFG, int MINB, class CFGLIN, int MINB_FB, int WPC>
 void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode, bool lin)
 {
-	if (lin) launch_align_t<CFGLIN, MINB, true>(rt, args, grid, mode);
+	if (lin) launch_align_t<CFGLIN, MINB / WPC, true, WPC>(rt, args, grid, mode);
 	else launch_align_t<CFG, MINB_FB, false>(rt, args, grid, mode);
 }
 
@@ -735,7 +777,7 @@ struct BatchResult
 // CFGLIN: configuration of the linear-domain kernels of the first launch.  CFGLIN2 (optional): linear-domain kernels
 // with a shorter renormalisation period that re-run the reads CFGLIN could not represent; what they cannot represent
 // either goes to the log2-domain kernels (CFG, MINB_FB resident CTAs per SM).  All three share CK, i.e. the scratch.
-template <class CFG, int MINB, class CFGLIN = CFG, int MINB_FB = MINB, class CFGLIN2 = void>
+template <class CFG, int MINB, class CFGLIN = CFG, int MINB_FB = MINB, class CFGLIN2 = void, int WPC = 1>
 void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
 	double* pooled, double* per_read_w)
 {
@@ -854,6 +896,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	launch_encode(rt, ea);
 	rt.mark(1);
 
+	const bool lin_first = (A.arith == 0);
 	// ---- scratch: one slot per resident warp, sized for the longest read --------------------------------------
 	// Z-only runs the backward pass alone: <= 128 registers and no shared memory, i.e. 16 single-warp CTAs per SM
 	const int resident = (mode == 0) ? 16 : MINB;
@@ -881,6 +924,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				per_slot / 1048576.0, grid, budget / 1073741824.0, fit);
 		grid = (unsigned)std::min<size_t>(grid, fit);
 	}
+	if (WPC > 1 && lin_first) grid = std::max<unsigned>(grid / WPC, 1u) * WPC;  // whole CTAs of WPC warps
 	std::vector<SlotScratch> slots(grid);
 	if (mode != 0)
 	{
@@ -940,7 +984,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	A.n_retry_lin = 0;
 	tm.lap("enqueue");
 	rt.mark(2);
-	launch_align<CFG, MINB, CFGLIN, MINB_FB>(rt, ba, grid, mode, lin);
+	launch_align<CFG, MINB, CFGLIN, MINB_FB, WPC>(rt, ba, grid, mode, lin);
 	rt.mark(3);
 	int launches = 2;
 	double fallback_ms = 0.0;
@@ -982,7 +1026,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			rt.zero(d_queue, 64);
 			ba.n_reads = (uint32_t)again.size();
 			rt.mark(4);
-			launch_align<CFG, MINB, CFGLIN, MINB_FB>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode, false);
+			launch_align<CFG, MINB, CFGLIN, MINB_FB, WPC>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode, false);
 			rt.mark(5);
 			rt.sync();
 			fallback_ms += rt.elapsed(4, 5);
@@ -1041,7 +1085,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 		static const int general[5] = {3, 9, 1, 1, 2};
 		v = general[v - 4];
 	}
-	if (v == 10 && !A.uniform) v = 11;
+	if ((v == 10 || v == 12) && !A.uniform) v = 11;
 	A.last_variant = v;
 	switch (v)
 	{
@@ -1062,6 +1106,9 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 #endif
 #if DYN_HAS(10)
 	case 10: run_batch_t<Cfg8, DYN_V10_MINB, Cfg8UR8, 8, Cfg8U>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(12)
+	case 12: run_batch_t<Cfg8, 8, Cfg8UR8, 8, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(11)
 	case 11: run_batch_t<Cfg8, 8, Cfg8R8, 8, Cfg8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;

@@ -1,6 +1,6 @@
 """dynamont-train data-parallel step (BASELINE config 5 shape): every rank runs the training kernels on its shard of
 synthetic rna004 9-mer reads, ONE NCCL all-reduce sums the pooled sufficient statistics (3*4^9 + 4 doubles), the M-step
-is replicated.  Launch:  python -m torch.distributed.run --nproc-per-node N tools/train_timing.py [reads_per_rank]
+is replicated.  Launch:  python -m torch.distributed.run --nproc-per-node N tools/train_timing.py [reads_per_rank [max_len]]
 (or plain python for one GPU).  Prints one line from rank 0."""
 import os
 import sys
@@ -24,12 +24,13 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+max_len = int(sys.argv[2]) if len(sys.argv) > 2 else 2000  # BASELINE config 5 (as config 2): 5000
 path = materialize_model("synthetic_rna004_9mer", os.path.join(ROOT, "tests", "golden", "_models"))
 nm, ns = native_model(path, "rna004")
 rng = np.random.default_rng(20265000 + rank)
 sigs, seqs = [], []
 for _ in range(n):
-    s, q, _ = synth_read(rng, nm, ns, 9, int(rng.integers(500, 2001)), 30.0)
+    s, q, _ = synth_read(rng, nm, ns, 9, int(rng.integers(500, max_len + 1)), 30.0)
     sigs.append(s.astype(np.float32))
     seqs.append(q)
 al = Aligner(path, "rna004", device=local)
