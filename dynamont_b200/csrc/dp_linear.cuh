@@ -635,6 +635,7 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 	constexpr int CK = CFG::CK;
 	constexpr int RN = CFG::RN;
 	constexpr int ROWF = CFG::ROWF;
+	constexpr int RCP_UNR = (WPC > 1) ? 3 : 1;
 	SmemL<CFG> sm(smem_raw);
 	FwdL<CPL> f;
 	BwdL<CPL> b;
@@ -696,8 +697,8 @@ DYN_DEV double forward_posterior_pass(Warp<CFG>& w, const SlotScratch& sc, const
 				{
 					// an aligned group of four rows without a band slide (see backward_pass)
 					float* dst = sm.bE + (size_t)(tt - (int)t_lo) * ROWF + lane;
-#pragma unroll 1
-					for (int q = 0; q < 3; ++q)
+#pragma unroll RCP_UNR
+					for (int q = 0; q < 3; ++q)  // (unrolled for the phase-synchronised CTAs, +1.2 %; see backward_pass)
 					{
 						bwd_row<CFG>(w, b, __shfl_sync(FULL, cur.xv, i - q), m1, e2);
 #pragma unroll

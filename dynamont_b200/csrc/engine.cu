@@ -175,6 +175,9 @@ using Cfg8UR8 = Cfg<13, 8, 8, 8, true>;
 //   variant 12: variant 10 launched as CTAs of 8 warps that run their reads pass by pass in step (uniform-sigma models)
 constexpr int N_VARIANTS = 13;
 // experiment builds: -DDYN_ONLY_VARIANT=n compiles the kernels of one variant only (seconds instead of minutes)
+#ifndef DYN_V12_WPC
+#define DYN_V12_WPC 8  // warps per CTA of the phase-synchronised launch shape (one CTA per SM)
+#endif
 #ifndef DYN_V10_MINB
 #define DYN_V10_MINB 8  // resident CTAs per SM of the default uniform-sigma kernels (experiment builds override it)
 #endif
@@ -1108,7 +1111,7 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 	case 10: run_batch_t<Cfg8, DYN_V10_MINB, Cfg8UR8, 8, Cfg8U>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(12)
-	case 12: run_batch_t<Cfg8, 8, Cfg8UR8, 8, Cfg8U, 8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+	case 12: run_batch_t<Cfg8, DYN_V12_WPC, Cfg8UR8, 8, Cfg8U, DYN_V12_WPC>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(11)
 	case 11: run_batch_t<Cfg8, 8, Cfg8R8, 8, Cfg8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
