@@ -453,7 +453,7 @@ def main():
         "cell_updates_per_s": 3.0 * cells / dp_s, "kernel_ms": dp_ms_all,
         "log2_fallback_reads": int(fallbacks), "lin_retry_reads": int(lin_retries),
         "traffic": None,
-        "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1i_k_align_uni_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
+        "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1l_k_align_final_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
         "hbm": {"achieved": hbm_bytes / dp_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
                 "note": "algorithmic signal + constants + checkpoint/decision-bit/record spill per launch"},
     }
