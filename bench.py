@@ -40,7 +40,7 @@ MODELS_DIR = os.path.join(ROOT, "tests", "golden", "_models")
 VARIANT_KERNELS = {0: ("Cfg<13,16,4,8>", 7), 1: ("Cfg<13,8,4,8>", 10), 2: ("Cfg<13,8,4,8>", 12), 3: ("Cfg<13,8,4,8>", 8),
                    4: ("Cfg<13,8,4,8,UNI>", 8), 5: ("Cfg<13,8,4,8,UNI>", 9), 6: ("Cfg<13,8,4,8,UNI>", 10),
                    7: ("Cfg<13,8,4,8,UNI>", 11), 8: ("Cfg<13,8,4,8,UNI>", 12), 9: ("Cfg<13,8,4,8>", 9),
-                   10: ("Cfg<13,8,8,8,UNI>", 8), 11: ("Cfg<13,8,8,8>", 8), 12: ("Cfg<13,8,8,8,UNI>", 1)}
+                   10: ("Cfg<13,8,8,8,UNI>", 8), 11: ("Cfg<13,8,8,8>", 8), 12: ("Cfg<13,8,8,8,UNI>", 1), 13: ("Cfg<13,8,8,8>", 1)}
 
 
 def kernel_label(variant, lin):
@@ -48,7 +48,7 @@ def kernel_label(variant, lin):
     if not lin:
         return f"k_align<{cfg.replace(',UNI', '')},1,{minb},LIN=0> (log2-domain FP32, 2 MUFU per cell-update)"
     uni = " uniform-sigma emission constants," if "UNI" in cfg else ""
-    if variant == 12:
+    if variant in (12, 13):
         return f"k_align<{cfg},1,1,LIN=1,WPC=8> (linear-domain FP32,{uni} CTAs of 8 warps in step pass by pass, 1 MUFU per cell-update)"
     return f"k_align<{cfg},1,{minb},LIN=1> (linear-domain FP32,{uni} 1 MUFU per cell-update)"
 

@@ -172,8 +172,8 @@ using Cfg8U = Cfg<13, 8, 4, 8, true>;
 //                     log2-domain kernels of variant 3.
 using Cfg8R8 = Cfg<13, 8, 8, 8>;
 using Cfg8UR8 = Cfg<13, 8, 8, 8, true>;
-//   variant 12: variant 10 launched as CTAs of 8 warps that run their reads pass by pass in step (uniform-sigma models)
-constexpr int N_VARIANTS = 13;
+//   variants 12 / 13: variants 10 / 11 launched as CTAs of 8 warps that run their reads pass by pass in step
+constexpr int N_VARIANTS = 14;
 // experiment builds: -DDYN_ONLY_VARIANT=n compiles the kernels of one variant only (seconds instead of minutes)
 #ifndef DYN_V12_WPC
 #define DYN_V12_WPC 8  // warps per CTA of the phase-synchronised launch shape (one CTA per SM)
@@ -186,7 +186,7 @@ constexpr int N_VARIANTS = 13;
 #else
 #define DYN_HAS(n) 1
 #endif
-constexpr int DEFAULT_VARIANT = 11;      // measured fastest on B200
+constexpr int DEFAULT_VARIANT = 11;      // (13 once verified on the GPU)
 constexpr int DEFAULT_VARIANT_UNI = 12;  // uniform-sigma models
 
 struct EncodeArgs
@@ -1088,7 +1088,8 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 		static const int general[5] = {3, 9, 1, 1, 2};
 		v = general[v - 4];
 	}
-	if ((v == 10 || v == 12) && !A.uniform) v = 11;
+	if (v == 10 && !A.uniform) v = 11;
+	if (v == 12 && !A.uniform) v = 13;
 	A.last_variant = v;
 	switch (v)
 	{
@@ -1112,6 +1113,9 @@ void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, ui
 #endif
 #if DYN_HAS(12)
 	case 12: run_batch_t<Cfg8, DYN_V12_WPC, Cfg8UR8, 8, Cfg8U, DYN_V12_WPC>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
+#endif
+#if DYN_HAS(13)
+	case 13: run_batch_t<Cfg8, DYN_V12_WPC, Cfg8R8, 8, Cfg8, DYN_V12_WPC>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;
 #endif
 #if DYN_HAS(11)
 	case 11: run_batch_t<Cfg8, 8, Cfg8R8, 8, Cfg8>(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w); break;

@@ -74,9 +74,9 @@ def test_emulated_range_fault_falls_back(emu_lib):
     np.testing.assert_allclose(pooled_lin["w"], pooled_log["w"], rtol=1e-12)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 8, 9, 10, 11, 12, -1])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 8, 9, 10, 11, 12, 13, -1])
 def test_emulated_variants(variant, emu_lib):
-    """build variants: general kernels (0-3, 9, 11), uniform-sigma kernels (4-8, 10), library default (-1)"""
+    """build variants: general kernels (0-3, 9, 11, 13), uniform-sigma kernels (4-8, 10, 12), library default (-1)"""
     case = [c for c in load_golden() if c.name == "rna002_band"][0]
     al = _aligner(emu_lib, case, variant)
     r = al.align(case.signal, case.sequence, True)
