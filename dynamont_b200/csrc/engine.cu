@@ -479,7 +479,6 @@ void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 	CK_CUDA(cudaGetLastError());
 #else
 	(void)rt;
-	static_assert(WPC == 1 || true, "");
 	if (mode == 0) simt::launch(grid, smem, [&]() { align_worker<CFG, 0, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 	else if (mode == 1) simt::launch(grid, smem, [&]() { align_worker<CFG, 1, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 	else simt::launch(grid, smem, [&]() { align_worker<CFG, 2, LIN>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
