@@ -196,7 +196,10 @@ class Aligner:
     def last_timing(self):
         t = np.zeros(3)
         self._lib.dyn_last_timing(self._h, t.ctypes.data_as(f64p))
+        rb = np.zeros(2, dtype=np.uint64)
+        self._lib.dyn_last_ribbon(self._h, rb.ctypes.data_as(u64p))
         return {"encode_ms": t[0], "dp_ms": t[1], "launches": int(t[2]),
+                "ribbon_reads": int(rb[0]), "ribbon_faults": int(rb[1]),
                 "log2_fallback_reads": int(self._lib.dyn_last_fallbacks(self._h)),
                 "lin_retry_reads": int(self._lib.dyn_last_lin_retries(self._h)),
                 "variant": int(self._lib.dyn_last_variant(self._h))}

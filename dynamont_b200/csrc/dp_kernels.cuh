@@ -55,6 +55,9 @@ struct SlotScratch
 	void* recs;         // [rec_cap] LaneRec<CPL>
 	uint32_t* pn;       // [T]       path column of row t (bit 31: match state)
 	float* pp;          // [T]       posterior of the path cell of row t
+	// ribbon kernels (dp_ribbon.cuh)
+	uint2* sched;       // [T/32+2]  window schedule: {window centre of row 32c, slide bits of rows 32c .. 32c+31}
+	uint32_t* hdr;      // [T+1][HDRW] row headers: first record, hot-lane mask, decision words
 };
 
 struct BatchArgs
@@ -77,6 +80,10 @@ struct BatchArgs
 	int mode;                   // 0: Z only (backward pass), 1: full alignment, 2: training statistics
 	float uni_a, uni_c;         // Cfg::UNI kernels: the model-wide emission constants (every kmer has the same sigma)
 	int fwd_fast;               // linear-domain pass 2: branch-free row body for groups of rows without a band slide
+	// ribbon kernels (dp_ribbon.cuh)
+	uint32_t n_slots;           // resident warps (scratch slots)
+	float thr_rib;              // a lane is recorded when one of its posteriors exceeds this
+	int rib_guard;              // the window's edge lanes must stay this many bits below the row maximum
 	// training (mode 2)
 	double* stat_w;             // [K] pooled sum of gamma              (NT:510)
 	double* stat_x;             // [K] pooled sum of gamma * x          (NT:511)

@@ -8,6 +8,7 @@
 #include "dp_kernels.cuh"
 #include "dp_linear.cuh"
 #include "ntk_kernels.cuh"
+#include "ribbon.h"
 
 #include <algorithm>
 #include <chrono>
@@ -44,7 +45,7 @@ using namespace dyn;
 struct Rt
 {
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int device = 0;
 	int sms = 148;
 	size_t smem_optin = 0;
@@ -125,7 +126,7 @@ struct Rt
 	int sms = 2;
 	bool async_alloc = false;
 	size_t smem_optin = 227 * 1024;
-	double tm[6] = {0, 0, 0, 0, 0, 0};
+	double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	void init(int) {}
 	void use_stream(void*) {}
 	void fini() {}
@@ -637,6 +638,14 @@ struct dyn_aligner
 	int last_variant = -1;    // resolved build variant of the last batch
 	uint64_t n_retry_lin = 0; // reads of the last batch that were re-run by the second-tier linear-domain kernels
 	double thr2 = -22.0;
+	// ribbon kernels (dp_ribbon.cuh): first tier for every read whose band is wider than the window
+	int ribbon = 2;            // lattice columns per lane of the window (2: 63 columns, 4: 127 columns); 0: off
+	int rib_guard = 40;        // the window's edge lanes must stay this many bits below the row maximum
+	double thr_rib = -16.0;    // log2 of the posterior above which a lane is recorded (unrecorded path cells count as 0)
+	double rib_recs_per_row = 4.0;
+	uint64_t n_ribbon = 0;     // reads of the last batch the ribbon kernels were given ...
+	uint64_t n_rib_fault = 0;  // ... and how many of them they handed on to the full-band kernels
+	double ribbon_ms = 0.0;
 	double recs_per_row = 1.6;  // lane records per row (typical use: ~1.1; a read that overflows is retried alone with a full buffer)
 	double mem_fraction = 0.92;  // share of the free HBM the scratch of the resident warps may take
 	// device state
@@ -737,7 +746,7 @@ void dyn_aligner::upload_table()
 		t[q].a = (float)a;
 		t[q].b = (float)(mu * a);
 		t[q].c = (float)(-std::log2(sd) - 0.5 * std::log2(2.0 * M_PI));
-		t[q].pad = 0.0f;
+		t[q].pad = (float)mu;  // centre of the ribbon kernels' training statistics
 	}
 	uniform = K > 0;
 	for (uint64_t q = 1; q < K && uniform; ++q) uniform = (t[q].a == t[0].a && t[q].c == t[0].c);
@@ -898,6 +907,163 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	launch_encode(rt, ea);
 	rt.mark(1);
 
+	// ---- arguments shared by every DP launch of this batch ---------------------------------------------------
+	BatchArgs ba;
+	memset(&ba, 0, sizeof(ba));
+	ba.reads = d_desc; ba.order = d_order; ba.n_reads = (uint32_t)order.size(); ba.queue = d_queue;
+	ba.signal = d_sig; ba.pc = d_pc; ba.out = d_out;
+	ba.out_sigpos = d_sigpos; ba.out_prob = d_prob;
+	ba.m1 = (float)(A.trans[0] * LOG2E);
+	ba.e2 = (float)(A.trans[2] * LOG2E);
+	ba.thr2 = (float)A.thr2;
+	ba.m1_lin = (float)std::exp(A.trans[0]);
+	ba.e2_lin = (float)std::exp(A.trans[2]);
+	ba.thr_lin = (float)std::exp2(A.thr2);
+	ba.mode = mode;
+	ba.uni_a = A.uni_a;
+	ba.uni_c = A.uni_c;
+	ba.fwd_fast = A.fwd_fast;
+	ba.kmers = d_kmers;
+	ba.thr_rib = (float)std::exp2(A.thr_rib);
+	ba.rib_guard = A.rib_guard;
+	if (mode == 2)
+	{
+		ba.read_w = (double*)A.d_rw.get(rt, pc_total * 8);
+		ba.read_x = (double*)A.d_rx.get(rt, pc_total * 8);
+		ba.read_xx = (double*)A.d_rxx.get(rt, pc_total * 8);
+		rt.zero(ba.read_w, pc_total * 8);
+		rt.zero(ba.read_x, pc_total * 8);
+		rt.zero(ba.read_xx, pc_total * 8);
+		ba.stat_w = (double*)A.d_sw.get(rt, A.K * 8);
+		ba.stat_x = (double*)A.d_sx.get(rt, A.K * 8);
+		ba.stat_xx = (double*)A.d_sxx.get(rt, A.K * 8);
+		rt.zero(ba.stat_w, A.K * 8);
+		rt.zero(ba.stat_x, A.K * 8);
+		rt.zero(ba.stat_xx, A.K * 8);
+	}
+	A.n_fallback = 0;
+	A.n_retry_lin = 0;
+	A.n_ribbon = 0;
+	A.n_rib_fault = 0;
+	A.ribbon_ms = 0.0;
+	int launches = 1;
+
+	// ---- tier 0: the ribbon kernels (dp_ribbon.cuh) -----------------------------------------------------------
+	// every read whose reference band leaves room for the window; what they cannot represent (ST_LIN_FAULT) and the
+	// short reads go on to the full-band kernels below
+	rib::Geometry rg;
+	if (A.arith == 0 && A.ribbon > 0 && rib::geometry(A.ribbon, rg))
+	{
+		std::vector<uint32_t> rorder, rest;
+		uint32_t maxTr = 0;
+		for (uint32_t r : order)
+		{
+			if ((int)res.desc[r].bw - rg.hw - 18 >= 2)
+			{
+				rorder.push_back(r);
+				maxTr = std::max(maxTr, res.desc[r].S + 1);
+			}
+			else rest.push_back(r);
+		}
+		if (!rorder.empty())
+		{
+			const size_t resident = (size_t)rt.sms * (A.warps_per_sm > 0 ? (size_t)A.warps_per_sm : (size_t)rg.blocks_per_sm * rg.warps_per_block);
+			unsigned gridw = (unsigned)std::min<size_t>(resident, rorder.size());
+			size_t per_slot = 0, o_sch = 0, o_ck = 0, o_ob = 0, o_hdr = 0, o_rec = 0, o_pp = 0;
+			uint64_t rcap = 0;
+			if (mode != 0)
+			{
+				const size_t nck = (size_t)maxTr / rg.ck + 2;
+				size_t o = 0;
+				o_sch = o; o = align_up(o + ((size_t)maxTr / 32 + 2) * 8, 256);
+				o_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
+				o_ob = o; o = align_up(o + nck * 64 * 4, 256);
+				if (mode == 1)
+				{
+					rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64;
+					o_hdr = o; o = align_up(o + ((size_t)maxTr + 32) * rg.hdrw * 4, 256);
+					o_rec = o; o = align_up(o + rcap * rg.recf * 4, 256);
+					o_pp = o; o = align_up(o + ((size_t)maxTr + 32) * 4, 256);
+				}
+				per_slot = o;
+				const size_t budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
+				const size_t fit = std::max<size_t>(1, budget / per_slot);
+				if (tm.on)
+					fprintf(stderr, "[dyn timing] ribbon scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit\n",
+						per_slot / 1048576.0, gridw, budget / 1073741824.0, fit);
+				gridw = (unsigned)std::min<size_t>(gridw, fit);
+			}
+			std::vector<SlotScratch> slots(gridw);
+			memset(slots.data(), 0, slots.size() * sizeof(SlotScratch));
+			if (mode != 0)
+			{
+				unsigned char* base = (unsigned char*)A.d_scratch.get(rt, per_slot * gridw);
+				for (unsigned q = 0; q < gridw; ++q)
+				{
+					unsigned char* b = base + per_slot * q;
+					slots[q].sched = (uint2*)(b + o_sch);
+					slots[q].ckpt = (float*)(b + o_ck);
+					slots[q].ckpt_ob = (double*)(b + o_ob);
+					if (mode == 1)
+					{
+						slots[q].hdr = (uint32_t*)(b + o_hdr);
+						slots[q].recs = (void*)(b + o_rec);
+						slots[q].pp = (float*)(b + o_pp);
+					}
+				}
+			}
+			SlotScratch* d_slots = (SlotScratch*)A.d_slots.get(rt, (size_t)gridw * sizeof(SlotScratch));
+			rt.h2d(d_slots, slots.data(), (size_t)gridw * sizeof(SlotScratch));
+			rt.h2d(d_order, rorder.data(), rorder.size() * 4);
+			BatchArgs rb = ba;
+			rb.n_reads = (uint32_t)rorder.size();
+			rb.slots = d_slots;
+			rb.n_slots = gridw;
+			rb.rec_cap = rcap;
+			tm.lap("enqueue_ribbon");
+			rt.mark(6);
+#ifndef DYN_HOST_EMU
+			const int le = rib::launch((void*)rt.stream, rb, gridw, mode, A.ribbon);
+			if (le != 0) throw std::runtime_error(std::string("CUDA error launching the ribbon kernel: ") + cudaGetErrorString((cudaError_t)le));
+#else
+			rib::launch(nullptr, rb, gridw, mode, A.ribbon);
+#endif
+			rt.mark(7);
+			++launches;
+			rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
+			rt.sync();
+			tm.lap("ribbon_kernel");
+			A.ribbon_ms = rt.elapsed(6, 7);
+			A.n_ribbon = rorder.size();
+			for (uint32_t r : rorder)
+				if (res.out[r].status == ST_LIN_FAULT)
+				{
+					rest.push_back(r);
+					++A.n_rib_fault;
+					if (mode == 2)
+					{
+						// columns the read flushed before its fault was detected: the full-band kernels accumulate
+						const ReadDesc& d = res.desc[r];
+						rt.zero(ba.read_w + d.pc_off, (size_t)d.N * 8);
+						rt.zero(ba.read_x + d.pc_off, (size_t)d.N * 8);
+						rt.zero(ba.read_xx + d.pc_off, (size_t)d.N * 8);
+					}
+				}
+			std::stable_sort(rest.begin(), rest.end(), [&](uint32_t x, uint32_t y) {
+				return (uint64_t)res.desc[x].S * (2 * res.desc[x].bw + 1) > (uint64_t)res.desc[y].S * (2 * res.desc[y].bw + 1);
+			});
+			order.swap(rest);
+			maxT = 0;
+			for (uint32_t r : order) maxT = std::max(maxT, res.desc[r].S + 1);
+			if (!order.empty()) rt.h2d(d_order, order.data(), order.size() * 4);
+			rt.zero(d_queue, 64);
+			ba.n_reads = (uint32_t)order.size();
+		}
+	}
+
+	double fallback_ms = 0.0, main_ms = 0.0;
+	if (!order.empty())
+	{
 	const bool lin_first = (A.arith == 0);
 	// ---- scratch: one slot per resident warp, sized for the longest read --------------------------------------
 	// Z-only runs the backward pass alone: <= 128 registers and no shared memory, i.e. 16 single-warp CTAs per SM
@@ -928,6 +1094,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	}
 	if (WPC > 1 && lin_first) grid = std::max<unsigned>(grid / WPC, 1u) * WPC;  // whole CTAs of WPC warps
 	std::vector<SlotScratch> slots(grid);
+	memset(slots.data(), 0, slots.size() * sizeof(SlotScratch));
 	if (mode != 0)
 	{
 		unsigned char* base = (unsigned char*)A.d_scratch.get(rt, per_slot * grid);
@@ -943,53 +1110,19 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			slots[s].pp = (float*)(b + o_pp);
 		}
 	}
-	else
-		memset(slots.data(), 0, slots.size() * sizeof(SlotScratch));
 	SlotScratch* d_slots = (SlotScratch*)A.d_slots.get(rt, (size_t)grid * sizeof(SlotScratch));
 	rt.h2d(d_slots, slots.data(), (size_t)grid * sizeof(SlotScratch));
+	ba.slots = d_slots;
+	ba.n_slots = grid;
+	ba.rec_cap = rec_cap;
 
-	BatchArgs ba;
-	memset(&ba, 0, sizeof(ba));
-	ba.reads = d_desc; ba.order = d_order; ba.n_reads = (uint32_t)order.size(); ba.queue = d_queue;
-	ba.signal = d_sig; ba.pc = d_pc; ba.slots = d_slots; ba.rec_cap = rec_cap; ba.out = d_out;
-	ba.out_sigpos = d_sigpos; ba.out_prob = d_prob;
-	ba.m1 = (float)(A.trans[0] * LOG2E);
-	ba.e2 = (float)(A.trans[2] * LOG2E);
-	ba.thr2 = (float)A.thr2;
-	ba.m1_lin = (float)std::exp(A.trans[0]);
-	ba.e2_lin = (float)std::exp(A.trans[2]);
-	ba.thr_lin = (float)std::exp2(A.thr2);
-	ba.mode = mode;
-	ba.uni_a = A.uni_a;
-	ba.uni_c = A.uni_c;
-	ba.fwd_fast = A.fwd_fast;
-	ba.kmers = d_kmers;
-	if (mode == 2)
-	{
-		ba.read_w = (double*)A.d_rw.get(rt, pc_total * 8);
-		ba.read_x = (double*)A.d_rx.get(rt, pc_total * 8);
-		ba.read_xx = (double*)A.d_rxx.get(rt, pc_total * 8);
-		rt.zero(ba.read_w, pc_total * 8);
-		rt.zero(ba.read_x, pc_total * 8);
-		rt.zero(ba.read_xx, pc_total * 8);
-		ba.stat_w = (double*)A.d_sw.get(rt, A.K * 8);
-		ba.stat_x = (double*)A.d_sx.get(rt, A.K * 8);
-		ba.stat_xx = (double*)A.d_sxx.get(rt, A.K * 8);
-		rt.zero(ba.stat_w, A.K * 8);
-		rt.zero(ba.stat_x, A.K * 8);
-		rt.zero(ba.stat_xx, A.K * 8);
-	}
-
-	// ---- K2..K5: the DP kernel ------------------------------------------------------------------------------------
+	// ---- K2..K5: the full-band DP kernel ----------------------------------------------------------------------------
 	const bool lin = (A.arith == 0);
-	A.n_fallback = 0;
-	A.n_retry_lin = 0;
 	tm.lap("enqueue");
 	rt.mark(2);
 	launch_align<CFG, MINB, CFGLIN, MINB_FB, WPC>(rt, ba, grid, mode, lin);
 	rt.mark(3);
-	int launches = 2;
-	double fallback_ms = 0.0;
+	++launches;
 	if (lin)
 	{
 		// reads the FP32 linear arithmetic could not represent (ST_LIN_FAULT) are re-run in the log2 domain
@@ -1035,6 +1168,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			++launches;
 		}
 	}
+	rt.sync();
+	main_ms = rt.elapsed(2, 3);
+	}
 	if (mode == 2)
 	{
 		FoldArgs fa;
@@ -1068,7 +1204,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	rt.sync();
 	tm.lap("results_d2h");
 	A.timing[0] = rt.elapsed(0, 1);
-	A.timing[1] = rt.elapsed(2, 3) + fallback_ms;
+	A.timing[1] = A.ribbon_ms + main_ms + fallback_ms;
 	A.timing[2] = launches;
 	for (uint32_t r = 0; r < n; ++r)
 	{
@@ -2031,6 +2167,11 @@ const char* dyn_last_error(const dyn_aligner* A) { return A->last_error.c_str();
 uint64_t dyn_last_fallbacks(const dyn_aligner* A) { return A->n_fallback; }
 uint64_t dyn_last_lin_retries(const dyn_aligner* A) { return A->n_retry_lin; }
 int dyn_last_variant(const dyn_aligner* A) { return A->last_variant; }
+void dyn_last_ribbon(const dyn_aligner* A, uint64_t* out2)
+{
+	out2[0] = A->n_ribbon;
+	out2[1] = A->n_rib_fault;
+}
 
 void dyn_last_timing(const dyn_aligner* A, double* out3)
 {
@@ -2062,8 +2203,16 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	else if (k == "recs_per_row") A->recs_per_row = value;
 	else if (k == "mem_fraction") A->mem_fraction = value;
 	else if (k == "sms") A->rt.sms = std::max(1, (int)value);
+	else if (k == "ribbon") A->ribbon = (value == 2.0 || value == 4.0) ? (int)value : 0;
+	else if (k == "rib_guard") A->rib_guard = std::max(8, (int)value);
+	else if (k == "thr_rib") A->thr_rib = value;
+	else if (k == "rib_recs_per_row") A->rib_recs_per_row = value;
 	else return -1;
 	return 0;
 }
 
 } // extern "C"
+
+#ifdef DYN_HOST_EMU
+#include "ribbon.cu"  // the emulator build is one translation unit
+#endif

@@ -1,0 +1,123 @@
+// Ribbon kernels (dp_ribbon.cuh): kernel entry points and launcher.  Built by nvcc for sm_100a; under the test emulator
+// this file is included by engine.cu (one translation unit, g++).
+#include "dp_ribbon.cuh"
+#include "ribbon.h"
+
+namespace dyn
+{
+namespace rib
+{
+
+namespace
+{
+
+constexpr int WPB = 4;  // warps per CTA; the warps of a CTA are independent (each pulls its own reads)
+
+using RC2 = RCfg<2, 16, 8, 8>;
+using RC4 = RCfg<4, 16, 8, 8>;
+constexpr int BPS2 = 6;  // 24 resident warps per SM: <= 80 registers per thread
+constexpr int BPS4 = 4;  // 16 resident warps per SM: <= 128 registers per thread
+
+template <class RC, int MODE>
+DYN_DEV void worker(const BatchArgs& args, unsigned char* smem_raw, int lane, unsigned slot)
+{
+	if (slot >= args.n_slots) return;
+	const SlotScratch sc = args.slots[slot];
+	while (true)
+	{
+		uint32_t i = 0;
+		if (lane == 0) i = atomicAdd(args.queue, 1u);
+		i = __shfl_sync(FULL, i, 0);
+		if (i >= args.n_reads) break;
+		const uint32_t ridx = args.order[i];
+		const ReadDesc rd = args.reads[ridx];
+		if (rd.status != ST_OK)
+		{
+			if (lane == 0)
+			{
+				ReadOut o;
+				o.Z = 0.0; o.dZ = 0.0; o.nrec = 0; o.status = rd.status; o.xi_m = 0.0; o.xi_e = 0.0;
+				args.out[ridx] = o;
+			}
+			continue;
+		}
+		ribbon_read<RC, MODE>(args, rd, ridx, sc, smem_raw, lane);
+		__syncwarp();
+	}
+}
+
+#ifndef DYN_HOST_EMU
+template <class RC, int MODE, int BPS>
+__global__ void __launch_bounds__(32 * WPB, BPS) k_ribbon(BatchArgs args)
+{
+	extern __shared__ __align__(16) unsigned char smem_all[];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	worker<RC, MODE>(args, smem_all + (size_t)wid * RC::SMEM_BYTES, lane, blockIdx.x * WPB + wid);
+}
+
+template <class RC, int BPS>
+int launch_t(cudaStream_t stream, const BatchArgs& args, unsigned n_warps, int mode)
+{
+	const size_t smem = RC::SMEM_BYTES * WPB;
+	cudaError_t e = cudaSuccess;
+	// the opt-in is per device and cheap: set it before every launch (a handle per device may share this process)
+	e = cudaFuncSetAttribute(k_ribbon<RC, 1, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	e = cudaFuncSetAttribute(k_ribbon<RC, 2, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	const unsigned ctas = (n_warps + WPB - 1) / WPB;
+	if (mode == 0) k_ribbon<RC, 0, BPS><<<ctas, 32 * WPB, 0, stream>>>(args);
+	else if (mode == 1) k_ribbon<RC, 1, BPS><<<ctas, 32 * WPB, smem, stream>>>(args);
+	else k_ribbon<RC, 2, BPS><<<ctas, 32 * WPB, smem, stream>>>(args);
+	return (int)cudaGetLastError();
+}
+#else
+template <class RC, int BPS>
+int launch_t(void*, const BatchArgs& args, unsigned n_warps, int mode)
+{
+	const size_t smem = RC::SMEM_BYTES;
+	if (mode == 0) simt::launch(n_warps, smem, [&]() { worker<RC, 0>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else if (mode == 1) simt::launch(n_warps, smem, [&]() { worker<RC, 1>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else simt::launch(n_warps, smem, [&]() { worker<RC, 2>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	return 0;
+}
+#endif
+
+template <class RC>
+void fill(Geometry& g, int bps)
+{
+	g.cpl = RC::CPL;
+	g.hw = RC::HW;
+	g.ck = RC::CK;
+	g.ckf = RC::CKF;
+	g.hdrw = RC::HDRW;
+	g.recf = RC::RECF;
+	g.smem_per_warp = RC::SMEM_BYTES;
+	g.warps_per_block = WPB;
+	g.blocks_per_sm = bps;
+}
+
+} // namespace
+
+bool geometry(int cpl, Geometry& g)
+{
+	if (cpl == 2) fill<RC2>(g, BPS2);
+	else if (cpl == 4) fill<RC4>(g, BPS4);
+	else return false;
+	return true;
+}
+
+int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl)
+{
+#ifndef DYN_HOST_EMU
+	cudaStream_t s = (cudaStream_t)stream;
+#else
+	void* s = stream;
+#endif
+	if (cpl == 2) return launch_t<RC2, BPS2>(s, args, n_warps, mode);
+	if (cpl == 4) return launch_t<RC4, BPS4>(s, args, n_warps, mode);
+	return -1;
+}
+
+} // namespace rib
+} // namespace dyn

@@ -1,0 +1,35 @@
+// Launcher interface of the ribbon kernels (dp_ribbon.cuh); its own translation unit (ribbon.cu) so that it builds in
+// parallel with engine.cu.
+#pragma once
+
+#include <stddef.h>
+#include <stdint.h>
+
+namespace dyn
+{
+struct BatchArgs;
+namespace rib
+{
+
+struct Geometry
+{
+	int cpl;              // lattice columns per lane
+	int hw;               // half window: live columns of a row are [mid - hw, mid + hw]
+	int ck;               // checkpoint spacing (rows)
+	int ckf;              // floats per checkpoint
+	int hdrw;             // 32-bit words per row header
+	int recf;             // floats per lane record
+	size_t smem_per_warp;
+	int warps_per_block;
+	int blocks_per_sm;    // resident CTAs per SM the kernels are built for (mode 1 / 2)
+};
+
+// cpl: 2 or 4.  Returns false for an unsupported width.
+bool geometry(int cpl, Geometry& g);
+
+// n_warps resident warps (one scratch slot each, args.slots[0 .. n_warps)); mode 0: Z only, 1: align, 2: train.
+// Returns 0 or the cudaError_t of the launch.
+int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl);
+
+} // namespace rib
+} // namespace dyn

@@ -181,6 +181,10 @@ uint64_t dyn_last_lin_retries(const dyn_aligner*);
 /* kernel build variant the last batch call ran (csrc/engine.cu: 3 = general kernels at 8 CTAs/SM, 4 = uniform-sigma
  * kernels at 8 CTAs/SM, ...); -1 before the first call */
 int dyn_last_variant(const dyn_aligner*);
+/* ribbon kernels (first tier: the same recurrences on a narrow window that follows the probability mass, every loss
+ * checked on the device): out2[0] = reads of the last batch call they were given, out2[1] = reads they handed on to
+ * the full-band kernels (window / range checks failed); results are identical either way */
+void dyn_last_ribbon(const dyn_aligner*, uint64_t* out2);
 /* run all work of this handle on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
  * of the handle's own stream, so that the caller's CUDA events bracket it */
 int dyn_set_stream(dyn_aligner*, void* cuda_stream);

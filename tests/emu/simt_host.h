@@ -37,6 +37,11 @@ struct uint4
 	unsigned x, y, z, w;
 };
 inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+struct uint2
+{
+	unsigned x, y;
+};
+inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 struct dim3e
 {
 	unsigned x = 1, y = 1, z = 1;
