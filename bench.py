@@ -338,6 +338,7 @@ def main():
     def step_device():
         """One step: every batch through the C ABI with device-resident inputs.  Returns (#ok reads, kernel ms, launches)."""
         ok, kms, nl, fb, rl = 0, 0.0, 0, 0, 0
+        rib = step_device.rib
         for b in batches:
             res, _, _, _ = al.align_packed(b["sig"].data_ptr(), b["sig_off"], b["bases"].data_ptr(), b["seq_off"],
                                            not args.z_only, device=True)
@@ -346,12 +347,16 @@ def main():
             nl += tm["launches"]
             fb += tm["log2_fallback_reads"]
             rl += tm["lin_retry_reads"]
+            rib[0] += tm["ribbon_reads"]
+            rib[1] += tm["ribbon_faults"]
             ok += sum(1 for i in range(b["sig_off"].size - 1) if res[i].status == 0)
         return ok, kms, nl, fb, rl
 
     dp_ms, launches, fallbacks, lin_retries = [], 0, 0, 0
+    step_device.rib = [0, 0]
     for _ in range(args.warmup):
         step_device()
+    step_device.rib = [0, 0]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -452,6 +457,7 @@ def main():
         "peak_at_max_clock": mufu_peak_max, "peak_source": "16 MUFU/clk/SM x SMs x SM clock sampled by nvidia-smi during the timed region",
         "cell_updates_per_s": 3.0 * cells / dp_s, "kernel_ms": dp_ms_all,
         "log2_fallback_reads": int(fallbacks), "lin_retry_reads": int(lin_retries),
+        "ribbon_reads": int(step_device.rib[0]), "ribbon_fault_reads": int(step_device.rib[1]),
         "traffic": None,
         "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1l_k_align_final_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
         "hbm": {"achieved": hbm_bytes / dp_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

@@ -998,8 +998,12 @@ DYN_DEV bool trace_decisions(Warp<CFG>& w, const SlotScratch& sc, const BatchArg
 	return true;
 }
 
+DYN_DEV void segment_medians_impl(int lane, uint32_t T, uint32_t N, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd);
 template <class CFG>
-DYN_DEV void segment_medians(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd);
+DYN_DEV void segment_medians(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd)
+{
+	segment_medians_impl(w.lane, w.T, w.N, sc, args, rd);
+}
 
 template <class CFG>
 DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, unsigned char* smem_raw,
@@ -1044,13 +1048,10 @@ DYN_DEV bool traceback_pass(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs
 }
 
 // phase 3 of pass 3: per-segment median of the path posteriors sc.pp (NT:418-422, aligner.cpp:247-263)
-template <class CFG>
-DYN_DEV void segment_medians(Warp<CFG>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd)
+DYN_DEV void segment_medians_impl(int lane, uint32_t T, uint32_t N, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd)
 {
 	constexpr int NV = 4;           // register path: dwells up to 32 * NV samples
 	constexpr float PAD = 3.0e38f;  // above every posterior
-	const int lane = w.lane;
-	const uint32_t T = w.T, N = w.N;
 	const uint32_t* border = args.out_sigpos + rd.out_off;
 	double* prob = args.out_prob + rd.out_off;
 	const uint32_t Kc = N - 1;

@@ -975,7 +975,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			{
 				const size_t nck = (size_t)maxTr / rg.ck + 2;
 				size_t o = 0;
-				o_sch = o; o = align_up(o + ((size_t)maxTr / 32 + 2) * 8, 256);
+				o_sch = o; o = align_up(o + nck * 8, 256);
 				o_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
 				o_ob = o; o = align_up(o + nck * 64 * 4, 256);
 				if (mode == 1)

@@ -13,8 +13,8 @@ namespace
 
 constexpr int WPB = 4;  // warps per CTA; the warps of a CTA are independent (each pulls its own reads)
 
-using RC2 = RCfg<2, 16, 8, 8>;
-using RC4 = RCfg<4, 16, 8, 8>;
+using RC2 = RCfg<2>;
+using RC4 = RCfg<4>;
 constexpr int BPS2 = 6;  // 24 resident warps per SM: <= 80 registers per thread
 constexpr int BPS4 = 4;  // 16 resident warps per SM: <= 128 registers per thread
 
@@ -88,7 +88,7 @@ void fill(Geometry& g, int bps)
 {
 	g.cpl = RC::CPL;
 	g.hw = RC::HW;
-	g.ck = RC::CK;
+	g.ck = RC::GR;
 	g.ckf = RC::CKF;
 	g.hdrw = RC::HDRW;
 	g.recf = RC::RECF;
