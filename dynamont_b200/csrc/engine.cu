@@ -465,14 +465,10 @@ void launch_align_t(Rt& rt, const BatchArgs& args, unsigned grid, int mode)
 {
 	const size_t smem = CFG::SMEM_BYTES * WPC;
 #ifndef DYN_HOST_EMU
-	static bool attr_set = false;
-	if (!attr_set)
-	{
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 0, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
-	}
+	// the shared-memory opt-in is a per-DEVICE attribute of the function: set it for the kernel about to be launched on
+	// the current device every time (cheap), so that a second handle on another device of the same process works too
+	if (mode == 1) CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 1, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	else if (mode == 2) CK_CUDA(cudaFuncSetAttribute(k_align<CFG, 2, MINB, LIN, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const unsigned ctas = std::max(1u, grid / WPC);  // the host sizes the slot table for grid warps
 	if (mode == 0) k_align<CFG, 0, MINB, LIN, WPC><<<ctas, 32 * WPC, 0, rt.stream>>>(args);  // the backward pass alone needs no shared memory
 	else if (mode == 1) k_align<CFG, 1, MINB, LIN, WPC><<<ctas, 32 * WPC, smem, rt.stream>>>(args);
@@ -862,8 +858,15 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		float* p = (float*)A.d_sig.get(rt, sig_total * sizeof(float));
 		if (io.sig_host64)
 		{
+			// round to FP32 (what the DP consumes) on up to 8 host threads
 			conv.resize(sig_total);
-			for (uint64_t i = 0; i < sig_total; ++i) conv[i] = (float)io.sig_host64[i];
+			const double* src = io.sig_host64;
+			float* dstf = conv.data();
+			const uint32_t parts = (uint32_t)std::min<uint64_t>(4096, sig_total / 65536 + 1);
+			parallel_ranges(parts, sig_total, [&](uint32_t a, uint32_t b) {
+				const uint64_t i0 = sig_total * a / parts, i1 = sig_total * b / parts;
+				for (uint64_t i = i0; i < i1; ++i) dstf[i] = (float)src[i];
+			});
 			rt.h2d(p, conv.data(), sig_total * sizeof(float));
 		}
 		else
@@ -915,10 +918,14 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	ba.out_sigpos = d_sigpos; ba.out_prob = d_prob;
 	ba.m1 = (float)(A.trans[0] * LOG2E);
 	ba.e2 = (float)(A.trans[2] * LOG2E);
-	ba.thr2 = (float)A.thr2;
+	// full-band kernels: training statistics are gathered from the sparse posterior records, so the record threshold is
+	// what truncates a kmer's weight: 2^-40 keeps every kmer above the documented weight threshold (1e-3) exact to
+	// ~1e-9 relative (2^-22, the alignment threshold, cost 2e-3 on the trained stdev of light kmers)
+	const double thr2_eff = (mode == 2) ? std::min(A.thr2, -40.0) : A.thr2;
+	ba.thr2 = (float)thr2_eff;
 	ba.m1_lin = (float)std::exp(A.trans[0]);
 	ba.e2_lin = (float)std::exp(A.trans[2]);
-	ba.thr_lin = (float)std::exp2(A.thr2);
+	ba.thr_lin = (float)std::exp2(thr2_eff);
 	ba.mode = mode;
 	ba.uni_a = A.uni_a;
 	ba.uni_c = A.uni_c;
@@ -1477,7 +1484,23 @@ static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilitie
 			if (res.out[r].status == ST_REC_OVERFLOW) retry.push_back(r);
 		if (!retry.empty())
 		{
-			const double saved = A->recs_per_row;
+			// restores the record budget and the per-batch counters however the single-read retries end
+			struct Restore
+			{
+				dyn_aligner* A;
+				double recs;
+				uint64_t fb, rl, nr, nf;
+				double t0, t1, t2;
+				int lv;
+				~Restore()
+				{
+					A->recs_per_row = recs;
+					A->n_fallback = fb; A->n_retry_lin = rl; A->n_ribbon = nr; A->n_rib_fault = nf;
+					A->timing[0] = t0; A->timing[1] = t1; A->timing[2] = t2;
+					A->last_variant = lv;
+				}
+			} restore{A, A->recs_per_row, A->n_fallback, A->n_retry_lin, A->n_ribbon, A->n_rib_fault, A->timing[0], A->timing[1],
+				A->timing[2], A->last_variant};
 			A->recs_per_row = 1e9;  // clamped to the band width inside run_batch
 			for (uint32_t r : retry)
 			{
@@ -1508,7 +1531,6 @@ static int align_common(dyn_aligner* A, const BatchIO& io, int calc_probabilitie
 				std::copy(sp.begin(), sp.end(), sigpos + res.seg_off[r]);
 				std::copy(pr.begin(), pr.end(), prob_st + res.seg_off[r]);
 			}
-			A->recs_per_row = saved;
 		}
 
 		for (uint32_t r = 0; r < io.n; ++r)

@@ -48,7 +48,7 @@ def test_train_matches_reference_golden(case, aligners):
     np.testing.assert_allclose(pooled["xx"][km][heavy], case.stat_xx[heavy], rtol=TRAIN_RTOL)
     # per-read M-step (reference semantics)
     np.testing.assert_allclose(r["emission_model"]["mean"][km][heavy], case.train_mean[heavy], rtol=TRAIN_RTOL, atol=1e-5)
-    np.testing.assert_allclose(r["emission_model"]["stdev"][km][heavy], case.train_stdev[heavy], rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(r["emission_model"]["stdev"][km][heavy], case.train_stdev[heavy], rtol=TRAIN_RTOL, atol=1e-6)
     # untouched kmers keep the model (NT:531-534)
     mean0, sd0 = al.model()
     untouched = np.ones(al.num_kmers, bool)

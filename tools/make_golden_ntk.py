@@ -25,6 +25,8 @@ CASES = [  # name, pore, model, length, spb, seed, want end-to-end
     ("ntk_rna002_120", "rna002", "rna002_5mer", 120, 8, 202, True),
     ("ntk_dna_r9_80", "dna_r9", "rna004_5mer", 80, 9, 203, True),
     ("ntk_rna004_9mer_14", "rna004", "synthetic_rna004_9mer", 14, 6, 204, False),
+    # config 3 is 9-mer: one polyA-prefixed 9-mer read WITH an end-to-end alignment (reference: ~25 s, 1.7 GB for T ~ 150)
+    ("ntk_rna004_9mer_polyA", "rna004", "synthetic_rna004_9mer", 24, 9, 205, True),
 ]
 
 
