@@ -32,7 +32,15 @@ CONFIGS = {
     # name: (pore, model, min_len, max_len, samples/base, dwell, default reads per step per GPU)
     "c1": ("rna002", "rna002_5mer", 1000, 1000, 30.0, "geometric", 1000),
     "c2": ("rna004", "synthetic_rna004_9mer", 500, 5000, 30.0, "geometric", 100000),
+    # c2 with a per-kmer sigma (what a trained model looks like): same kernels, the emission constants are per column anyway
+    "c2v": ("rna004", "synthetic_rna004_9mer_varsd", 500, 5000, 30.0, "geometric", 100000),
+    # config 4 (long-read stress): 50 kb reads of ~2 M samples, Gamma-4 dwell; 10 000 reads = 8 steps
+    "c4": ("rna004", "synthetic_rna004_9mer", 50000, 50000, 40.0, "gamma", 1280),
+    # config 5 (dynamont-train): one step = one pooled Baum-Welch iteration (expected counts of all reads, ONE all-reduce of
+    # the 3*4^9+4 statistics over NCCL, M-step on the device); 1 M reads = 10 steps of 100 000 per GPU at 1 GPU
+    "c5": ("rna004", "synthetic_rna004_9mer", 500, 5000, 30.0, "geometric", 100000),
 }
+TRAIN_CONFIGS = {"c5"}
 MODELS_DIR = os.path.join(ROOT, "tests", "golden", "_models")
 
 
@@ -60,6 +68,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--em-iterations", type=int, default=0, help="c5: (unused; every step is one EM iteration)")
     ap.add_argument("--reads", type=int, default=0, help="reads per step per GPU (0 = config default)")
     ap.add_argument("--batch", type=int, default=20000, help="reads per C-ABI call (a step runs ceil(reads/batch) calls)")
     ap.add_argument("--seed", type=int, default=20262000)
@@ -171,7 +180,7 @@ def cpu_pool_plan(cfg, sample):
     avail = psutil.virtual_memory().available
     procs = int(max(1, min(cores, (0.5 * avail) // worst)))
     if sample <= 0:
-        sample = max(3 * procs, 8)  # ~3 reads per worker: bounded (tens of seconds) yet not dominated by the longest read
+        sample = max(4 * procs, 8)  # ~4 reads per worker: bounded (tens of seconds per step) yet not dominated by the longest read
     return kind, procs, sample
 
 
@@ -251,7 +260,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     reads_per_gpu = args.reads or default_reads
-    workload = f"{args.config}: {pore} {model} basic mode, reads {lo}-{hi} b at ~{spb:g} samples/base ({dwell} dwell), band 400"
+    train = args.config in TRAIN_CONFIGS
+    what = "dynamont-train (pooled Baum-Welch iteration: expected counts, all-reduce, M-step)" if train else "basic mode align(calc_probabilities=True)"
+    workload = f"{args.config}: {pore} {model} {what}, reads {lo}-{hi} b at ~{spb:g} samples/base ({dwell} dwell), band 400"
 
     # ------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -260,6 +271,11 @@ def main():
         kind, procs, sample = cpu_pool_plan(cfg, args.cpu_sample)
         model_path, reads = gen_reads_numpy(cfg, sample, args.seed + 17)
         cells = cells_of(reads, model_path, pore)
+        if kind == "reference":
+            # the workers are forked from this process: load the compiled reference here as well, so that the library the
+            # arm runs (oracle/_ref/libdynamont_ref.so) is visible in this process' memory map
+            import oracle
+            _parent_handle = oracle.Reference(model_path, pore)  # noqa: F841
         times = []
         for i in range(args.warmup + args.steps):
             dt = run_cpu_sample(cfg, kind, procs, reads, model_path)
@@ -335,8 +351,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    stats = torch.zeros(3 * al.num_kmers + 4, dtype=torch.float64, device=dev) if train else None
+    ar_ms, mstep_ms = [], []
+
+    def step_train():
+        """One pooled EM iteration: dyn_train_accumulate over every batch (device-resident inputs, statistics accumulated
+        in `stats` on the device), ONE all-reduce of `stats` in place, M-step on the device (dyn_train_mstep_device)."""
+        ok, kms, nl, fb, rl = 0, 0.0, 0, 0, 0
+        rib = step_device.rib
+        stats.zero_()
+        for b in batches:
+            st = al.train_accumulate_packed(b["sig"].data_ptr(), b["sig_off"], b["bases"].data_ptr(), b["seq_off"],
+                                            stats.data_ptr(), device=True)
+            tm = al.last_timing()
+            kms += tm["dp_ms"]
+            nl += tm["launches"]
+            fb += tm["log2_fallback_reads"]
+            rl += tm["lin_retry_reads"]
+            rib[0] += tm["ribbon_reads"]
+            rib[1] += tm["ribbon_faults"]
+            ok += int((st == 0).sum())
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        if world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        a1.record()
+        t0m = time.perf_counter()
+        al.mstep_device(stats.data_ptr())  # synchronises the handle's stream
+        torch.cuda.synchronize()
+        mstep_ms.append((time.perf_counter() - t0m) * 1e3)
+        ar_ms.append(a0.elapsed_time(a1))
+        return ok, kms, nl + 2, fb, rl
+
     def step_device():
         """One step: every batch through the C ABI with device-resident inputs.  Returns (#ok reads, kernel ms, launches)."""
+        if train:
+            return step_train()
         ok, kms, nl, fb, rl = 0, 0.0, 0, 0, 0
         rib = step_device.rib
         for b in batches:
@@ -390,17 +440,39 @@ def main():
             host.append((hs, hb, b["sig_off"], b["seq_off"]))
         torch.cuda.synchronize()
 
-        def step_host():
+        # the call a streaming user makes: dyn_align_submit / dyn_align_wait (Aligner.submit_packed / wait), two batches in
+        # flight, so that the H2D copy of the next batch and the D2H copy + fan-out of the previous one overlap the kernels
+        from collections import deque
+        inflight = deque()
+
+        def step_host_train():
+            stats.zero_()
             for bi in range(len(batches)):
                 hs, hb, so, qo = host[bi % len(host)]
-                al.align_packed(hs.data_ptr(), so, hb.data_ptr(), qo, True, device=False)
-        step_host()
+                al.train_accumulate_packed(hs.data_ptr(), so, hb.data_ptr(), qo, stats.data_ptr(), device=False)
+            if world > 1:
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            al.mstep_device(stats.data_ptr())
+            torch.cuda.synchronize()
+
+        def step_host(drain):
+            if train:
+                return step_host_train()
+            for bi in range(len(batches)):
+                hs, hb, so, qo = host[bi % len(host)]
+                inflight.append(al.submit_packed(hs.data_ptr(), so, hb.data_ptr(), qo, True))
+                if len(inflight) >= 2:
+                    al.wait(inflight.popleft())
+            while drain and inflight:
+                al.wait(inflight.popleft())
+        for _ in range(max(1, args.warmup)):
+            step_host(True)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(args.steps):
-            step_host()
+        for i in range(args.steps):
+            step_host(i == args.steps - 1)
         e1.record()
         barrier()
         wall = (time.perf_counter() - t0) / args.steps
@@ -409,23 +481,29 @@ def main():
         nseg = sum(int(al._lib.dyn_count_segments(al._h, b["seq_off"].ctypes.data_as(u64p), b["seq_off"].size - 1))
                    for b in batches)
         e2e = {"ms": e2e_ms, "wall_ms": wall * 1e3, "h2d": n_samples * 4 + n_bases + (n_reads + 1) * 8 + n_reads * 48,
-               "d2h": nseg * 12 + n_reads * 52, "distinct_host_batches": len(host)}
+               "d2h": (n_reads * 52 + 2 * 4 ** 9 * 8) if train else (nseg * 12 + n_reads * 52), "distinct_host_batches": len(host)}
 
     # ---- reduce over ranks: time = max, work = sum
-    stats = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(np.mean(dp_ms))], dtype=torch.float64, device=dev)
+    tstats = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(np.mean(dp_ms))], dtype=torch.float64, device=dev)
     work = torch.tensor([float(cells), float(n_reads), float(n_ok)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tstats, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    ms_all, e2e_ms_all, dp_ms_all = [float(x) for x in stats.tolist()]
+    ms_all, e2e_ms_all, dp_ms_all = [float(x) for x in tstats.tolist()]
     cells_all, reads_all, ok_all = [float(x) for x in work.tolist()]
     gcups = cells_all / (ms_all * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (k_align): SFU/MUFU-bound (north_star), HBM traffic reported beside it
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------------------
+    # north_star: "achieved FP32/SFU throughput against B200 peak".  `achieved` keeps the ALGORITHMIC definition of
+    # the reference's log-space forward + backward = 2 passes x 2 MUFU (ex2 + lg2) per in-band lattice cell
+    # (training: + 2 for the two exp of gamma, NT:505-508), divided by the kernel time measured with CUDA events.  The
+    # ribbon kernels evaluate only the window of the band in which FP32 values are non-zero (63 of ~401 columns) with
+    # 1 MUFU per evaluated cell-update, so `frac` can exceed 1: `executed` / `executed_frac` are the MUFU ops actually
+    # issued, and `issue` (from the committed ncu capture of the same kernel) is what really bounds it: issue slots.
     props = torch.cuda.get_device_properties(dev)
     sms = props.multi_processor_count
     peaks = {}
@@ -434,34 +512,54 @@ def main():
             peaks = json.load(fh)
     except Exception:
         pass
+    counters = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ribbon_counters.json")) as fh:
+            counters = json.load(fh)
+    except Exception:
+        pass
     clk_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
     mufu_peak = 16.0 * sms * clk_mhz * 1e6 / 1e9           # G MUFU op/s at the clock seen under load
     mufu_peak_max = 16.0 * sms * (peaks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
     dp_s = dp_ms_all * 1e-3
-    # algorithmic work: the log-space forward + backward of the reference = 2 passes x 2 MUFU (ex2 + lg2)
-    # per cell.  Executed: the linear-domain kernels run 3 passes (backward, backward recomputation, forward) x 1 MUFU
-    # (the emission ex2) per cell; the log2-domain kernels (--opt arith=1, and the fallback reads) 3 x 2.
     lin = not any(kv.startswith("arith=") and float(kv.split("=")[1]) != 0 for kv in args.opt)
-    alg_mufu = 4.0 * cells / dp_s / 1e9
-    exe_mufu = (3.0 if lin else 6.0) * cells / dp_s / 1e9
-    # algorithmic HBM bytes per launch: 4*S signal in + 16*N emission constants + 12*Kc out + spill
-    # (checkpoints 3584 B per 8 rows written+read, decision bits 64 B/row written+read, records ~1.1 x 112 B / row
-    # written + read once)
-    hbm_bytes = n_samples * 4.0 + n_bases * 17.0 + (n_samples / 8.0) * 3584 * 2 + n_samples * 64.0 * 2 + n_samples * 125.0 * 2
+    rib_frac = step_device.rib[0] / max(1.0, float(n_reads) * args.steps)  # share of the reads the ribbon kernels kept
+    ribbon_on = rib_frac > 0.5
+    alg_per_cell = 6.0 if train else 4.0
+    alg_mufu = alg_per_cell * cells / dp_s / 1e9
+    rows = float(n_samples)
+    if ribbon_on:
+        # executed: 3 passes x 64 ring slots per row x 1 MUFU
+        exe_mufu = 3.0 * 64.0 * rows / dp_s / 1e9
+        kern = "k_ribbon<RCfg<2>,%d,5> (ribbon: 63-column window that follows the probability mass, groups of 8 rows, linear-domain FP32 " \
+               "block floating point, 1 MUFU per evaluated cell-update, 3 passes)" % (2 if train else 1)
+    else:
+        exe_mufu = (3.0 if lin else 6.0) * cells / dp_s / 1e9
+        kern = kernel_label(al.last_timing()["variant"], lin)
+    ck = counters.get("train" if train else "align", {}) if ribbon_on else {}
+    traffic = ck.get("dram_bytes_per_row") * rows / max(1, len(batches)) if ck.get("dram_bytes_per_row") else None
     roofline = {
         "bound": "sfu",
-        "kernel": kernel_label(al.last_timing()["variant"], lin),
+        "kernel": kern,
         "achieved": alg_mufu, "peak": mufu_peak, "unit": "G MUFU op/s", "frac": alg_mufu / mufu_peak,
-        "achieved_definition": "algorithmic: 4 MUFU per lattice cell (log-space forward + backward, SURVEY 8d) x cells / kernel time",
+        "achieved_definition": "algorithmic: %g MUFU per in-band lattice cell (log-space forward + backward of the reference, SURVEY 8d) x cells / kernel time (CUDA events)" % alg_per_cell,
         "executed": exe_mufu, "executed_frac": exe_mufu / mufu_peak,
+        "evaluated_cells_frac": (64.0 * rows / cells) if ribbon_on else 1.0,
         "peak_at_max_clock": mufu_peak_max, "peak_source": "16 MUFU/clk/SM x SMs x SM clock sampled by nvidia-smi during the timed region",
-        "cell_updates_per_s": 3.0 * cells / dp_s, "kernel_ms": dp_ms_all,
+        "kernel_ms": dp_ms_all, "lattice_rows_per_s": 3.0 * rows / dp_s,
         "log2_fallback_reads": int(fallbacks), "lin_retry_reads": int(lin_retries),
         "ribbon_reads": int(step_device.rib[0]), "ribbon_fault_reads": int(step_device.rib[1]),
-        "traffic": None,
-        "traffic_note": "ncu --set full, c1 x 1184 reads (profiles/r1l_k_align_final_full.md): 22.6 GB read + 22.3 GB written per launch = 3.5 B per lattice cell",
-        "hbm": {"achieved": hbm_bytes / dp_s / 1e9, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "note": "algorithmic signal + constants + checkpoint/decision-bit/record spill per launch"},
+        "issue": {"source": ck.get("source"), "warp_instructions_per_lattice_row": ck.get("instr_per_row"),
+                  "issue_slots_busy_pct": ck.get("issue_busy_pct"), "xu_pipe_pct": ck.get("xu_pct"),
+                  "achieved_warp_instr_per_s": (ck.get("instr_per_row") * rows / dp_s) if ck.get("instr_per_row") else None,
+                  "peak_warp_instr_per_s": 4.0 * sms * clk_mhz * 1e6,
+                  "note": "the ribbon kernels are bound by issue slots (FP32 FMUL/FFMA + shuffles), not by the MUFU pipe"},
+        "traffic": traffic,
+        "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (%s), scaled per lattice row to "
+                         "this launch (one launch = one batch)" % ck.get("source")) if traffic else "no ncu capture for this kernel",
+        "hbm": {"achieved": (ck.get("dram_bytes_per_row") * rows / dp_s / 1e9) if ck.get("dram_bytes_per_row") else None,
+                "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "note": "measured DRAM traffic of the capture (checkpoints, row headers, posterior records, signal) over the kernel time"},
     }
     line = {
         "metric": "dp_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
@@ -476,10 +574,15 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
+    if train:
+        line["train"] = {"stats_bytes_allreduced": (3 * al.num_kmers + 4) * 8, "allreduce_ms": float(np.mean(ar_ms[-args.steps:])),
+                         "mstep_ms": float(np.mean(mstep_ms[-args.steps:])), "em_iterations_timed": args.steps,
+                         "collective": "torch.distributed all_reduce (NCCL) on the device tensor, in place" if world > 1 else "none (1 rank)"}
     if e2e:
         line["e2e"] = {"value": cells_all / (e2e_ms_all * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": e2e_ms_all,
                        "reads_per_s": reads_all / (e2e_ms_all * 1e-3),
                        "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                       "api": "dyn_align_submit / dyn_align_wait (Aligner.submit_packed / wait), two batches in flight; results in fresh host arrays",
                        "host_buffers": "pinned; %d of %d batches distinct on the host (cycled if fewer)" % (e2e["distinct_host_batches"], len(batches))}
     print(json.dumps(line))
     if world > 1:

@@ -122,6 +122,53 @@ class Aligner:
             raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
         return res, seqpos, sigpos, prob
 
+    # ---- asynchronous batches (dyn_align_submit / dyn_align_wait) -------------------------------------------------
+    def submit_packed(self, signal_ptr: int, sig_off, seq_ptr: int, seq_off, calc_probabilities: bool = True, keep=None):
+        """Start a batch of HOST-resident reads (float32 samples at ``signal_ptr``, ASCII bases at ``seq_ptr``) on one of
+        the handle's two lanes and return a job; ``wait(job)`` returns what ``align_packed`` returns.  With two jobs in
+        flight the copies and the result fan-out of neighbouring batches overlap the kernels.  ``keep``: any object that
+        owns the input memory (kept alive until the job is waited for)."""
+        sig_off = np.ascontiguousarray(sig_off, dtype=np.uint64)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        n = sig_off.size - 1
+        res = (ReadResult * max(n, 1))()
+        nseg = int(self._lib.dyn_count_segments(self._h, seq_off.ctypes.data_as(u64p), n))
+        seqpos = np.empty(max(nseg, 1), dtype=np.uint64)
+        sigpos = np.empty(max(nseg, 1), dtype=np.uint64)
+        prob = np.empty(max(nseg, 1), dtype=np.float64)
+        ticket = self._lib.dyn_align_submit(self._h, C.c_void_p(signal_ptr), sig_off.ctypes.data_as(u64p), C.c_void_p(seq_ptr),
+                                            seq_off.ctypes.data_as(u64p), n, int(calc_probabilities), res,
+                                            seqpos.ctypes.data_as(u64p), sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p))
+        if ticket < 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        return {"ticket": ticket, "out": (res, seqpos, sigpos, prob), "keep": (keep, sig_off, seq_off)}
+
+    def wait(self, job):
+        rc = self._lib.dyn_align_wait(self._h, job["ticket"])
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        return job["out"]
+
+    def align_stream(self, batches, calc_probabilities: bool = True, depth: int = 2):
+        """Pipelined alignment of an iterable of (signals, sequences) batches: yields, in input order, the list that
+        ``align_batch`` would return for each batch while up to ``depth`` batches are in flight on the device."""
+        from collections import deque
+        inflight = deque()
+
+        def finish(item):
+            job, meta = item
+            res, seqpos, sigpos, prob = self.wait(job)
+            return self._unpack(meta, res, seqpos, sigpos, prob, calc_probabilities)
+        for signals, sequences in batches:
+            sig, sig_off, seq, seq_off = self._pack(signals, sequences, np.float32)
+            seqbuf = np.frombuffer(seq, dtype=np.uint8)
+            job = self.submit_packed(sig.ctypes.data, sig_off, seqbuf.ctypes.data, seq_off, calc_probabilities, keep=(sig, seq, seqbuf))
+            inflight.append((job, len(signals)))
+            if len(inflight) >= depth:
+                yield finish(inflight.popleft())
+        while inflight:
+            yield finish(inflight.popleft())
+
     # ---- front-end stages either side of the DP (SURVEY.md 8f N1, N2) ------------------------------------------
     def preprocess_batch(self, raws, shifts, scales, window: int = 3, n_sigmas: float = 3.0):
         """(raw - shift) / scale + Hampel filter (utils.py:16-43, segment.py:151-153) on the GPU; returns float32 arrays."""
@@ -246,6 +293,9 @@ class Aligner:
                 sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p))
         if rc != 0:
             raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        return self._unpack(n, res, seqpos, sigpos, prob, calc_probabilities, raise_errors)
+
+    def _unpack(self, n, res, seqpos, sigpos, prob, calc_probabilities=True, raise_errors=False):
         out = []
         for i in range(n):
             r = res[i]
@@ -382,6 +432,35 @@ class Aligner:
                 d["emission_model"] = {"mean": pm[i], "stdev": ps[i]}
             out.append(d)
         return out, {"w": w, "x": x, "xx": xx, "xi": xi}
+
+    # ---- pooled training with device-resident statistics (dyn_train_accumulate / dyn_train_mstep_device) ----------
+    def train_accumulate_packed(self, signal_ptr: int, sig_off, seq_ptr: int, seq_off, stats_ptr: int, device: bool = False):
+        """Add the sufficient statistics of a batch to the DEVICE buffer at ``stats_ptr`` (3K + 4 doubles: w, x, xx,
+        xi_m, xi_e, sum Z, reads ok).  Returns the per-read status codes (numpy int32)."""
+        sig_off = np.ascontiguousarray(sig_off, dtype=np.uint64)
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+        n = sig_off.size - 1
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        rc = self._lib.dyn_train_accumulate(self._h, C.c_void_p(signal_ptr), sig_off.ctypes.data_as(u64p), C.c_void_p(seq_ptr),
+                                            seq_off.ctypes.data_as(u64p), n, int(device), C.c_void_p(stats_ptr),
+                                            C.c_void_p(status.ctypes.data))
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        return status[:n]
+
+    def train_accumulate(self, signals, sequences, stats_ptr: int):
+        sig, sig_off, seq, seq_off = self._pack(signals, sequences, np.float32)
+        seqbuf = np.frombuffer(seq, dtype=np.uint8)
+        return self.train_accumulate_packed(sig.ctypes.data, sig_off, seqbuf.ctypes.data, seq_off, stats_ptr, device=False)
+
+    def mstep_device(self, stats_ptr: int) -> dict:
+        """M-step (NT:519-535, 703-722) on the pooled statistics at ``stats_ptr`` (device); the result becomes this
+        handle's model.  Returns the re-estimated transitions."""
+        t = np.zeros(3)
+        rc = self._lib.dyn_train_mstep_device(self._h, C.c_void_p(stats_ptr), t.ctypes.data_as(f64p))
+        if rc != 0:
+            raise RuntimeError(self._lib.dyn_last_error(self._h).decode())
+        return {"m1": float(t[0]), "e1": float(t[1]), "e2": float(t[2])}
 
     def train(self, signal, sequence: str, as_dicts: bool = True) -> dict:
         """aligner_bindings.cpp:149-163 -> NTAligner::train (NT_aligner_api.cpp:567-639).  ``emission_model`` is the

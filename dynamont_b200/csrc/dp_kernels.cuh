@@ -864,10 +864,41 @@ DYN_DEV void rank_select(float v, uint32_t d, uint32_t k, int lane, float& kth, 
 
 // the same for d <= 32*NV non-negative values held in registers (value i in lane i % 32, slot i / 32; unused slots hold
 // a value above every real one): bisection on the bit pattern, one vote per slot and step.  prev = (k-1)-th smallest.
+DYN_DEV uint32_t warp_min_u32(uint32_t v, int lane)
+{
+#ifndef DYN_HOST_EMU
+	(void)lane;
+	return __reduce_min_sync(FULL, v);
+#else
+	for (int o = 16; o; o >>= 1) v = min(v, (uint32_t)__shfl_sync(FULL, (int)v, (lane + o) & 31));
+	return v;
+#endif
+}
+DYN_DEV uint32_t warp_max_u32(uint32_t v, int lane)
+{
+#ifndef DYN_HOST_EMU
+	(void)lane;
+	return __reduce_max_sync(FULL, v);
+#else
+	for (int o = 16; o; o >>= 1) v = max(v, (uint32_t)__shfl_sync(FULL, (int)v, (lane + o) & 31));
+	return v;
+#endif
+}
+
 template <int NV>
 DYN_DEV void reg_select(const float (&v)[NV], uint32_t k, int lane, float& kth, float& prev)
 {
-	uint32_t lo = 0u, hi = 0x7f800000u;
+	// bisection on the bit pattern, started from the smallest / largest real value (unused slots hold PAD = 3e38): the
+	// path posteriors of a dwell mostly lie within a few percent of each other, which halves the number of steps
+	uint32_t mn = 0x7f800000u, mx = 0u;
+#pragma unroll
+	for (int q = 0; q < NV; ++q)
+	{
+		const uint32_t bits = __float_as_uint(v[q]);
+		mn = min(mn, bits);
+		mx = max(mx, bits < 0x7f000000u ? bits : 0u);
+	}
+	uint32_t lo = warp_min_u32(mn, lane), hi = max(warp_max_u32(mx, lane), lo);
 	while (lo < hi)
 	{
 		const uint32_t midv = lo + (hi - lo) / 2;
@@ -879,17 +910,17 @@ DYN_DEV void reg_select(const float (&v)[NV], uint32_t k, int lane, float& kth, 
 	}
 	kth = __uint_as_float(lo);
 	// sorted s[k] = kth.  s[k-1] = kth when fewer than k values lie strictly below it, else the largest of those
-	uint32_t below = 0, mx = 0;
+	uint32_t below = 0, mxb = 0;
 #pragma unroll
 	for (int q = 0; q < NV; ++q)
 	{
 		const uint32_t bits = __float_as_uint(v[q]);
 		const bool lt = bits < lo;
 		below += __popc(__ballot_sync(FULL, lt));
-		mx = max(mx, lt ? bits : 0u);
+		mxb = max(mxb, lt ? bits : 0u);
 	}
-	for (int o = 16; o; o >>= 1) mx = max(mx, (uint32_t)__shfl_sync(FULL, (int)mx, (lane + o) & 31));
-	prev = (below == k && k > 0) ? __uint_as_float(mx) : kth;
+	mxb = warp_max_u32(mxb, lane);
+	prev = (below == k && k > 0) ? __uint_as_float(mxb) : kth;
 }
 
 // k-th smallest (0-based) of d non-negative floats at v[0..d) (global memory), all lanes cooperating: binary

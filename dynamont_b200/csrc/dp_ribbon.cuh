@@ -496,7 +496,7 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 		const bool hot = !(lmax <= thr);
 		const unsigned hm = __ballot_sync(FULL, hot);
 		const uint32_t pos = rs.n + __popc(hm & ((1u << lane) - 1u));
-		if (hot && pos < rs.cap)
+		if (hot)  // room for a whole group of rows is checked once per group (forward_pass)
 		{
 			float tmp[RC::RECF];
 #pragma unroll
@@ -524,9 +524,7 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 #pragma unroll
 			for (int q = 0; q < RC::HDRW / 4; ++q) dst[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
 		}
-		const uint32_t nn = rs.n + __popc(hm);
-		rs.overflow = rs.overflow || (nn > rs.cap);
-		rs.n = min(nn, rs.cap);
+		rs.n += __popc(hm);
 	}
 	else
 	{
@@ -647,6 +645,13 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	for (int g = 0; g <= gl; ++g)
 	{
 		const int nr = (g < gl) ? 8 : S - 8 * gl;  // samples of this group
+		if (MODE == 1 && rs.n + 9u * 32u > rs.cap)
+		{
+			// not enough room for the records this group can produce at most (pathological record density)
+			rs.overflow = true;
+			fault = true;
+			break;
+		}
 		const float xg = x8;
 		const int midn = mid_next;
 		// ---- step a: recompute the backward rows 8g+nr .. 8g of this group into shared memory, scaled by the group's

@@ -45,7 +45,7 @@ using namespace dyn;
 struct Rt
 {
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int device = 0;
 	int sms = 148;
 	size_t smem_optin = 0;
@@ -111,6 +111,9 @@ struct Rt
 		return f;
 	}
 	void mark(int i) { CK_CUDA(cudaEventRecord(ev[i], stream)); }
+	void mark_on(int i, const Rt& other) { CK_CUDA(cudaEventRecord(ev[i], other.stream)); }  // my event, recorded on other's stream
+	void wait_on(const Rt& other, int i) { CK_CUDA(cudaStreamWaitEvent(other.stream, ev[i], 0)); }  // other's stream waits for my event
+	void wait_self(int i) { CK_CUDA(cudaStreamWaitEvent(stream, ev[i], 0)); }
 	double elapsed(int a, int b)
 	{
 		float ms = 0;
@@ -126,7 +129,7 @@ struct Rt
 	int sms = 2;
 	bool async_alloc = false;
 	size_t smem_optin = 227 * 1024;
-	double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	double tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 	void init(int) {}
 	void use_stream(void*) {}
 	void fini() {}
@@ -142,6 +145,9 @@ struct Rt
 	void sync() {}
 	size_t free_bytes() { return (size_t)4 << 30; }
 	void mark(int i) { tm[i] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	void mark_on(int i, const Rt&) { mark(i); }
+	void wait_on(const Rt&, int) {}
+	void wait_self(int) {}
 	double elapsed(int a, int b) { return tm[b] - tm[a]; }
 };
 #endif
@@ -201,6 +207,8 @@ struct EncodeArgs
 	PosConst* pc;
 	int32_t* kmers;
 	uint32_t* bad_pos;
+	ReadOut* out;      // zeroed here
+	uint32_t* queue;   // work counters of the DP kernels, zeroed here
 };
 
 DYN_DEV int base_digit(unsigned char ch)
@@ -223,6 +231,14 @@ DYN_DEV int base_digit(unsigned char ch)
 DYN_DEV void encode_read(const EncodeArgs& a, uint32_t r, int lane)
 {
 	ReadDesc rd = a.reads[r];
+	if (lane == 0)
+	{
+		ReadOut o;
+		o.Z = 0.0; o.dZ = 0.0; o.nrec = 0; o.status = 0; o.xi_m = 0.0; o.xi_e = 0.0;
+		a.out[r] = o;
+		a.bad_pos[r] = 0xffffffffu;
+		if (r == 0) a.queue[0] = 0u;
+	}
 	if (rd.status != ST_OK) return;
 	const char* s = a.seq + a.seq_off[r];
 	const uint32_t Kc = rd.N - 1;
@@ -490,6 +506,70 @@ void launch_align(Rt& rt, const BatchArgs& args, unsigned grid, int mode, bool l
 	else launch_align_t<CFG, MINB_FB, false>(rt, args, grid, mode);
 }
 
+// pooled training on device-resident statistics: stats[3K + 4] = w[K], x[K], xx[K], xi_m, xi_e, sum Z, reads ok
+struct SumOutArgs
+{
+	const ReadOut* out;
+	uint32_t n_reads;
+	double* tail;  // stats + 3K
+};
+
+DYN_DEV void sum_out_lane(const SumOutArgs& a, uint32_t first, uint32_t step, int lane)
+{
+	double xm = 0.0, xe = 0.0, z = 0.0, ok = 0.0;
+	for (uint32_t r = first + lane; r < a.n_reads; r += step)
+	{
+		const ReadOut o = a.out[r];
+		if (o.status != ST_OK) continue;
+		xm += o.xi_m;
+		xe += o.xi_e;
+		z += o.Z;
+		ok += 1.0;
+	}
+	for (int off = 16; off; off >>= 1)
+	{
+		xm += shfl_f64(xm, (lane + off) & 31);
+		xe += shfl_f64(xe, (lane + off) & 31);
+		z += shfl_f64(z, (lane + off) & 31);
+		ok += shfl_f64(ok, (lane + off) & 31);
+	}
+	if (lane == 0 && ok > 0.0)
+	{
+		atomicAdd(&a.tail[0], xm);
+		atomicAdd(&a.tail[1], xe);
+		atomicAdd(&a.tail[2], z);
+		atomicAdd(&a.tail[3], ok);
+	}
+}
+
+// M-step of NT_aligner_api.cpp:519-535 on pooled statistics, one thread per kmer: kmers without weight keep the model
+struct MStepArgs
+{
+	const double* stats;
+	uint64_t K;
+	double* mean;   // in: old model, out: new model
+	double* stdev;
+};
+
+DYN_DEV void mstep_kmer(const MStepArgs& a, uint64_t q)
+{
+	const double w = a.stats[q];
+	if (!(w > 0.0)) return;
+	const double mu = a.stats[a.K + q] / w;
+	double var = a.stats[2 * a.K + q] / w - mu * mu;
+	if (var < 1e-12) var = 1e-12;
+	a.mean[q] = mu;
+	a.stdev[q] = sqrt(var);
+}
+
+#ifndef DYN_HOST_EMU
+__global__ void __launch_bounds__(32) k_sum_out(SumOutArgs a) { sum_out_lane(a, blockIdx.x * 32u, gridDim.x * 32u, threadIdx.x); }
+__global__ void k_mstep(MStepArgs a)
+{
+	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < a.K; q += (uint64_t)gridDim.x * blockDim.x) mstep_kmer(a, q);
+}
+#endif
+
 void launch_fold(Rt& rt, const FoldArgs& a)
 {
 	if (!a.n_reads) return;
@@ -514,10 +594,13 @@ struct DevBuf
 	{
 		if (n > cap)
 		{
+			const bool first = (cap == 0);
 			if (p) rt.dfree(p);
 			p = nullptr;
 			cap = 0;
-			const size_t want = rt.async_alloc ? n + n / 2 : n;  // worker pools see varying sizes: grow with slack
+			// growing costs a cudaFree + cudaMalloc, which synchronise the whole device (and stall the other lane's running
+			// kernel): after the first allocation grow with slack so that batches of varying size settle quickly
+			const size_t want = rt.async_alloc ? n + n / 2 : (first ? n : n + n / 8);
 			p = rt.dmalloc(want);
 			cap = want;
 		}
@@ -639,6 +722,7 @@ struct dyn_aligner
 	int rib_guard = 40;        // the window's edge lanes must stay this many bits below the row maximum
 	double thr_rib = -16.0;    // log2 of the posterior above which a lane is recorded (unrecorded path cells count as 0)
 	double rib_recs_per_row = 4.0;
+	int rib_bps = 0;           // resident CTAs (of 4 warps) per SM of the ribbon kernels; 0: the build's default
 	uint64_t n_ribbon = 0;     // reads of the last batch the ribbon kernels were given ...
 	uint64_t n_rib_fault = 0;  // ... and how many of them they handed on to the full-band kernels
 	double ribbon_ms = 0.0;
@@ -648,8 +732,51 @@ struct dyn_aligner
 	DevBuf d_table, d_sig, d_seq, d_seqoff, d_desc, d_order, d_pc, d_kmers, d_bad, d_out, d_sigpos, d_prob, d_scratch,
 		d_slots, d_queue, d_rw, d_rx, d_rxx, d_sw, d_sx, d_sxx;
 	HostBuf h_sigpos, h_prob;  // pinned staging of a batch's segment borders / probabilities
+	// pinned bump arena for the small per-call tables (descriptors, orders, slot tables, per-read outputs).  Copies from / to
+	// pageable memory are staged by the driver in a way that waits for kernels running on OTHER streams (measured: a
+	// 1 MB pageable D2H issued next to another lane's ribbon kernel returned when that kernel ended, 300 ms later), which
+	// serialised the lanes; everything a batch call copies in steady state goes through pinned memory instead.
+	HostBuf h_arena;
+	size_t arena_off = 0;
+	void* stage(size_t bytes)
+	{
+		const size_t at = (arena_off + 255) / 256 * 256;
+		if (at + bytes > h_arena.cap) throw std::runtime_error("dynamont_b200: pinned staging arena exhausted");
+		arena_off = at + bytes;
+		return (unsigned char*)h_arena.p + at;
+	}
+	void h2d_staged(void* d, const void* h, size_t bytes)
+	{
+		if (!bytes) return;
+		void* st = stage(bytes);
+		std::memcpy(st, h, bytes);
+		rt.h2d(d, st, bytes);
+	}
 	bool table_dirty = true;
 	double timing[3] = {0, 0, 0};
+	double* ext_stats = nullptr;  // dyn_train_accumulate: caller-owned device buffer [3K + 4] the statistics are added to
+	// asynchronous entry points (dyn_align_submit / dyn_align_wait): calls alternate between LANES child handles on the
+	// same device, each with its own stream and buffers, so that the host-to-device copy of call i+1 and the result
+	// copy + fan-out of call i-1 overlap the kernels of call i
+	static constexpr int LANES = 2;
+	dyn_aligner* lane[LANES] = {nullptr, nullptr};
+	// The lanes run their ribbon kernels on the ROOT handle's stream and in the root's scratch: kernels of successive
+	// batches execute one after the other anyway (each fills the GPU), so one scratch pool — the largest allocation by
+	// far, tens of GB — serves all of them.  compute_mu orders "size the pool, build the slot table, enqueue the kernel".
+	dyn_aligner* root = nullptr;  // nullptr: this handle is a root
+	std::mutex compute_mu;
+	DevBuf d_rib_scratch;
+	std::string model_path_, pore_, mode_;
+	int device_ = -1;
+	struct Job
+	{
+		std::thread th;
+		int rc = 0;
+		bool joined = false;
+	};
+	std::mutex jobs_mu;
+	std::vector<Job*> jobs;
+	std::vector<std::pair<std::string, double>> options;  // replayed on the lanes
 
 	void upload_table();
 };
@@ -799,6 +926,12 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	res.desc.assign(n, ReadDesc{});
 	A.timing[0] = A.timing[1] = A.timing[2] = 0.0;
 	if (n == 0) return;
+	ReadOut* h_out_stage = nullptr;  // pinned landing zone of the per-read outputs
+	// the previous call has synchronised its stream: the arena is free
+	A.h_arena.get(rt, (size_t)n * (sizeof(ReadDesc) + 4 * 6 + 8 + 2 * sizeof(ReadOut) + 8) + ((size_t)8 << 20));
+	A.arena_off = 0;
+	h_out_stage = (ReadOut*)A.stage((size_t)n * sizeof(ReadOut));
+	uint32_t* h_bad_stage = (uint32_t*)A.stage((size_t)n * 4);
 
 	// ---- host: validation (aligner.cpp:145-164) and geometry (NT:240-247) ------------------------------------
 	uint64_t pc_total = 0, seg_total = 0;
@@ -881,19 +1014,16 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		d_seq = p;
 	}
 	uint64_t* d_seqoff = (uint64_t*)A.d_seqoff.get(rt, ((size_t)n + 1) * 8);
-	rt.h2d(d_seqoff, io.seq_off, ((size_t)n + 1) * 8);
+	A.h2d_staged(d_seqoff, io.seq_off, ((size_t)n + 1) * 8);
 	ReadDesc* d_desc = (ReadDesc*)A.d_desc.get(rt, (size_t)n * sizeof(ReadDesc));
-	rt.h2d(d_desc, res.desc.data(), (size_t)n * sizeof(ReadDesc));
+	A.h2d_staged(d_desc, res.desc.data(), (size_t)n * sizeof(ReadDesc));
 	uint32_t* d_order = (uint32_t*)A.d_order.get(rt, order.size() * 4);
-	rt.h2d(d_order, order.data(), order.size() * 4);
+	A.h2d_staged(d_order, order.data(), order.size() * 4);
 	PosConst* d_pc = (PosConst*)A.d_pc.get(rt, pc_total * sizeof(PosConst));
 	int32_t* d_kmers = (int32_t*)A.d_kmers.get(rt, pc_total * 4);
 	uint32_t* d_bad = (uint32_t*)A.d_bad.get(rt, (size_t)n * 4);
-	rt.fill_ff(d_bad, (size_t)n * 4);
 	ReadOut* d_out = (ReadOut*)A.d_out.get(rt, (size_t)n * sizeof(ReadOut));
-	rt.zero(d_out, (size_t)n * sizeof(ReadOut));
 	uint32_t* d_queue = (uint32_t*)A.d_queue.get(rt, 64);
-	rt.zero(d_queue, 64);
 	uint32_t* d_sigpos = nullptr;
 	double* d_prob = nullptr;
 	if (mode == 1)
@@ -906,6 +1036,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	EncodeArgs ea;
 	ea.reads = d_desc; ea.n_reads = n; ea.seq = d_seq; ea.seq_off = d_seqoff; ea.k = A.k;
 	ea.table = (const PosConst*)A.d_table.p; ea.pc = d_pc; ea.kmers = d_kmers; ea.bad_pos = d_bad;
+	ea.out = d_out; ea.queue = d_queue;
 	rt.mark(0);
 	launch_encode(rt, ea);
 	rt.mark(1);
@@ -941,12 +1072,22 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		rt.zero(ba.read_w, pc_total * 8);
 		rt.zero(ba.read_x, pc_total * 8);
 		rt.zero(ba.read_xx, pc_total * 8);
-		ba.stat_w = (double*)A.d_sw.get(rt, A.K * 8);
-		ba.stat_x = (double*)A.d_sx.get(rt, A.K * 8);
-		ba.stat_xx = (double*)A.d_sxx.get(rt, A.K * 8);
-		rt.zero(ba.stat_w, A.K * 8);
-		rt.zero(ba.stat_x, A.K * 8);
-		rt.zero(ba.stat_xx, A.K * 8);
+		if (A.ext_stats)
+		{
+			// pooled statistics stay on the device, in the caller's buffer (accumulated, not zeroed)
+			ba.stat_w = A.ext_stats;
+			ba.stat_x = A.ext_stats + A.K;
+			ba.stat_xx = A.ext_stats + 2 * A.K;
+		}
+		else
+		{
+			ba.stat_w = (double*)A.d_sw.get(rt, A.K * 8);
+			ba.stat_x = (double*)A.d_sx.get(rt, A.K * 8);
+			ba.stat_xx = (double*)A.d_sxx.get(rt, A.K * 8);
+			rt.zero(ba.stat_w, A.K * 8);
+			rt.zero(ba.stat_x, A.K * 8);
+			rt.zero(ba.stat_xx, A.K * 8);
+		}
 	}
 	A.n_fallback = 0;
 	A.n_retry_lin = 0;
@@ -959,7 +1100,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	// every read whose reference band leaves room for the window; what they cannot represent (ST_LIN_FAULT) and the
 	// short reads go on to the full-band kernels below
 	rib::Geometry rg;
-	if (A.arith == 0 && A.ribbon > 0 && rib::geometry(A.ribbon, rg))
+	if (A.arith == 0 && A.ribbon > 0 && rib::geometry(A.ribbon, A.rib_bps, rg))
 	{
 		std::vector<uint32_t> rorder, rest;
 		uint32_t maxTr = 0;
@@ -984,27 +1125,37 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				size_t o = 0;
 				o_sch = o; o = align_up(o + nck * 8, 256);
 				o_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
-				o_ob = o; o = align_up(o + nck * 64 * 4, 256);
+				o_ob = o; o = align_up(o + nck * 32 * 4, 256);
 				if (mode == 1)
 				{
-					rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64;
+					rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64 + 9 * 32;
 					o_hdr = o; o = align_up(o + ((size_t)maxTr + 32) * rg.hdrw * 4, 256);
 					o_rec = o; o = align_up(o + rcap * rg.recf * 4, 256);
 					o_pp = o; o = align_up(o + ((size_t)maxTr + 32) * 4, 256);
 				}
 				per_slot = o;
-				const size_t budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
+				const size_t budget = (size_t)((double)(rt.free_bytes() + (A.root ? A.root : &A)->d_rib_scratch.cap) * A.mem_fraction);
 				const size_t fit = std::max<size_t>(1, budget / per_slot);
 				if (tm.on)
 					fprintf(stderr, "[dyn timing] ribbon scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit\n",
 						per_slot / 1048576.0, gridw, budget / 1073741824.0, fit);
 				gridw = (unsigned)std::min<size_t>(gridw, fit);
 			}
+			{
+			dyn_aligner& R = A.root ? *A.root : A;
+			std::lock_guard<std::mutex> cl(R.compute_mu);
 			std::vector<SlotScratch> slots(gridw);
 			memset(slots.data(), 0, slots.size() * sizeof(SlotScratch));
 			if (mode != 0)
 			{
-				unsigned char* base = (unsigned char*)A.d_scratch.get(rt, per_slot * gridw);
+				if (per_slot * gridw > R.d_rib_scratch.cap)
+				{
+					// growing the shared pool: nothing enqueued may still use the old one (holding compute_mu keeps the
+					// other lanes from enqueueing; cudaFree synchronises the device)
+					R.rt.sync();
+					rt.sync();
+				}
+				unsigned char* base = (unsigned char*)R.d_rib_scratch.get(R.rt, per_slot * gridw);
 				for (unsigned q = 0; q < gridw; ++q)
 				{
 					unsigned char* b = base + per_slot * q;
@@ -1020,25 +1171,35 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				}
 			}
 			SlotScratch* d_slots = (SlotScratch*)A.d_slots.get(rt, (size_t)gridw * sizeof(SlotScratch));
-			rt.h2d(d_slots, slots.data(), (size_t)gridw * sizeof(SlotScratch));
-			rt.h2d(d_order, rorder.data(), rorder.size() * 4);
+			A.h2d_staged(d_slots, slots.data(), (size_t)gridw * sizeof(SlotScratch));
+			A.h2d_staged(d_order, rorder.data(), rorder.size() * 4);
 			BatchArgs rb = ba;
 			rb.n_reads = (uint32_t)rorder.size();
 			rb.slots = d_slots;
 			rb.n_slots = gridw;
 			rb.rec_cap = rcap;
 			tm.lap("enqueue_ribbon");
-			rt.mark(6);
+			// inputs ready on this handle's stream -> kernel on the root's stream -> results back on this handle's stream
+			const bool cross = (&R != &A);
+			if (cross)
+			{
+				rt.mark(8);
+				rt.wait_on(R.rt, 8);
+			}
+			rt.mark_on(6, R.rt);
 #ifndef DYN_HOST_EMU
-			const int le = rib::launch((void*)rt.stream, rb, gridw, mode, A.ribbon);
+			const int le = rib::launch((void*)R.rt.stream, rb, gridw, mode, A.ribbon, A.rib_bps);
 			if (le != 0) throw std::runtime_error(std::string("CUDA error launching the ribbon kernel: ") + cudaGetErrorString((cudaError_t)le));
 #else
-			rib::launch(nullptr, rb, gridw, mode, A.ribbon);
+			rib::launch(nullptr, rb, gridw, mode, A.ribbon, A.rib_bps);
 #endif
-			rt.mark(7);
+			rt.mark_on(7, R.rt);
+			if (cross) rt.wait_self(7);
 			++launches;
-			rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
+			}
+			rt.d2h(h_out_stage, d_out, (size_t)n * sizeof(ReadOut));
 			rt.sync();
+			std::memcpy(res.out.data(), h_out_stage, (size_t)n * sizeof(ReadOut));
 			tm.lap("ribbon_kernel");
 			A.ribbon_ms = rt.elapsed(6, 7);
 			A.n_ribbon = rorder.size();
@@ -1062,8 +1223,11 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			order.swap(rest);
 			maxT = 0;
 			for (uint32_t r : order) maxT = std::max(maxT, res.desc[r].S + 1);
-			if (!order.empty()) rt.h2d(d_order, order.data(), order.size() * 4);
-			rt.zero(d_queue, 64);
+			if (!order.empty())
+			{
+				A.h2d_staged(d_order, order.data(), order.size() * 4);
+				rt.zero(d_queue, 64);
+			}
 			ba.n_reads = (uint32_t)order.size();
 		}
 	}
@@ -1118,7 +1282,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		}
 	}
 	SlotScratch* d_slots = (SlotScratch*)A.d_slots.get(rt, (size_t)grid * sizeof(SlotScratch));
-	rt.h2d(d_slots, slots.data(), (size_t)grid * sizeof(SlotScratch));
+	A.h2d_staged(d_slots, slots.data(), (size_t)grid * sizeof(SlotScratch));
 	ba.slots = d_slots;
 	ba.n_slots = grid;
 	ba.rec_cap = rec_cap;
@@ -1133,8 +1297,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	if (lin)
 	{
 		// reads the FP32 linear arithmetic could not represent (ST_LIN_FAULT) are re-run in the log2 domain
-		rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
+		rt.d2h(h_out_stage, d_out, (size_t)n * sizeof(ReadOut));
 		rt.sync();
+		std::memcpy(res.out.data(), h_out_stage, (size_t)n * sizeof(ReadOut));
 		tm.lap("kernels");
 		std::vector<uint32_t> again;
 		for (uint32_t r : order)
@@ -1145,14 +1310,15 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			{
 				// second tier: the linear-domain kernels that renormalise twice as often
 				A.n_retry_lin = again.size();
-				rt.h2d(d_order, again.data(), again.size() * 4);
+				A.h2d_staged(d_order, again.data(), again.size() * 4);
 				rt.zero(d_queue, 64);
 				ba.n_reads = (uint32_t)again.size();
 				rt.mark(4);
 				launch_align_t<CFGLIN2, MINB_FB, true>(rt, ba, (unsigned)std::min<size_t>(grid, again.size()), mode);
 				rt.mark(5);
-				rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
+				rt.d2h(h_out_stage, d_out, (size_t)n * sizeof(ReadOut));
 				rt.sync();
+				std::memcpy(res.out.data(), h_out_stage, (size_t)n * sizeof(ReadOut));
 				fallback_ms += rt.elapsed(4, 5);
 				++launches;
 				std::vector<uint32_t> still;
@@ -1164,7 +1330,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		if (!again.empty())
 		{
 			A.n_fallback = again.size();
-			rt.h2d(d_order, again.data(), again.size() * 4);
+			A.h2d_staged(d_order, again.data(), again.size() * 4);
 			rt.zero(d_queue, 64);
 			ba.n_reads = (uint32_t)again.size();
 			rt.mark(4);
@@ -1186,11 +1352,23 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		fa.stat_w = ba.stat_w; fa.stat_x = ba.stat_x; fa.stat_xx = ba.stat_xx;
 		launch_fold(rt, fa);
 		++launches;
+		if (A.ext_stats)
+		{
+			SumOutArgs sa;
+			sa.out = d_out; sa.n_reads = n; sa.tail = A.ext_stats + 3 * A.K;
+#ifndef DYN_HOST_EMU
+			k_sum_out<<<std::min<unsigned>((n + 31) / 32, 256u), 32, 0, rt.stream>>>(sa);
+			CK_CUDA(cudaGetLastError());
+#else
+			simt::launch(1, 0, [&]() { sum_out_lane(sa, 0u, 32u, threadIdx.x); });
+#endif
+			++launches;
+		}
 	}
 
 	// ---- results ---------------------------------------------------------------------------------------------------
-	rt.d2h(res.out.data(), d_out, (size_t)n * sizeof(ReadOut));
-	rt.d2h(res.bad_pos.data(), d_bad, (size_t)n * 4);
+	rt.d2h(h_out_stage, d_out, (size_t)n * sizeof(ReadOut));
+	rt.d2h(h_bad_stage, d_bad, (size_t)n * 4);
 	if (mode == 1 && seg_total)
 	{
 		rt.d2h(sigpos_h, d_sigpos, seg_total * 4);
@@ -1209,6 +1387,8 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		rt.d2h(per_read_w + 2 * pc_total, ba.read_xx, pc_total * 8);
 	}
 	rt.sync();
+	std::memcpy(res.out.data(), h_out_stage, (size_t)n * sizeof(ReadOut));
+	std::memcpy(res.bad_pos.data(), h_bad_stage, (size_t)n * 4);
 	tm.lap("results_d2h");
 	A.timing[0] = rt.elapsed(0, 1);
 	A.timing[1] = A.ribbon_ms + main_ms + fallback_ms;
@@ -1315,6 +1495,9 @@ dyn_aligner* dyn_create(const char* model_path, const char* pore, const char* mo
 		}
 		A = new dyn_aligner();
 		A->ntk = ntk;
+		A->model_path_ = model_path;
+		A->pore_ = pore;
+		A->mode_ = m;
 		{
 			// NTKAligner::initializeTransitions (NTK_aligner_api.cpp:35-104)
 			static const double RNA002_T[14] = {0.019326040280789637, 0.19725479693713352, 0.1979799841413514,
@@ -1340,6 +1523,7 @@ dyn_aligner* dyn_create(const char* model_path, const char* pore, const char* mo
 		A->trans[2] = std::log(pi->e2);
 		load_model(*A, model_path);
 		A->rt.init(device);
+		A->device_ = A->rt.device;
 		A->upload_table();
 		return A;
 	}
@@ -1358,12 +1542,23 @@ dyn_aligner* dyn_create(const char* model_path, const char* pore, const char* mo
 void dyn_destroy(dyn_aligner* A)
 {
 	if (!A) return;
+	for (dyn_aligner::Job* j : A->jobs)
+	{
+		if (!j->joined && j->th.joinable()) j->th.join();
+		delete j;
+	}
+	A->jobs.clear();
+	for (dyn_aligner*& l : A->lane)
+	{
+		if (l) dyn_destroy(l);
+		l = nullptr;
+	}
 	try
 	{
 		A->rt.bind();
 		for (DevBuf* b : {&A->d_table, &A->d_sig, &A->d_seq, &A->d_seqoff, &A->d_desc, &A->d_order, &A->d_pc, &A->d_kmers,
 				 &A->d_bad, &A->d_out, &A->d_sigpos, &A->d_prob, &A->d_scratch, &A->d_slots, &A->d_queue, &A->d_rw,
-				 &A->d_rx, &A->d_rxx, &A->d_sw, &A->d_sx, &A->d_sxx})
+				 &A->d_rx, &A->d_rxx, &A->d_sw, &A->d_sx, &A->d_sxx, &A->d_rib_scratch})
 			b->release(A->rt);
 		A->h_sigpos.release(A->rt);
 		A->h_prob.release(A->rt);
@@ -1391,6 +1586,8 @@ int dyn_set_model(dyn_aligner* A, const double* mean, const double* stdev)
 	A->mean.assign(mean, mean + A->K);
 	A->stdev.assign(stdev, stdev + A->K);
 	A->table_dirty = true;
+	for (dyn_aligner* l : A->lane)
+		if (l) dyn_set_model(l, mean, stdev);
 	return 0;
 }
 
@@ -1607,6 +1804,70 @@ int dyn_align_batch_device(dyn_aligner* A, const float* d_signal, const uint64_t
 	return align_common(A, io, calc_probabilities, results, sequence_positions, signal_positions, probabilities);
 }
 
+// ---- asynchronous batches ---------------------------------------------------------------------------------------
+static dyn_aligner* lane_of(dyn_aligner* A, int64_t ticket)
+{
+	const int li = (int)(ticket % dyn_aligner::LANES);
+	if (!A->lane[li])
+	{
+		char err[512];
+		int kind = 0;
+		dyn_aligner* l = dyn_create(A->model_path_.c_str(), A->pore_.c_str(), A->mode_.c_str(), 1, A->band, A->device_, err, sizeof err, &kind);
+		if (!l) throw std::runtime_error(std::string("dyn_align_submit: cannot create lane: ") + err);
+		dyn_set_model(l, A->mean.data(), A->stdev.data());
+		for (const auto& kv : A->options) dyn_set_option(l, kv.first.c_str(), kv.second);
+		l->root = A;
+		A->lane[li] = l;
+	}
+	return A->lane[li];
+}
+
+int64_t dyn_align_submit(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
+	uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
+	uint64_t* signal_positions, double* probabilities)
+{
+	try
+	{
+		std::lock_guard<std::mutex> g(A->jobs_mu);
+		const int64_t ticket = (int64_t)A->jobs.size();
+		dyn_aligner* l = lane_of(A, ticket);
+		dyn_aligner::Job* j = new dyn_aligner::Job();
+		A->jobs.push_back(j);
+		// the lane's own mutex serialises the calls that share it; the caller's buffers must stay valid until dyn_align_wait
+		j->th = std::thread([=]() {
+			j->rc = dyn_align_batch(l, signal, sig_off, seq, seq_off, n_reads, calc_probabilities, results, sequence_positions,
+				signal_positions, probabilities);
+		});
+		return ticket;
+	}
+	catch (const std::exception& e)
+	{
+		A->last_error = e.what();
+		return -1;
+	}
+}
+
+int dyn_align_wait(dyn_aligner* A, int64_t ticket)
+{
+	dyn_aligner::Job* j = nullptr;
+	{
+		std::lock_guard<std::mutex> g(A->jobs_mu);
+		if (ticket < 0 || ticket >= (int64_t)A->jobs.size()) return -1;
+		j = A->jobs[(size_t)ticket];
+	}
+	if (!j->joined)
+	{
+		if (j->th.joinable()) j->th.join();
+		j->joined = true;
+	}
+	if (j->rc != 0)
+	{
+		dyn_aligner* l = A->lane[ticket % dyn_aligner::LANES];
+		A->last_error = l ? l->last_error : "dyn_align_wait: job failed";
+	}
+	return j->rc;
+}
+
 int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq,
 	const uint64_t* seq_off, uint32_t n_reads, dyn_train_result* results, double* pooled_w, double* pooled_x,
 	double* pooled_xx, double* pooled_xi, double* per_read_mean, double* per_read_stdev)
@@ -1731,6 +1992,116 @@ int dyn_train_batch(dyn_aligner* A, const float* signal, const uint64_t* sig_off
 					}
 				}
 			}
+		}
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		A->last_error = e.what();
+		return -1;
+	}
+}
+
+int dyn_train_accumulate(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
+	uint32_t n_reads, int inputs_on_device, double* d_stats, int32_t* status)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	try
+	{
+		if (A->ntk) throw std::runtime_error(NTK_PARTIAL);
+		BatchIO io;
+		if (inputs_on_device) { io.sig_dev = signal; io.seq_dev = seq; }
+		else { io.sig_host = signal; io.seq_host = seq; }
+		io.sig_off = sig_off; io.seq_off = seq_off; io.n = n_reads;
+		struct Guard
+		{
+			dyn_aligner* A;
+			double recs;
+			~Guard() { A->ext_stats = nullptr; A->recs_per_row = recs; }
+		} guard{A, A->recs_per_row};
+		A->ext_stats = d_stats;
+		BatchResult res;
+		run_batch(*A, io, 2, res, nullptr, nullptr, nullptr, nullptr);
+		// a read whose sparse records overflowed (full-band kernels only) has accumulated nothing: re-run it alone
+		std::vector<uint32_t> retry;
+		for (uint32_t r = 0; r < n_reads; ++r)
+			if (res.out[r].status == ST_REC_OVERFLOW) retry.push_back(r);
+		if (!retry.empty())
+		{
+			const uint64_t f0 = A->n_fallback, f1 = A->n_retry_lin, f2 = A->n_ribbon, f3 = A->n_rib_fault;
+			const double t1 = A->timing[1];
+			A->recs_per_row = 1e9;
+			for (uint32_t r : retry)
+			{
+				BatchIO sh;
+				uint64_t so0[2] = {0, sig_off[r + 1] - sig_off[r]};
+				uint64_t qo0[2] = {0, seq_off[r + 1] - seq_off[r]};
+				if (inputs_on_device) { sh.sig_dev = signal + sig_off[r]; sh.seq_dev = seq + seq_off[r]; }
+				else { sh.sig_host = signal + sig_off[r]; sh.seq_host = seq + seq_off[r]; }
+				sh.sig_off = so0; sh.seq_off = qo0; sh.n = 1;
+				BatchResult r1;
+				run_batch(*A, sh, 2, r1, nullptr, nullptr, nullptr, nullptr);
+				res.out[r] = r1.out[0];
+			}
+			A->n_fallback = f0; A->n_retry_lin = f1; A->n_ribbon = f2; A->n_rib_fault = f3;
+			A->timing[1] = t1;
+		}
+		if (status)
+			for (uint32_t r = 0; r < n_reads; ++r) status[r] = res.out[r].status == ST_REC_OVERFLOW ? (int32_t)ST_INTERNAL : res.out[r].status;
+		return 0;
+	}
+	catch (const std::exception& e)
+	{
+		A->last_error = e.what();
+		return -1;
+	}
+}
+
+int dyn_train_mstep_device(dyn_aligner* A, const double* d_stats, double* transitions3)
+{
+	std::lock_guard<std::mutex> g(A->mu);
+	try
+	{
+		Rt& rt = A->rt;
+		rt.bind();
+		const uint64_t K = A->K;
+		// persistent device buffers and pinned staging: no allocation (= device synchronisation) per iteration
+		double* d_mean = (double*)A->d_sx.get(rt, K * 8);
+		double* d_sd = (double*)A->d_sxx.get(rt, K * 8);
+		A->h_arena.get(rt, 2 * K * 8 + 4096);
+		double* h_mean = (double*)A->h_arena.p;
+		double* h_sd = h_mean + K;
+		double* h_tail = h_sd + K;
+		std::memcpy(h_mean, A->mean.data(), K * 8);
+		std::memcpy(h_sd, A->stdev.data(), K * 8);
+		rt.h2d(d_mean, h_mean, K * 8);
+		rt.h2d(d_sd, h_sd, K * 8);
+		MStepArgs ma;
+		ma.stats = d_stats; ma.K = K; ma.mean = d_mean; ma.stdev = d_sd;
+#ifndef DYN_HOST_EMU
+		k_mstep<<<(unsigned)std::min<uint64_t>((K + 255) / 256, 1024), 256, 0, rt.stream>>>(ma);
+		CK_CUDA(cudaGetLastError());
+#else
+		for (uint64_t q = 0; q < K; ++q) mstep_kmer(ma, q);
+#endif
+		double tail[4] = {0, 0, 0, 0};
+		rt.d2h(h_mean, d_mean, K * 8);
+		rt.d2h(h_sd, d_sd, K * 8);
+		rt.d2h(h_tail, d_stats + 3 * K, 32);
+		rt.sync();
+		std::memcpy(A->mean.data(), h_mean, K * 8);
+		std::memcpy(A->stdev.data(), h_sd, K * 8);
+		std::memcpy(tail, h_tail, 32);
+		A->table_dirty = true;
+		for (dyn_aligner* l : A->lane)
+			if (l) dyn_set_model(l, A->mean.data(), A->stdev.data());
+		if (transitions3)
+		{
+			// NT:703-722: normalised re-estimates of m1 and e2; e1 = exp(log 1)
+			const double norm = tail[0] + tail[1];
+			transitions3[0] = norm > 0 ? tail[0] / norm : 0.0;
+			transitions3[1] = std::exp(A->trans[1]);
+			transitions3[2] = norm > 0 ? tail[1] / norm : 0.0;
 		}
 		return 0;
 	}
@@ -2217,6 +2588,9 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 {
 	std::lock_guard<std::mutex> g(A->mu);
 	const std::string k(key);
+	A->options.emplace_back(k, value);
+	for (dyn_aligner* l : A->lane)
+		if (l) dyn_set_option(l, key, value);
 	if (k == "warps_per_sm") A->warps_per_sm = std::max(0, (int)value);
 	else if (k == "arith") A->arith = std::min(1, std::max(0, (int)value));
 	else if (k == "variant") A->variant = std::min(N_VARIANTS - 1, std::max(-1, (int)value));
@@ -2229,6 +2603,7 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	else if (k == "rib_guard") A->rib_guard = std::max(8, (int)value);
 	else if (k == "thr_rib") A->thr_rib = value;
 	else if (k == "rib_recs_per_row") A->rib_recs_per_row = value;
+	else if (k == "rib_bps") A->rib_bps = (int)value;
 	else return -1;
 	return 0;
 }

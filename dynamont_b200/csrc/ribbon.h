@@ -25,11 +25,11 @@ struct Geometry
 };
 
 // cpl: 2 or 4.  Returns false for an unsupported width.
-bool geometry(int cpl, Geometry& g);
+bool geometry(int cpl, int bps, Geometry& g);  // bps: resident CTAs per SM (0 = default)
 
 // n_warps resident warps (one scratch slot each, args.slots[0 .. n_warps)); mode 0: Z only, 1: align, 2: train.
 // Returns 0 or the cudaError_t of the launch.
-int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl);
+int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps);
 
 } // namespace rib
 } // namespace dyn

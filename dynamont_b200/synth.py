@@ -52,8 +52,10 @@ def kmer_strings(k: int):
     return ["".join(r) for r in chars]
 
 
-def make_synthetic_9mer_model(path_5mer: str, out_path: str, seed: int = 42, stdv: float = 0.15) -> str:
-    """level_mean(kmer9) = model5[kmer9[2:7]] + 0.05*N(0,1); level_stdv = 0.15 (inverse of models/9merTo5mer.py)."""
+def make_synthetic_9mer_model(path_5mer: str, out_path: str, seed: int = 42, stdv: float = 0.15, var_sd: bool = False) -> str:
+    """level_mean(kmer9) = model5[kmer9[2:7]] + 0.05*N(0,1); level_stdv = 0.15 (inverse of models/9merTo5mer.py).
+    var_sd: per-kmer level_stdv drawn uniformly from [0.10, 0.30] (the spread of the shipped trained 5-mer model) — what
+    a trained 9-mer model looks like to the kernels."""
     if os.path.exists(out_path):
         return out_path
     k5, m5, _ = read_kmer_model(path_5mer)
@@ -68,12 +70,13 @@ def make_synthetic_9mer_model(path_5mer: str, out_path: str, seed: int = 42, std
     central = (idx9 >> 4) & (4 ** 5 - 1)  # digits 2..6 of a 9-digit base-4 number
     rng = np.random.default_rng(seed)
     mean9 = lut[central] + 0.05 * rng.standard_normal(4 ** 9)
+    sd9 = rng.uniform(0.10, 0.30, 4 ** 9) if var_sd else np.full(4 ** 9, stdv)
     os.makedirs(os.path.dirname(os.path.abspath(out_path)), exist_ok=True)
     tmp = out_path + ".tmp%d" % os.getpid()
     kmers = kmer_strings(9)
     with open(tmp, "w") as fh:
         fh.write("kmer\tlevel_mean\tlevel_stdv\n")
-        fh.write("".join(f"{q}\t{float(m)}\t{stdv}\n" for q, m in zip(kmers, mean9)))
+        fh.write("".join(f"{q}\t{float(m)}\t{float(v)}\n" for q, m, v in zip(kmers, mean9, sd9)))
     os.replace(tmp, out_path)
     return out_path
 
@@ -172,6 +175,8 @@ def materialize_model(name: str, outdir: str) -> str:
         return path
     if name == "synthetic_rna004_9mer":
         return make_synthetic_9mer_model(materialize_model("rna004_5mer", outdir), path)
+    if name == "synthetic_rna004_9mer_varsd":
+        return make_synthetic_9mer_model(materialize_model("rna004_5mer", outdir), path, var_sd=True)
     with np.load(_TABLES) as z:
         mean, sd = z[name + "_mean"], z[name + "_stdv"]
     tmp = path + ".tmp%d" % os.getpid()

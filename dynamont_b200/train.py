@@ -34,6 +34,27 @@ class PooledTrainer:
         self.al = aligner
         self.rank, self.world, self.device = rank, world, device
 
+    def iteration_device(self, signals, sequences):
+        """One EM iteration with the pooled statistics resident on the device: every rank adds its shard's expected counts
+        to a float64 tensor of 3K + 4 entries on ``self.device`` (dyn_train_accumulate), ONE all-reduce sums it in place
+        (NCCL over NVLink on GPUs; the tensor never visits the host), and the M-step runs on the device on every rank
+        (dyn_train_mstep_device), which also installs the new model.  Returns (transitions, stats tensor)."""
+        import torch
+        import torch.distributed as dist
+        K = self.al.num_kmers
+        stats = torch.zeros(3 * K + 4, dtype=torch.float64, device=self.device if self.device is not None else "cpu")
+        costs = [self.al.read_cells(len(s), len(q)) for s, q in zip(signals, sequences)]
+        mine = shard_indices(costs, self.rank, self.world)
+        self.al.train_accumulate([signals[i] for i in mine], [sequences[i] for i in mine], stats.data_ptr())
+        if stats.is_cuda:
+            torch.cuda.synchronize(stats.device)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        if stats.is_cuda:
+            torch.cuda.synchronize(stats.device)
+        trans = self.al.mstep_device(stats.data_ptr())
+        return trans, stats
+
     def iteration(self, signals, sequences, update: bool = True):
         """One EM iteration over the given reads (the full set is passed on every rank; each rank processes its
         shard).  Returns (mean, stdev, transitions, stats) — identical on all ranks."""

@@ -169,6 +169,32 @@ int dyn_ntk_align_batch(dyn_aligner*, const float* signal, const uint64_t* sig_o
 	char* states, uint64_t* sequence_positions, uint64_t* signal_positions, double* probabilities, uint32_t* polish_kmers,
 	int concurrency);
 
+/* Pooled (data-parallel) Baum-Welch with the statistics resident on the device — what dynamont-train's per-batch
+ * loop (train.py:185-223) becomes when the expected counts are pooled instead of averaging per-read estimates.
+ * dyn_train_accumulate ADDS the sufficient statistics of the batch's successful reads to the caller's DEVICE buffer
+ * d_stats[3K + 4] (doubles): w[K], x[K], xx[K] (NT:510-512, native kmer order), then expected E->M and E->E transition
+ * counts (NT:641-725), sum of Z, number of successful reads.  Nothing but the per-read status (status[n_reads], host,
+ * may be NULL) returns to the host, so ranks can all-reduce d_stats in place (ncclAllReduce / torch.distributed on the
+ * device pointer).  signal / seq are host pointers, or device pointers if inputs_on_device.
+ * dyn_train_mstep_device applies the M-step (NT:519-535: mean, stdev with the 1e-12 variance floor, kmers without
+ * weight keep the model) to d_stats on the device, installs the result as the handle's model, and returns the
+ * re-estimated transitions {m1, e1, e2} (NT:703-722) in transitions3 (host, may be NULL). */
+int dyn_train_accumulate(dyn_aligner*, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
+	uint32_t n_reads, int inputs_on_device, double* d_stats, int32_t* status);
+int dyn_train_mstep_device(dyn_aligner*, const double* d_stats, double* transitions3);
+
+/* Asynchronous form of dyn_align_batch for callers that stream batches: dyn_align_submit starts the batch on one of two
+ * internal lanes (own CUDA stream and device buffers each, same device and model as the handle) and returns a ticket
+ * (>= 0; -1 on error); dyn_align_wait blocks until that batch is complete and returns what dyn_align_batch would have
+ * returned.  With two batches in flight the host-to-device copy of the next batch and the device-to-host copy + result
+ * fan-out of the previous one overlap the kernels of the current one.  All input and output buffers of a submitted
+ * batch must stay valid and untouched until its wait returns; every ticket must be waited for exactly once before
+ * dyn_destroy.  Replaces the mp.Pool fan-out of the reference front end (segment.py:296-324) for one GPU. */
+int64_t dyn_align_submit(dyn_aligner*, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
+	uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
+	uint64_t* signal_positions, double* probabilities);
+int dyn_align_wait(dyn_aligner*, int64_t ticket);
+
 /* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
  * last batch call: [0] encode/emission-constant kernel, [1] main DP kernel, [2] number of kernel launches */
 void dyn_last_timing(const dyn_aligner*, double* out3);

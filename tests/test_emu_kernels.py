@@ -195,3 +195,37 @@ def test_emulated_training_record_overflow_retry(emu_lib):
     r0 = al.align(case.signal, case.sequence, True)
     check_alignment(r0, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
 
+
+
+def test_emulated_async_lanes_match_sync_batches(emu_lib):
+    """dyn_align_submit / dyn_align_wait (two lanes sharing the root handle's ribbon scratch): same results, same order
+    as the synchronous entry point, errors included"""
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import native_model, synth_read
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    nm, ns = native_model(case.model_path, case.pore)
+    rng = np.random.default_rng(3)
+    batches = []
+    for b in range(3):
+        sigs, seqs = [], []
+        for L in (130, 60, 150):
+            s, q, _ = synth_read(rng, nm, ns, 5, L, 9)
+            sigs.append(s.astype(np.float32))
+            seqs.append(q)
+        if b == 1:
+            sigs.append(sigs[0][:10])
+            seqs.append(seqs[0])
+        batches.append((sigs, seqs))
+    al = Aligner(case.model_path, case.pore, _lib_path=emu_lib)
+    ref = [al.align_batch(s, q, True) for s, q in batches]
+    got = list(al.align_stream(batches, True, depth=2))
+    assert len(got) == len(ref)
+    for rb, gb in zip(ref, got):
+        assert len(rb) == len(gb)
+        for r, g in zip(rb, gb):
+            if isinstance(r, Exception):
+                assert isinstance(g, Exception) and str(g) == str(r)
+                continue
+            assert r["Z"] == g["Z"]
+            assert np.array_equal(r["signal_positions"], g["signal_positions"])
+            assert np.array_equal(r["probabilities"], g["probabilities"])

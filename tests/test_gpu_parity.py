@@ -191,3 +191,52 @@ def test_range_fault_reads_fall_back_to_log2_domain(aligners, models_dir):
             check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
         except RuntimeError as e:
             assert isinstance(r, RuntimeError) and str(r) == str(e)
+
+
+def test_async_lanes_match_sync_batches(aligners, models_dir):
+    """dyn_align_submit / dyn_align_wait: three batches streamed through the two lanes return exactly what the synchronous
+    entry point returns, in input order (the lanes share the root handle's ribbon scratch and stream)."""
+    from dynamont_b200.synth import materialize_model
+    path = materialize_model("rna002_5mer", models_dir)
+    al = aligners(path, "rna002")
+    batches = [_synth_batch(path, "rna002", 12, 100, 1500, 12, seed=100 + i) for i in range(3)]
+    batches[1][0].append(batches[1][0][0][:10])
+    batches[1][1].append(batches[1][1][0])
+    ref = [al.align_batch(s, q, True) for s, q in batches]
+    got = list(al.align_stream(batches, True, depth=2))
+    for rb, gb in zip(ref, got):
+        assert len(rb) == len(gb)
+        for r, g in zip(rb, gb):
+            if isinstance(r, Exception):
+                assert isinstance(g, Exception) and str(g) == str(r)
+                continue
+            assert r["Z"] == g["Z"]
+            assert np.array_equal(r["signal_positions"], g["signal_positions"])
+            assert np.array_equal(r["probabilities"], g["probabilities"])
+
+
+def test_pooled_trainer_device_statistics(aligners):
+    """dyn_train_accumulate / dyn_train_mstep_device (PooledTrainer.iteration_device, world 1): the statistics stay in a
+    CUDA tensor, are the reference's per-read expected counts (golden raw statistics of runTraining), and the device
+    M-step equals the reference's per-read M-step.  The all-reduce itself is exercised at world 2 by the gloo test and by
+    bench.py --config c5 --gpus N."""
+    import torch
+    from dynamont_b200 import Aligner
+    from dynamont_b200.train import PooledTrainer
+    case = [c for c in load_golden() if c.name == "rna002_band"][0]
+    al = Aligner(case.model_path, case.pore)
+    tr = PooledTrainer(al, 0, 1, device=torch.device("cuda", 0))
+    trans, st = tr.iteration_device([case.signal.astype(np.float32)], [case.sequence])
+    assert st.is_cuda and st.dtype == torch.float64
+    K = al.num_kmers
+    h = st.cpu().numpy()
+    km = case.train_kmers
+    heavy = case.stat_w > 1e-3
+    np.testing.assert_allclose(h[:K][km][heavy], case.stat_w[heavy], rtol=TRAIN_RTOL)
+    np.testing.assert_allclose(h[K:2 * K][km][heavy], case.stat_x[heavy], rtol=TRAIN_RTOL, atol=1e-6)
+    np.testing.assert_allclose(h[2 * K:3 * K][km][heavy], case.stat_xx[heavy], rtol=TRAIN_RTOL)
+    assert h[3 * K + 3] == 1.0 and abs(h[3 * K + 2] - case.train_Z) <= 1e-6 * abs(case.train_Z)
+    np.testing.assert_allclose([trans["m1"], trans["e1"], trans["e2"]], case.train_trans, rtol=TRAIN_RTOL)
+    mean, sd = al.model()
+    np.testing.assert_allclose(mean[km][heavy], case.train_mean[heavy], rtol=TRAIN_RTOL, atol=1e-5)
+    np.testing.assert_allclose(sd[km][heavy], case.train_stdev[heavy], rtol=TRAIN_RTOL, atol=1e-6)

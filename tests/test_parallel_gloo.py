@@ -36,6 +36,13 @@ def _worker(rank, world, port, out_dir):
     al = Aligner(path, "rna002", _lib_path=build_emu.build())
     mean, sd, trans, stats = PooledTrainer(al, rank, world).iteration(sigs, seqs)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), mean=mean, sd=sd, w=stats["w"], n=stats["n"], m1=trans["m1"])
+    # the same iteration with the statistics kept in "device" memory (the emulator's device memory is host memory) and
+    # all-reduced in place: dyn_train_accumulate -> all_reduce(tensor) -> dyn_train_mstep_device
+    al2 = Aligner(path, "rna002", _lib_path=build_emu.build())
+    trans2, st = PooledTrainer(al2, rank, world).iteration_device(sigs, seqs)
+    mean2, sd2 = al2.model()
+    K = al2.num_kmers
+    np.savez(os.path.join(out_dir, f"d{rank}.npz"), mean=mean2, sd=sd2, w=st[:K].numpy(), n=float(st[3 * K + 3]), m1=trans2["m1"])
     dist.destroy_process_group()
 
 
@@ -56,3 +63,9 @@ def test_two_ranks_agree_with_one(tmp_path):
         np.testing.assert_allclose(z["mean"], mean, rtol=1e-12)
         np.testing.assert_allclose(z["sd"], sd, rtol=1e-9)
         assert abs(z["m1"] - trans["m1"]) < 1e-12
+        d = np.load(tmp_path / f"d{r}.npz")
+        assert d["n"] == len(sigs)
+        np.testing.assert_allclose(d["w"], stats["w"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(d["mean"], mean, rtol=1e-12)
+        np.testing.assert_allclose(d["sd"], sd, rtol=1e-9)
+        assert abs(d["m1"] - trans["m1"]) < 1e-12
