@@ -549,6 +549,7 @@ def main():
         "kernel_ms": dp_ms_all, "lattice_rows_per_s": 3.0 * rows / dp_s,
         "log2_fallback_reads": int(fallbacks), "lin_retry_reads": int(lin_retries),
         "ribbon_reads": int(step_device.rib[0]), "ribbon_fault_reads": int(step_device.rib[1]),
+        "ribbon_fault_reasons": al.ribbon_fault_reasons(),
         "issue": {"source": ck.get("source"), "warp_instructions_per_lattice_row": ck.get("instr_per_row"),
                   "issue_slots_busy_pct": ck.get("issue_busy_pct"), "xu_pipe_pct": ck.get("xu_pct"),
                   "achieved_warp_instr_per_s": (ck.get("instr_per_row") * rows / dp_s) if ck.get("instr_per_row") else None,

@@ -240,6 +240,15 @@ class Aligner:
     def read_cells(self, S: int, L: int) -> int:
         return int(self._lib.dyn_read_cells(self._h, int(S), int(L)))
 
+    def ribbon_fault_reasons(self):
+        """cumulative {reason code: reads} the ribbon kernels handed to the full-band kernels (csrc/dp_ribbon.cuh)"""
+        r = np.zeros(16, dtype=np.uint64)
+        self._lib.dyn_ribbon_fault_reasons(self._h, r.ctypes.data_as(u64p))
+        out = {int(i): int(v) for i, v in enumerate(r[:13]) if v}
+        out["records_per_row"] = float(r[13]) / 1000.0
+        out["two_level_checkpoints"] = bool(r[14])
+        return out
+
     def last_timing(self):
         t = np.zeros(3)
         self._lib.dyn_last_timing(self._h, t.ctypes.data_as(f64p))

@@ -58,6 +58,7 @@ struct SlotScratch
 	// ribbon kernels (dp_ribbon.cuh)
 	uint2* sched;       // [T/32+2]  window schedule: {window centre of row 32c, slide bits of rows 32c .. 32c+31}
 	uint32_t* hdr;      // [T+1][HDRW] row headers: first record, hot-lane mask, decision words
+	float* ring;        // two-level checkpoints: the 8 group checkpoints of the current super-group (+ their lane offsets)
 };
 
 struct BatchArgs

@@ -68,7 +68,21 @@ struct RCfg
 #define RIB_DBG(...) do { } while (0)
 #endif
 
-constexpr int BAND_SLACK = 18;  // slack of the window-inside-band check (the band centre moves <= 5 columns per group)
+// The reference forces every cell outside its band (NT:96-106) to -inf.  The window may reach beyond the band as long as
+// the MASS does not: the lanes within 2^-G of the row maximum must lie inside the band at every group boundary with this
+// many columns to spare (the alignment moves <= 8 columns and the band centre <= 5 during a group), so that whatever
+// the window holds outside the band is below 2^-G of the row maximum — the same level the window edges are held to.
+constexpr int BAND_SLACK = 14;
+
+// columns covered by relative lanes first .. last of the window centred at mid
+template <class RC>
+DYN_DEV void extent_columns(int mid, int first, int last, int& col_lo, int& col_hi)
+{
+	const int lo = mid - RC::HW;
+	const int ub = lo - pmod(lo, RC::SLOTS) % RC::CPL;
+	col_lo = ub + first * RC::CPL;
+	col_hi = ub + last * RC::CPL + RC::CPL - 1;
+}
 // Largest offset deficit of a lane against the row's largest lane (forward / backward values).  The posterior factor
 // 2^(OF + OB - Z) must stay a normal float when a lane that was empty at the last boundary holds the ridge in BOTH
 // directions: 2 * (RDC + 12) < 126.  Cells more than 2^-(126 + RDC) below the row maximum flush to zero — far below the
@@ -286,30 +300,72 @@ DYN_DEV void slide_down(RWarp<RC>& w, Bw<RC::CPL>& b, int& mid)
 }
 
 template <class RC>
-DYN_DEV void ckpt_store(const SlotScratch& sc, uint32_t g, int lane, const Bw<RC::CPL>& b)
+DYN_DEV void ckpt_put(float* base, int* ob, uint32_t idx, int lane, const Bw<RC::CPL>& b)
 {
 	constexpr int C = RC::CPL;
-	float* f = sc.ckpt + (size_t)g * RC::CKF;
+	float* f = base + (size_t)idx * RC::CKF;
 #pragma unroll
 	for (int j = 0; j < C; ++j)
 	{
 		f[j * 32 + lane] = b.bM[j];
 		f[(C + j) * 32 + lane] = b.bE[j];
 	}
-	reinterpret_cast<int*>(sc.ckpt_ob)[(size_t)g * 32 + lane] = b.OB;
+	ob[(size_t)idx * 32 + lane] = b.OB;
+}
+
+template <class RC>
+DYN_DEV void ckpt_store(const SlotScratch& sc, uint32_t g, int lane, const Bw<RC::CPL>& b)
+{
+	ckpt_put<RC>(sc.ckpt, reinterpret_cast<int*>(sc.ckpt_ob), g, lane, b);
+}
+
+// Two-level checkpointing (long reads): pass 1 keeps the checkpoint of every SG-th group only (plus the last group's);
+// pass 2 replays the backward pass over one super-group at a time and parks the 8 group checkpoints in a small ring.
+constexpr int SG = 8;
+
+// largest value / candidate exponent of this lane and the row maximum, as the group boundary of pass 1 computes them
+template <class RC>
+DYN_DEV void bwd_stats(const Bw<RC::CPL>& b, int& cand, int& kmax)
+{
+	float lm = b.bE[0];
+#pragma unroll
+	for (int j = 1; j < RC::CPL; ++j) lm = fmaxf(lm, b.bE[j]);
+	cand = is_alive(lm) ? b.OB + fexp(lm) : NONE;
+	kmax = warp_max_int(cand);
+}
+
+template <class RC>
+DYN_DEV void slide_down(RWarp<RC>& w, Bw<RC::CPL>& b, int& mid);
+
+// group boundary of the backward direction: renormalise, move the window down to the next group's centre
+template <class RC>
+DYN_DEV void bwd_boundary(RWarp<RC>& w, Bw<RC::CPL>& b, int cand, int kmax, int& mid, int target)
+{
+	constexpr int C = RC::CPL;
+	const int nO = max(cand, kmax - RDC);
+	const float scl = lin::pow2i(b.OB - nO);
+#pragma unroll
+	for (int j = 0; j < C; ++j)
+	{
+		b.bM[j] *= scl;
+		b.bE[j] *= scl;
+	}
+	b.OB = nO;
+#pragma unroll 1
+	while (mid > target) slide_down<RC>(w, b, mid);
+	b.sR = lin::pow2i(__shfl_sync(FULL, nO, (w.lane + 1) & 31) - nO);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // pass 1: backward over the whole read; decides and stores the window schedule.  Returns log2 Zb.
 // ------------------------------------------------------------------------------------------------------
-template <class RC, bool STORE>
-DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs& args, bool& fault)
+template <class RC, bool STORE, bool TL>
+DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs& args, int& fault)
 {
 	constexpr int C = RC::CPL;
 	const float m1 = args.m1_lin, e2 = args.e2_lin;
 	const int lane = w.lane;
 	const int G = args.rib_guard;
-	const int band_margin = w.bw_ref - RC::HW - BAND_SLACK;  // >= 0 (host)
 	const int S = (int)w.S;
 	const int gl = (S - 1) >> 3;  // last group
 	Bw<C> b;
@@ -325,7 +381,7 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 	}
 	if (STORE)
 	{
-		ckpt_store<RC>(sc, (uint32_t)gl, lane, b);
+		ckpt_store<RC>(sc, (uint32_t)(TL ? gl / SG : gl), lane, b);
 		if (lane == 0) sc.sched[gl].x = (unsigned)mid;
 	}
 	float x8;
@@ -349,41 +405,36 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 		}
 		if (g == 0) break;
 		// ---- group boundary: row 8g.  Renormalise, decide the window of group g-1, move there, checkpoint -----
-		float lm = b.bE[0];
-#pragma unroll
-		for (int j = 1; j < C; ++j) lm = fmaxf(lm, b.bE[j]);
-		const int cand = is_alive(lm) ? b.OB + fexp(lm) : NONE;
-		const int kmax = warp_max_int(cand);
-		if (kmax == NONE) { fault = true; RIB_DBG("p1 g=%d nothing alive\n", g); return NAN; }
+		int cand, kmax;
+		bwd_stats<RC>(b, cand, kmax);
+		if (kmax == NONE) { fault = 1; RIB_DBG("p1 g=%d nothing alive\n", g); return NAN; }
 		int first, last;
 		mass_extent<RC>(cand, kmax, mid, G, first, last);
-		if (first == 0 || last == 31) { fault = true; RIB_DBG("p1 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
+		if ((first == 0 || last == 31) && !fault) { fault = 2; RIB_DBG("p1 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
+		{
+			// the mass must lie inside the reference band around row 8g
+			int col_lo, col_hi;
+			extent_columns<RC>(mid, first, last, col_lo, col_hi);
+			const int mref = (int)band_mid(8u * (uint32_t)g, w.ratio);
+			if ((col_hi + BAND_SLACK > mref + w.bw_ref || col_lo - BAND_SLACK < mref - w.bw_ref) && !fault)
+			{
+				fault = 3;
+				RIB_DBG("p1 g=%d mass [%d, %d] vs band centre %d +- %d\n", g, col_lo, col_hi, mref, w.bw_ref);
+			}
+		}
 		int s = (2 * mid - extent_centre2<RC>(mid, first, last)) / 2;  // window centre above the mass centre: move down
 		s = max(0, min(s, min(8, mid)));
-		const int nO = max(cand, kmax - RDC);
-		const float scl = lin::pow2i(b.OB - nO);
-#pragma unroll
-		for (int j = 0; j < C; ++j)
-		{
-			b.bM[j] *= scl;
-			b.bE[j] *= scl;
-		}
-		b.OB = nO;
-#pragma unroll 1
-		for (int i = 0; i < s; ++i) slide_down<RC>(w, b, mid);
-		b.sR = lin::pow2i(__shfl_sync(FULL, nO, (lane + 1) & 31) - nO);
-		// the windows of both groups must lie inside the reference band (NT:96-106) around row 8g
-		const int dref = mid - (int)band_mid(8u * (uint32_t)g, w.ratio);
-		if (dref + s > band_margin || dref < -band_margin) { fault = true; RIB_DBG("p1 g=%d mid=%d dref=%d margin=%d\n", g, mid, dref, band_margin); }
+		bwd_boundary<RC>(w, b, cand, kmax, mid, mid - s);
 		if (fault) return NAN;
 		if (STORE)
 		{
-			ckpt_store<RC>(sc, (uint32_t)(g - 1), lane, b);
+			if (!TL) ckpt_store<RC>(sc, (uint32_t)(g - 1), lane, b);
+			else if ((g - 1) % SG == SG - 1) ckpt_store<RC>(sc, (uint32_t)((g - 1) / SG), lane, b);
 			if (lane == 0) sc.sched[g - 1].x = (unsigned)mid;
 		}
 	}
-	// column 0 must be inside the window of row 0, and the window inside the reference band there as well
-	if (mid > RC::HW || mid > band_margin) { fault = true; RIB_DBG("p1 end mid=%d\n", mid); }
+	// column 0 must be inside the window of row 0
+	if (mid > RC::HW && !fault) { fault = 4; RIB_DBG("p1 end mid=%d\n", mid); }
 	if (fault) return NAN;
 	// Zb = bE[0][0] (NT:286): column 0 is ring slot 0 = lane 0, j 0
 	const double z = log2((double)b.bE[0]) + (double)b.OB;
@@ -559,9 +610,9 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 
 // pass 2: recomputation + forward + posterior (+ posterior-Viterbi fill | training statistics), group by group.
 // Returns log2 Zf - log2 Zb (NaN on a fault).
-template <class RC, int MODE>
+template <class RC, int MODE, bool TL>
 DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs& args, uint64_t pc_off,
-	unsigned char* smem_raw, double Z2, uint32_t& nrec_out, bool& overflow, double& xi_m, double& xi_e)
+	unsigned char* smem_raw, double Z2, uint32_t& nrec_out, bool& overflow, double& xi_m, double& xi_e, int& fault_out)
 {
 	constexpr int C = RC::CPL;
 	constexpr int ROWF = RC::ROWF;
@@ -585,7 +636,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	const double Z2f = floor(Z2);
 	const int Z2i = (int)Z2f;
 	float c0 = (float)exp2(Z2f - Z2);
-	bool fault = false;
+	int fault = 0;
 
 	int mid = (int)sc.sched[0].x;
 	w.load_window(mid);
@@ -625,19 +676,60 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	int ckO;
 	float x8;
 	int mid_next;
+	int* const ring_ob = reinterpret_cast<int*>(sc.ring + (size_t)SG * RC::CKF);
+	// two-level checkpoints: replay the backward pass over the super-group that starts at group g0 and park the group
+	// checkpoints in the ring (the emission window travels up to the super-group's last group and back down to g0's)
+	auto replay = [&](int g0) {
+		const int gs = min(g0 + SG - 1, gl);
+		const float* cf = sc.ckpt + (size_t)(gs / SG) * RC::CKF;
+#pragma unroll
+		for (int j = 0; j < C; ++j)
+		{
+			b.bM[j] = cf[j * 32 + lane];
+			b.bE[j] = cf[(C + j) * 32 + lane];
+		}
+		b.OB = reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)(gs / SG) * 32 + lane];
+		b.sR = lin::pow2i(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
+		int mr = (int)sc.sched[gs].x;
+		if (gs != g0) w.load_window(mr);
+		ckpt_put<RC>(sc.ring, ring_ob, (uint32_t)(gs % SG), lane, b);
+#pragma unroll 1
+		for (int gp = gs; gp > g0; --gp)
+		{
+			const int i = 8 * gp + (lane & 7);
+			const float xr = (i < S) ? w.sig[i] : 0.0f;
+			const int target = (int)sc.sched[gp - 1].x;
+			if (gp < gl)
+			{
+#pragma unroll
+				for (int k = 7; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
+			}
+			else
+			{
+#pragma unroll 1
+				for (int k = S - 8 * gl - 1; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
+			}
+			int cand, kmax;
+			bwd_stats<RC>(b, cand, kmax);
+			bwd_boundary<RC>(w, b, cand, kmax, mr, target);
+			ckpt_put<RC>(sc.ring, ring_ob, (uint32_t)((gp - 1) % SG), lane, b);
+		}
+		__syncwarp();
+	};
 	auto prefetch = [&](int g) {
-		const float* cf = sc.ckpt + (size_t)g * RC::CKF;
+		const float* cf = TL ? sc.ring + (size_t)(g % SG) * RC::CKF : sc.ckpt + (size_t)g * RC::CKF;
 #pragma unroll
 		for (int j = 0; j < C; ++j)
 		{
 			ckM[j] = cf[j * 32 + lane];
 			ckE[j] = cf[(C + j) * 32 + lane];
 		}
-		ckO = reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)g * 32 + lane];
+		ckO = TL ? ring_ob[(size_t)(g % SG) * 32 + lane] : reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)g * 32 + lane];
 		const int i = 8 * g + (lane & 7);
 		x8 = (i < S) ? w.sig[i] : 0.0f;
 		mid_next = (g < gl) ? (int)sc.sched[g + 1].x : 0;
 	};
+	if (TL) replay(0);
 	prefetch(0);
 	float xprev = 0.0f;
 	float macc = 0.0f;
@@ -649,7 +741,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		{
 			// not enough room for the records this group can produce at most (pathological record density)
 			rs.overflow = true;
-			fault = true;
+			fault = 10;
 			break;
 		}
 		const float xg = x8;
@@ -690,7 +782,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			}
 		}
 		__syncwarp();
-		if (g < gl) prefetch(g + 1);
+		if (g < gl && !(TL && (g + 1) % SG == 0)) prefetch(g + 1);
 
 		// ---- step b: forward rows 8g .. 8g+nr-1 -------------------------------------------------------------
 		uint32_t* const hdr_g = sc.hdr + (size_t)(8 * g) * RC::HDRW;
@@ -735,7 +827,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		const float cnt = (g < gl) ? 8.0f : (float)(nr + 1);
 		const float mass = warp_sum(macc, lane);
 		macc = 0.0f;
-		if (!(fabsf(mass - cnt) <= RIB_MASS_TOL)) { fault = true; RIB_DBG("p2 g=%d mass=%g of %g\n", g, mass, cnt); }
+		if (!(fabsf(mass - cnt) <= RIB_MASS_TOL) && !fault) { fault = 5; RIB_DBG("p2 g=%d mass=%g of %g\n", g, mass, cnt); }
 		if (MODE == 2)
 		{
 			ta.dM += (double)ta.sM;
@@ -757,10 +849,16 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			const int cand = is_alive(lm) ? f.OF + fexp(lm) : NONE;
 			const int kmax = warp_max_int(cand);
 			const int kb = warp_max_int(is_alive(bm) ? fexp(bm) - f.OF : NONE);
-			if (kmax == NONE || kb == NONE || kmax + kb > lin::LIN_GUARD_BITS) { fault = true; RIB_DBG("p2 g=%d range kmax=%d kb=%d\n", g, kmax, kb); }
+			if ((kmax == NONE || kb == NONE || kmax + kb > lin::LIN_GUARD_BITS) && !fault) { fault = 6; RIB_DBG("p2 g=%d range kmax=%d kb=%d\n", g, kmax, kb); }
 			int first, last;
 			mass_extent<RC>(cand, kmax, mid, G, first, last);
-			if (first == 0 || last == 31) { fault = true; RIB_DBG("p2 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
+			if ((first == 0 || last == 31) && !fault) { fault = 7; RIB_DBG("p2 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
+			{
+				int col_lo, col_hi;
+				extent_columns<RC>(mid, first, last, col_lo, col_hi);
+				const int mref = (int)band_mid(8u * (uint32_t)(g + 1), w.ratio);
+				if ((col_hi + BAND_SLACK > mref + w.bw_ref || col_lo - BAND_SLACK < mref - w.bw_ref) && !fault) fault = 3;
+			}
 			const int nO = max(cand, kmax - RDC);
 			const float scl = lin::pow2i(f.OF - nO);
 #pragma unroll
@@ -780,7 +878,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			const int cand = is_alive(lm) ? f.OV + fexp(lm) - lin::E0V : NONE;
 			const int kmax = warp_max_int(cand);
 			// every posterior-Viterbi score underflowed (or is NaN): the decision bits from here on would be meaningless
-			if (kmax == NONE) { fault = true; RIB_DBG("p2 g=%d viterbi dead\n", g); }
+			if (kmax == NONE && !fault) { fault = 8; RIB_DBG("p2 g=%d viterbi dead\n", g); }
 			const int nO = max(cand, kmax - RDCV);
 			const float scl = lin::pow2i(f.OV - nO);
 #pragma unroll
@@ -796,6 +894,12 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		// move to the window of the next group
 #pragma unroll 1
 		while (mid < midn) slide_up<RC, MODE>(w, f, ta, args, pc_off, mid);
+		if (TL && (g + 1) % SG == 0)
+		{
+			// next super-group: its checkpoints first (the replay leaves the emission window where it is now)
+			replay(g + 1);
+			prefetch(g + 1);
+		}
 	}
 	// Zf = fE[T-1][N-1] (NT:285)
 	float v = 0.0f;
@@ -803,8 +907,10 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	const int ql = pmod((int)w.N - 1, RC::SLOTS) / C;
 	double dz = log2((double)v) + (double)f.OF - Z2;
 	dz = shfl_f64(dz, ql);
-	RIB_DBG("p2 end dz=%g fault=%d\n", dz, (int)fault);
-	if (__any_sync(FULL, fault)) dz = NAN;
+	RIB_DBG("p2 end dz=%g fault=%d\n", dz, fault);
+	fault = warp_max_int(fault);
+	fault_out = fault;
+	if (fault) dz = NAN;
 	if (MODE == 2)
 	{
 		// columns still inside the window
@@ -926,7 +1032,7 @@ DYN_DEV bool traceback_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 }
 
 // one read, all passes.  A read the ribbon cannot represent leaves with ST_LIN_FAULT (host: full-band kernels).
-template <class RC, int MODE>
+template <class RC, int MODE, bool TL>
 DYN_DEV void ribbon_read(const BatchArgs& args, const ReadDesc& rd, uint32_t ridx, const SlotScratch& sc,
 	unsigned char* smem_raw, int lane)
 {
@@ -948,27 +1054,36 @@ DYN_DEV void ribbon_read(const BatchArgs& args, const ReadDesc& rd, uint32_t rid
 	out.xi_m = 0.0;
 	out.xi_e = 0.0;
 
-	bool fault = false;
-	const double Z2 = (MODE == 0) ? rib::backward_pass<RC, false>(w, sc, args, fault) : rib::backward_pass<RC, true>(w, sc, args, fault);
+	// why a read is handed to the full-band kernels (ReadOut.nrec of a faulted read; dyn_last_ribbon counts them):
+	//  1 nothing alive  2 backward mass at a window edge  3 window outside the reference band  4 window misses row 0
+	//  5 posterior mass of a group != 1  6 range guard  7 forward mass at a window edge  8 posterior-Viterbi scores died
+	//  9 Zf != Zb  10 record buffer full  11 traceback incomplete  12 Zb not finite
+	int fault = 0;
+	const double Z2 = (MODE == 0) ? rib::backward_pass<RC, false, TL>(w, sc, args, fault) : rib::backward_pass<RC, true, TL>(w, sc, args, fault);
 	out.Z = Z2 * LN2;
-	if (fault || !(Z2 > -1.0e30 && Z2 < 1.0e30)) out.status = ST_LIN_FAULT;
-	else if (MODE != 0)
+	fault = warp_max_int(fault);
+	if (!fault && !(Z2 > -1.0e30 && Z2 < 1.0e30)) fault = 12;
+	if (!fault && MODE != 0)
 	{
 		__threadfence_block();
 		__syncwarp();
 		uint32_t nrec = 0;
 		bool overflow = false;
-		const double dz2 = rib::forward_pass<RC, MODE>(w, sc, args, rd.pc_off, smem_raw, Z2, nrec, overflow, out.xi_m, out.xi_e);
+		const double dz2 = rib::forward_pass<RC, MODE, TL>(w, sc, args, rd.pc_off, smem_raw, Z2, nrec, overflow, out.xi_m, out.xi_e, fault);
 		out.nrec = nrec;
 		out.dZ = dz2 * LN2;
-		if (!(fabs(dz2) <= lin::LIN_Z_TOL)) out.status = ST_LIN_FAULT;
-		else if (overflow) out.status = ST_LIN_FAULT;  // pathological record density: the full-band kernels have their own retry
-		else if (MODE == 1)
+		if (!fault && !(fabs(dz2) <= lin::LIN_Z_TOL)) fault = 9;
+		if (!fault && MODE == 1)
 		{
 			__threadfence_block();
 			__syncwarp();
-			if (!rib::traceback_pass<RC>(w, sc, args, rd)) out.status = ST_LIN_FAULT;
+			if (!rib::traceback_pass<RC>(w, sc, args, rd)) fault = 11;
 		}
+	}
+	if (fault)
+	{
+		out.status = ST_LIN_FAULT;
+		out.nrec = (uint32_t)fault;
 	}
 	if (lane == 0) args.out[ridx] = out;
 }

@@ -722,9 +722,13 @@ struct dyn_aligner
 	int rib_guard = 40;        // the window's edge lanes must stay this many bits below the row maximum
 	double thr_rib = -16.0;    // log2 of the posterior above which a lane is recorded (unrecorded path cells count as 0)
 	double rib_recs_per_row = 4.0;
+	int rib_two_level = -1;    // checkpoints of every 8th group only: -1 when the scratch would not fit otherwise, 0 never, 1 always
+	double rib_last_two_level = 0;
+	double rib_recs_used = 0;  // lane records per lattice row the last batch actually wrote (align mode)
 	int rib_bps = 0;           // resident CTAs (of 4 warps) per SM of the ribbon kernels; 0: the build's default
 	uint64_t n_ribbon = 0;     // reads of the last batch the ribbon kernels were given ...
 	uint64_t n_rib_fault = 0;  // ... and how many of them they handed on to the full-band kernels
+	uint64_t rib_reason[16] = {0};  // cumulative over the handle's life: faults by reason (dp_ribbon.cuh ribbon_read)
 	double ribbon_ms = 0.0;
 	double recs_per_row = 1.6;  // lane records per row (typical use: ~1.1; a read that overflows is retried alone with a full buffer)
 	double mem_fraction = 0.92;  // share of the free HBM the scratch of the resident warps may take
@@ -1119,26 +1123,37 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			unsigned gridw = (unsigned)std::min<size_t>(resident, rorder.size());
 			size_t per_slot = 0, o_sch = 0, o_ck = 0, o_ob = 0, o_hdr = 0, o_rec = 0, o_pp = 0;
 			uint64_t rcap = 0;
+			size_t o_ring = 0;
+			bool two_level = false;
 			if (mode != 0)
 			{
-				const size_t nck = (size_t)maxTr / rg.ck + 2;
-				size_t o = 0;
-				o_sch = o; o = align_up(o + nck * 8, 256);
-				o_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
-				o_ob = o; o = align_up(o + nck * 32 * 4, 256);
-				if (mode == 1)
-				{
-					rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64 + 9 * 32;
-					o_hdr = o; o = align_up(o + ((size_t)maxTr + 32) * rg.hdrw * 4, 256);
-					o_rec = o; o = align_up(o + rcap * rg.recf * 4, 256);
-					o_pp = o; o = align_up(o + ((size_t)maxTr + 32) * 4, 256);
-				}
-				per_slot = o;
 				const size_t budget = (size_t)((double)(rt.free_bytes() + (A.root ? A.root : &A)->d_rib_scratch.cap) * A.mem_fraction);
+				// checkpoints of every group (640 B per 8 rows at 2 columns per lane) unless the scratch of the resident warps
+				// would not fit: then only every 8th group's, the others replayed in pass 2 (long reads; A.rib_two_level forces)
+				for (int pass = 0; pass < 2; ++pass)
+				{
+					two_level = (A.rib_two_level > 0) || (A.rib_two_level < 0 && pass == 1);
+					const size_t ngr = (size_t)maxTr / rg.ck + 2;
+					const size_t nck = two_level ? ngr / 8 + 2 : ngr;
+					size_t o = 0;
+					o_sch = o; o = align_up(o + ngr * 8, 256);
+					o_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
+					o_ob = o; o = align_up(o + nck * 32 * 4, 256);
+					o_ring = o; o = align_up(o + (two_level ? 8 * ((size_t)rg.ckf * 4 + 128) : 0), 256);
+					if (mode == 1)
+					{
+						rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64 + 9 * 32;
+						o_hdr = o; o = align_up(o + ((size_t)maxTr + 32) * rg.hdrw * 4, 256);
+						o_rec = o; o = align_up(o + rcap * rg.recf * 4, 256);
+						o_pp = o; o = align_up(o + ((size_t)maxTr + 32) * 4, 256);
+					}
+					per_slot = o;
+					if (A.rib_two_level >= 0 || budget / per_slot >= gridw) break;
+				}
 				const size_t fit = std::max<size_t>(1, budget / per_slot);
 				if (tm.on)
-					fprintf(stderr, "[dyn timing] ribbon scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit\n",
-						per_slot / 1048576.0, gridw, budget / 1073741824.0, fit);
+					fprintf(stderr, "[dyn timing] ribbon scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit%s\n",
+						per_slot / 1048576.0, gridw, budget / 1073741824.0, fit, two_level ? " (two-level checkpoints)" : "");
 				gridw = (unsigned)std::min<size_t>(gridw, fit);
 			}
 			{
@@ -1162,6 +1177,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 					slots[q].sched = (uint2*)(b + o_sch);
 					slots[q].ckpt = (float*)(b + o_ck);
 					slots[q].ckpt_ob = (double*)(b + o_ob);
+					slots[q].ring = (float*)(b + o_ring);
 					if (mode == 1)
 					{
 						slots[q].hdr = (uint32_t*)(b + o_hdr);
@@ -1188,10 +1204,10 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			}
 			rt.mark_on(6, R.rt);
 #ifndef DYN_HOST_EMU
-			const int le = rib::launch((void*)R.rt.stream, rb, gridw, mode, A.ribbon, A.rib_bps);
+			const int le = rib::launch((void*)R.rt.stream, rb, gridw, mode, A.ribbon, A.rib_bps, two_level);
 			if (le != 0) throw std::runtime_error(std::string("CUDA error launching the ribbon kernel: ") + cudaGetErrorString((cudaError_t)le));
 #else
-			rib::launch(nullptr, rb, gridw, mode, A.ribbon, A.rib_bps);
+			rib::launch(nullptr, rb, gridw, mode, A.ribbon, A.rib_bps, two_level);
 #endif
 			rt.mark_on(7, R.rt);
 			if (cross) rt.wait_self(7);
@@ -1203,11 +1219,23 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			tm.lap("ribbon_kernel");
 			A.ribbon_ms = rt.elapsed(6, 7);
 			A.n_ribbon = rorder.size();
+			{
+				double nrec = 0.0, nrow = 0.0;
+				for (uint32_t r : rorder)
+					if (res.out[r].status == ST_OK)
+					{
+						nrec += (double)res.out[r].nrec;
+						nrow += (double)res.desc[r].S;
+					}
+				A.rib_last_two_level = two_level ? 1.0 : 0.0;
+				A.rib_recs_used = nrow > 0 ? nrec / nrow : 0.0;
+			}
 			for (uint32_t r : rorder)
 				if (res.out[r].status == ST_LIN_FAULT)
 				{
 					rest.push_back(r);
 					++A.n_rib_fault;
+					++A.rib_reason[std::min<uint32_t>(res.out[r].nrec, 15u)];
 					if (mode == 2)
 					{
 						// columns the read flushed before its fault was detected: the full-band kernels accumulate
@@ -1256,8 +1284,23 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		o_pn = o; o = align_up(o + ((size_t)maxT + 1) * 4, 256);
 		o_pp = o; o = align_up(o + ((size_t)maxT + 1) * 4, 256);
 		per_slot = o;
-		const size_t budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
-		const size_t fit = std::max<size_t>(1, budget / per_slot);
+		size_t budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
+		size_t fit = std::max<size_t>(1, budget / per_slot);
+		if (fit < grid)
+		{
+			// long reads handed on by the ribbon kernels: their full-band scratch needs the room of the (shared) ribbon pool.
+			// Nothing enqueued may still use it: hold compute_mu (no lane can enqueue) and drain the root's stream.
+			dyn_aligner& R = A.root ? *A.root : A;
+			std::lock_guard<std::mutex> cl(R.compute_mu);
+			if (R.d_rib_scratch.cap)
+			{
+				R.rt.sync();
+				rt.sync();
+				R.d_rib_scratch.release(R.rt);
+				budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
+				fit = std::max<size_t>(1, budget / per_slot);
+			}
+		}
 		if (tm.on)
 			fprintf(stderr, "[dyn timing] scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit\n",
 				per_slot / 1048576.0, grid, budget / 1073741824.0, fit);
@@ -2565,6 +2608,13 @@ void dyn_last_ribbon(const dyn_aligner* A, uint64_t* out2)
 	out2[0] = A->n_ribbon;
 	out2[1] = A->n_rib_fault;
 }
+void dyn_ribbon_fault_reasons(const dyn_aligner* A, uint64_t* out16)
+{
+	for (int i = 0; i < 16; ++i) out16[i] = A->rib_reason[i];
+	// [13]: records per row of the last batch x 1000, [14]: the last batch ran with two-level checkpoints
+	out16[13] = (uint64_t)(A->rib_recs_used * 1000.0);
+	out16[14] = (uint64_t)A->rib_last_two_level;
+}
 
 void dyn_last_timing(const dyn_aligner* A, double* out3)
 {
@@ -2604,6 +2654,7 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	else if (k == "thr_rib") A->thr_rib = value;
 	else if (k == "rib_recs_per_row") A->rib_recs_per_row = value;
 	else if (k == "rib_bps") A->rib_bps = (int)value;
+	else if (k == "rib_two_level") A->rib_two_level = (int)value;
 	else return -1;
 	return 0;
 }

@@ -18,7 +18,7 @@ using RC4 = RCfg<4>;
 constexpr int BPS2 = 5;  // 20 resident warps per SM: <= 96 registers per thread, no spills (measured: 6 -> 80 registers: -4 %, 8 -> 64: -13 %)
 constexpr int BPS4 = 4;  // 16 resident warps per SM: <= 128 registers per thread
 
-template <class RC, int MODE>
+template <class RC, int MODE, bool TL>
 DYN_DEV void worker(const BatchArgs& args, unsigned char* smem_raw, int lane, unsigned slot)
 {
 	if (slot >= args.n_slots) return;
@@ -41,44 +41,39 @@ DYN_DEV void worker(const BatchArgs& args, unsigned char* smem_raw, int lane, un
 			}
 			continue;
 		}
-		ribbon_read<RC, MODE>(args, rd, ridx, sc, smem_raw, lane);
+		ribbon_read<RC, MODE, TL>(args, rd, ridx, sc, smem_raw, lane);
 		__syncwarp();
 	}
 }
 
 #ifndef DYN_HOST_EMU
-template <class RC, int MODE, int BPS>
+template <class RC, int MODE, int BPS, bool TL>
 __global__ void __launch_bounds__(32 * WPB, BPS) k_ribbon(BatchArgs args)
 {
 	extern __shared__ __align__(16) unsigned char smem_all[];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	worker<RC, MODE>(args, smem_all + (size_t)wid * RC::SMEM_BYTES, lane, blockIdx.x * WPB + wid);
+	worker<RC, MODE, TL>(args, smem_all + (size_t)wid * RC::SMEM_BYTES, lane, blockIdx.x * WPB + wid);
 }
 
-template <class RC, int BPS>
+template <class RC, int BPS, bool TL>
 int launch_t(cudaStream_t stream, const BatchArgs& args, unsigned n_warps, int mode)
 {
+	// (the dynamic shared memory of a CTA, 4 x 2.3 / 4.6 KB, is below the 48 KB that needs no opt-in)
 	const size_t smem = RC::SMEM_BYTES * WPB;
-	cudaError_t e = cudaSuccess;
-	// the opt-in is per device and cheap: set it before every launch (a handle per device may share this process)
-	e = cudaFuncSetAttribute(k_ribbon<RC, 1, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return (int)e;
-	e = cudaFuncSetAttribute(k_ribbon<RC, 2, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return (int)e;
 	const unsigned ctas = (n_warps + WPB - 1) / WPB;
-	if (mode == 0) k_ribbon<RC, 0, BPS><<<ctas, 32 * WPB, 0, stream>>>(args);
-	else if (mode == 1) k_ribbon<RC, 1, BPS><<<ctas, 32 * WPB, smem, stream>>>(args);
-	else k_ribbon<RC, 2, BPS><<<ctas, 32 * WPB, smem, stream>>>(args);
+	if (mode == 0) k_ribbon<RC, 0, BPS, false><<<ctas, 32 * WPB, 0, stream>>>(args);
+	else if (mode == 1) k_ribbon<RC, 1, BPS, TL><<<ctas, 32 * WPB, smem, stream>>>(args);
+	else k_ribbon<RC, 2, BPS, TL><<<ctas, 32 * WPB, smem, stream>>>(args);
 	return (int)cudaGetLastError();
 }
 #else
-template <class RC, int BPS>
+template <class RC, int BPS, bool TL>
 int launch_t(void*, const BatchArgs& args, unsigned n_warps, int mode)
 {
 	const size_t smem = RC::SMEM_BYTES;
-	if (mode == 0) simt::launch(n_warps, smem, [&]() { worker<RC, 0>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
-	else if (mode == 1) simt::launch(n_warps, smem, [&]() { worker<RC, 1>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
-	else simt::launch(n_warps, smem, [&]() { worker<RC, 2>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	if (mode == 0) simt::launch(n_warps, smem, [&]() { worker<RC, 0, false>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else if (mode == 1) simt::launch(n_warps, smem, [&]() { worker<RC, 1, TL>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else simt::launch(n_warps, smem, [&]() { worker<RC, 2, TL>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 	return 0;
 }
 #endif
@@ -107,7 +102,7 @@ bool geometry(int cpl, int bps, Geometry& g)
 	return true;
 }
 
-int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps)
+int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps, bool two_level)
 {
 #ifndef DYN_HOST_EMU
 	cudaStream_t s = (cudaStream_t)stream;
@@ -116,13 +111,14 @@ int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int 
 #endif
 	if (cpl == 2)
 	{
+		if (two_level) return launch_t<RC2, BPS2, true>(s, args, n_warps, mode);
 #ifndef DYN_HOST_EMU
-		if (bps == 6) return launch_t<RC2, 6>(s, args, n_warps, mode);
-		if (bps == 8) return launch_t<RC2, 8>(s, args, n_warps, mode);
+		if (bps == 6) return launch_t<RC2, 6, false>(s, args, n_warps, mode);
+		if (bps == 8) return launch_t<RC2, 8, false>(s, args, n_warps, mode);
 #endif
-		return launch_t<RC2, BPS2>(s, args, n_warps, mode);
+		return launch_t<RC2, BPS2, false>(s, args, n_warps, mode);
 	}
-	if (cpl == 4) return launch_t<RC4, BPS4>(s, args, n_warps, mode);
+	if (cpl == 4) return two_level ? launch_t<RC4, BPS4, true>(s, args, n_warps, mode) : launch_t<RC4, BPS4, false>(s, args, n_warps, mode);
 	(void)bps;
 	return -1;
 }

@@ -29,7 +29,8 @@ bool geometry(int cpl, int bps, Geometry& g);  // bps: resident CTAs per SM (0 =
 
 // n_warps resident warps (one scratch slot each, args.slots[0 .. n_warps)); mode 0: Z only, 1: align, 2: train.
 // Returns 0 or the cudaError_t of the launch.
-int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps);
+// two_level: checkpoints of every 8th group only (dp_ribbon.cuh SG), the rest replayed into a per-warp ring in pass 2
+int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps, bool two_level);
 
 } // namespace rib
 } // namespace dyn

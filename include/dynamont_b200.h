@@ -211,6 +211,8 @@ int dyn_last_variant(const dyn_aligner*);
  * checked on the device): out2[0] = reads of the last batch call they were given, out2[1] = reads they handed on to
  * the full-band kernels (window / range checks failed); results are identical either way */
 void dyn_last_ribbon(const dyn_aligner*, uint64_t* out2);
+/* cumulative count of those hand-overs by reason code 1..12 (csrc/dp_ribbon.cuh, ribbon_read), out16[reason] */
+void dyn_ribbon_fault_reasons(const dyn_aligner*, uint64_t* out16);
 /* run all work of this handle on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
  * of the handle's own stream, so that the caller's CUDA events bracket it */
 int dyn_set_stream(dyn_aligner*, void* cuda_stream);

@@ -229,3 +229,42 @@ def test_emulated_async_lanes_match_sync_batches(emu_lib):
             assert r["Z"] == g["Z"]
             assert np.array_equal(r["signal_positions"], g["signal_positions"])
             assert np.array_equal(r["probabilities"], g["probabilities"])
+
+
+def test_emulated_ribbon_two_level_checkpoints_identical(emu_lib):
+    """ribbon kernels: checkpoints of every 8th group only + replay into the per-warp ring (long reads) must give
+    bit-identical alignments and training statistics to a checkpoint per group; both identical to the golden reference"""
+    case = [c for c in load_golden() if c.name == "rna002_band"][0]
+    out = {}
+    for tl in (0, 1):
+        al = _aligner(emu_lib, case, -1)
+        al.set_option("rib_two_level", tl)
+        r = al.align(case.signal, case.sequence, True)
+        assert al.last_timing()["ribbon_reads"] == 1 and al.last_timing()["ribbon_faults"] == 0
+        check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+        _, pooled = al.train_batch([case.signal], [case.sequence])
+        out[tl] = (r, pooled)
+    assert out[0][0]["Z"] == out[1][0]["Z"]
+    assert np.array_equal(out[0][0]["signal_positions"], out[1][0]["signal_positions"])
+    assert np.array_equal(out[0][0]["probabilities"], out[1][0]["probabilities"])
+    assert np.array_equal(out[0][1]["w"], out[1][1]["w"]) and np.array_equal(out[0][1]["xx"], out[1][1]["xx"])
+
+
+def test_emulated_ribbon_hands_short_and_drifting_reads_to_full_band(emu_lib):
+    """reads whose band is narrower than the window never enter the ribbon kernels; a read whose alignment drifts out of
+    the window's reach (3 samples per base) faults on the device and comes back from the full-band kernels, identical to
+    the oracle either way"""
+    from dynamont_b200.synth import native_model, synth_read
+    from oracle import Oracle
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    al = _aligner(emu_lib, case, -1)
+    r = al.align(case.signal, case.sequence, True)
+    assert al.last_timing()["ribbon_reads"] == 0
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    nm, ns = native_model(case.model_path, case.pore)
+    s, q, _ = synth_read(np.random.default_rng(5), nm, ns, 5, 200, 3)
+    o = Oracle(case.model_path, case.pore).align(s, q, True)
+    r = al.align(s, q, True)
+    tm = al.last_timing()
+    assert tm["ribbon_reads"] == 1 and tm["ribbon_faults"] == 1 and sum(v for k, v in al.ribbon_fault_reasons().items() if isinstance(k, int)) == 1
+    check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"], "drifting read")
