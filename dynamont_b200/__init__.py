@@ -1,5 +1,6 @@
 """dynamont_b200 — B200-native implementation of Dynamont's segmentation hot path (basic-mode banded
 forward-backward HMM, posterior decoding and training statistics) behind the reference's operator API."""
 from .aligner import Aligner, PoreType, pore_type  # noqa: F401
+from .parallel import MultiDeviceAligner  # noqa: F401
 
-__all__ = ["Aligner", "PoreType", "pore_type"]
+__all__ = ["Aligner", "PoreType", "pore_type", "MultiDeviceAligner"]

@@ -244,6 +244,35 @@ DYN_DEV int extent_centre2(int mid, int first, int last)
 	return 2 * ub + (first + last) * RC::CPL + RC::CPL - 1;
 }
 
+// The reference forces every cell outside its band (row t: columns band_mid(t) +- bw, NT:96-106) to -inf.  A group whose
+// window lies inside the band of all its rows needs nothing; otherwise (the alignment has drifted to the band's edge,
+// or the band is narrower than the window) its rows run one by one and every row is clipped to the band exactly.
+template <class RC>
+DYN_DEV bool group_needs_clip(const RWarp<RC>& w, int mid, int g)
+{
+	const uint32_t t0 = 8u * (uint32_t)g, t1 = min(t0 + 8u, w.T - 1u);
+	const int m0 = (int)band_mid(t0, w.ratio), m1 = (int)band_mid(t1, w.ratio);  // band centres are non-decreasing in t
+	return (mid + RC::HW > m0 + w.bw_ref) || (mid - RC::HW < m1 - w.bw_ref);
+}
+
+// zero the cells of row t that lie outside the reference band
+template <class RC>
+DYN_DEV void clip_row(const RWarp<RC>& w, float (&p)[RC::CPL], float (&q)[RC::CPL], int mid, uint32_t t)
+{
+	const int m = (int)band_mid(t, w.ratio);
+	const int lo = m - w.bw_ref, hi = m + w.bw_ref;
+#pragma unroll
+	for (int j = 0; j < RC::CPL; ++j)
+	{
+		const int col = RWarp<RC>::col_of_slot(w.lane * RC::CPL + j, mid - RC::HW);
+		if (col < lo || col > hi)
+		{
+			p[j] = 0.0f;
+			q[j] = 0.0f;
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------
 // backward recurrence (NT_aligner_api.cpp:158-207), linear domain: one row
 // ------------------------------------------------------------------------------------------------------
@@ -393,7 +422,8 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 	{
 		const float xg = x8;
 		if (g > 0) x8 = w.sig[8 * (g - 1) + (lane & 7)];
-		if (g < gl)
+		const bool clip = group_needs_clip<RC>(w, mid, g);
+		if (g < gl && !clip)
 		{
 #pragma unroll
 			for (int k = 7; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
@@ -401,7 +431,11 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 		else
 		{
 #pragma unroll 1
-			for (int k = S - 8 * gl - 1; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
+			for (int k = ((g < gl) ? 8 : S - 8 * gl) - 1; k >= 0; --k)
+			{
+				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
+				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, 8u * (uint32_t)g + (uint32_t)k);
+			}
 		}
 		if (g == 0) break;
 		// ---- group boundary: row 8g.  Renormalise, decide the window of group g-1, move there, checkpoint -----
@@ -411,17 +445,6 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 		int first, last;
 		mass_extent<RC>(cand, kmax, mid, G, first, last);
 		if ((first == 0 || last == 31) && !fault) { fault = 2; RIB_DBG("p1 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
-		{
-			// the mass must lie inside the reference band around row 8g
-			int col_lo, col_hi;
-			extent_columns<RC>(mid, first, last, col_lo, col_hi);
-			const int mref = (int)band_mid(8u * (uint32_t)g, w.ratio);
-			if ((col_hi + BAND_SLACK > mref + w.bw_ref || col_lo - BAND_SLACK < mref - w.bw_ref) && !fault)
-			{
-				fault = 3;
-				RIB_DBG("p1 g=%d mass [%d, %d] vs band centre %d +- %d\n", g, col_lo, col_hi, mref, w.bw_ref);
-			}
-		}
 		int s = (2 * mid - extent_centre2<RC>(mid, first, last)) / 2;  // window centre above the mass centre: move down
 		s = max(0, min(s, min(8, mid)));
 		bwd_boundary<RC>(w, b, cand, kmax, mid, mid - s);
@@ -699,7 +722,8 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			const int i = 8 * gp + (lane & 7);
 			const float xr = (i < S) ? w.sig[i] : 0.0f;
 			const int target = (int)sc.sched[gp - 1].x;
-			if (gp < gl)
+			const bool clipr = group_needs_clip<RC>(w, mr, gp);
+			if (gp < gl && !clipr)
 			{
 #pragma unroll
 				for (int k = 7; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
@@ -707,7 +731,11 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			else
 			{
 #pragma unroll 1
-				for (int k = S - 8 * gl - 1; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
+				for (int k = ((gp < gl) ? 8 : S - 8 * gl) - 1; k >= 0; --k)
+				{
+					bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
+					if (clipr) clip_row<RC>(w, b.bM, b.bE, mr, 8u * (uint32_t)gp + (uint32_t)k);
+				}
 			}
 			int cand, kmax;
 			bwd_stats<RC>(b, cand, kmax);
@@ -757,7 +785,8 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		b.OB = ckO;
 		b.sR = lin::pow2i(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
 		const float kap = lin::kappa(f.OF, b.OB, Z2i, c0);
-		if (g < gl)
+		const bool clip = group_needs_clip<RC>(w, mid, g);
+		if (g < gl && !clip)
 		{
 #pragma unroll
 			for (int j = 0; j < C; ++j) rows[8 * ROWF + j * 32] = b.bE[j] * kap;
@@ -777,6 +806,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			for (int k = nr - 1; k >= 0; --k)
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
+				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, 8u * (uint32_t)g + (uint32_t)k);
 #pragma unroll
 				for (int j = 0; j < C; ++j) rows[k * ROWF + j * 32] = b.bE[j] * kap;
 			}
@@ -789,7 +819,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		float bc[C], bn[C];
 #pragma unroll
 		for (int j = 0; j < C; ++j) bc[j] = rows[j * 32];
-		if (g < gl)
+		if (g < gl && !clip)
 		{
 #pragma unroll
 			for (int k = 0; k < 8; ++k)
@@ -812,19 +842,20 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 				for (int j = 0; j < C; ++j) bn[j] = rows[(k + 1) * ROWF + j * 32];
 				const float x = __shfl_sync(FULL, xg, k);
 				macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * RC::HDRW, recs, thr, x, xprev, bc, bn, m1, e2);
+				if (clip) clip_row<RC>(w, f.fM, f.fE, mid, 8u * (uint32_t)g + (uint32_t)k + 1u);  // f now holds row t+1
 				xprev = x;
 #pragma unroll
 				for (int j = 0; j < C; ++j) bc[j] = bn[j];
 			}
 			// last row T-1: posteriors, Viterbi, bits, records; no forward step, no match posterior
-			macc += fwd_row<RC, MODE, false>(w, f, rs, ta, hdr_g + nr * RC::HDRW, recs, thr, 0.0f, xprev, bc, bn, m1, e2);
+			if (g == gl) macc += fwd_row<RC, MODE, false>(w, f, rs, ta, hdr_g + nr * RC::HDRW, recs, thr, 0.0f, xprev, bc, bn, m1, e2);
 		}
 		__syncwarp();
 
 		// ---- group boundary: state row 8g+8 ------------------------------------------------------------------
 		// closed loop: the posterior mass of every row is 1; a row that lost mass is a fault, the mean deviation (slow
 		// common-mode FP32 drift) is folded into the posterior factor of the next group
-		const float cnt = (g < gl) ? 8.0f : (float)(nr + 1);
+		const float cnt = (g < gl) ? (float)nr : (float)(nr + 1);
 		const float mass = warp_sum(macc, lane);
 		macc = 0.0f;
 		if (!(fabsf(mass - cnt) <= RIB_MASS_TOL) && !fault) { fault = 5; RIB_DBG("p2 g=%d mass=%g of %g\n", g, mass, cnt); }
@@ -853,12 +884,6 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			int first, last;
 			mass_extent<RC>(cand, kmax, mid, G, first, last);
 			if ((first == 0 || last == 31) && !fault) { fault = 7; RIB_DBG("p2 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
-			{
-				int col_lo, col_hi;
-				extent_columns<RC>(mid, first, last, col_lo, col_hi);
-				const int mref = (int)band_mid(8u * (uint32_t)(g + 1), w.ratio);
-				if ((col_hi + BAND_SLACK > mref + w.bw_ref || col_lo - BAND_SLACK < mref - w.bw_ref) && !fault) fault = 3;
-			}
 			const int nO = max(cand, kmax - RDC);
 			const float scl = lin::pow2i(f.OF - nO);
 #pragma unroll

@@ -721,7 +721,8 @@ struct dyn_aligner
 	int ribbon = 2;            // lattice columns per lane of the window (2: 63 columns, 4: 127 columns); 0: off
 	int rib_guard = 40;        // the window's edge lanes must stay this many bits below the row maximum
 	double thr_rib = -16.0;    // log2 of the posterior above which a lane is recorded (unrecorded path cells count as 0)
-	double rib_recs_per_row = 4.0;
+	double rib_recs_per_row = 2.5;   // lane records per lattice row budgeted (measured use: 1.2; a read that needs more faults to the full-band kernels)
+	int rib_min_bw = 0;        // reads whose half band is narrower than this skip the ribbon tier (0: none; the band is clipped exactly inside the window)
 	int rib_two_level = -1;    // checkpoints of every 8th group only: -1 when the scratch would not fit otherwise, 0 never, 1 always
 	double rib_last_two_level = 0;
 	double rib_recs_used = 0;  // lane records per lattice row the last batch actually wrote (align mode)
@@ -1110,7 +1111,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		uint32_t maxTr = 0;
 		for (uint32_t r : order)
 		{
-			if ((int)res.desc[r].bw - rg.hw - 18 >= 2)
+			if ((int)res.desc[r].bw >= A.rib_min_bw)
 			{
 				rorder.push_back(r);
 				maxTr = std::max(maxTr, res.desc[r].S + 1);
@@ -2655,6 +2656,7 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	else if (k == "rib_recs_per_row") A->rib_recs_per_row = value;
 	else if (k == "rib_bps") A->rib_bps = (int)value;
 	else if (k == "rib_two_level") A->rib_two_level = (int)value;
+	else if (k == "rib_min_bw") A->rib_min_bw = (int)value;
 	else return -1;
 	return 0;
 }

@@ -16,6 +16,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """a plain `pytest tests` on a box without a GPU skips the gpu-marked tests instead of failing at dyn_create"""
+    if have_cuda():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (the product has no CPU path; run with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 class GoldenCase:
     def __init__(self, z, name):
         g = lambda k: z[name + "/" + k]  # noqa: E731

@@ -250,21 +250,61 @@ def test_emulated_ribbon_two_level_checkpoints_identical(emu_lib):
     assert np.array_equal(out[0][1]["w"], out[1][1]["w"]) and np.array_equal(out[0][1]["xx"], out[1][1]["xx"])
 
 
-def test_emulated_ribbon_hands_short_and_drifting_reads_to_full_band(emu_lib):
-    """reads whose band is narrower than the window never enter the ribbon kernels; a read whose alignment drifts out of
-    the window's reach (3 samples per base) faults on the device and comes back from the full-band kernels, identical to
-    the oracle either way"""
+def test_emulated_ribbon_clips_the_reference_band_exactly(emu_lib):
+    """the ribbon kernels clip every row to the reference band (NT:96-106) when the window reaches beyond it: a read whose
+    band is narrower than the window, a read whose alignment drifts to the band edge (3 samples per base), and a band so
+    narrow that it cuts the alignment (the reference throws; the ribbon faults and the full-band kernels report it)"""
+    from dynamont_b200 import Aligner
     from dynamont_b200.synth import native_model, synth_read
     from oracle import Oracle
     case = [c for c in load_golden() if c.name == "rna002_short"][0]
     al = _aligner(emu_lib, case, -1)
     r = al.align(case.signal, case.sequence, True)
-    assert al.last_timing()["ribbon_reads"] == 0
+    tm = al.last_timing()
+    assert tm["ribbon_reads"] == 1 and tm["ribbon_faults"] == 0
     check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
     nm, ns = native_model(case.model_path, case.pore)
     s, q, _ = synth_read(np.random.default_rng(5), nm, ns, 5, 200, 3)
     o = Oracle(case.model_path, case.pore).align(s, q, True)
     r = al.align(s, q, True)
-    tm = al.last_timing()
-    assert tm["ribbon_reads"] == 1 and tm["ribbon_faults"] == 1 and sum(v for k, v in al.ribbon_fault_reasons().items() if isinstance(k, int)) == 1
+    assert al.last_timing()["ribbon_reads"] == 1
     check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"], "drifting read")
+    for band in (40, 16, 6):
+        aln = Aligner(case.model_path, case.pore, band=band, _lib_path=emu_lib)
+        orn = Oracle(case.model_path, case.pore, band=band)
+        rng = np.random.default_rng(band)
+        for L in (90, 150):
+            s, q, _ = synth_read(rng, nm, ns, 5, L, 8)
+            try:
+                o = orn.align(s, q, True)
+            except RuntimeError as e:
+                with pytest.raises(RuntimeError, match=str(e)[:20]):
+                    aln.align(s, q, True)
+                continue
+            check_alignment(aln.align(s, q, True), o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"],
+                            "band %d" % band)
+
+
+def test_emulated_multi_device_front_equals_single(emu_lib):
+    """MultiDeviceAligner (reads dealt over a device list, merged in input order): exactly the single-handle results"""
+    from dynamont_b200 import MultiDeviceAligner
+    from dynamont_b200.synth import native_model, synth_read
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    nm, ns = native_model(case.model_path, case.pore)
+    rng = np.random.default_rng(9)
+    sigs, seqs = [], []
+    for L in (140, 40, 90, 120, 60, 75, 130):
+        s, q, _ = synth_read(rng, nm, ns, 5, L, 8)
+        sigs.append(s.astype(np.float32))
+        seqs.append(q)
+    sigs.append(sigs[0][:12])
+    seqs.append(seqs[0])
+    single = _aligner(emu_lib, case, -1).align_batch(sigs, seqs, True)
+    multi = MultiDeviceAligner(case.model_path, case.pore, devices=[0, 0, 0], _lib_path=emu_lib).align_batch(sigs, seqs, True)
+    assert len(single) == len(multi)
+    for a, b in zip(single, multi):
+        if isinstance(a, Exception):
+            assert isinstance(b, Exception) and str(a) == str(b)
+            continue
+        assert a["Z"] == b["Z"] and np.array_equal(a["signal_positions"], b["signal_positions"])
+        assert np.array_equal(a["probabilities"], b["probabilities"])

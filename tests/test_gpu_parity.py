@@ -240,3 +240,20 @@ def test_pooled_trainer_device_statistics(aligners):
     mean, sd = al.model()
     np.testing.assert_allclose(mean[km][heavy], case.train_mean[heavy], rtol=TRAIN_RTOL, atol=1e-5)
     np.testing.assert_allclose(sd[km][heavy], case.train_stdev[heavy], rtol=TRAIN_RTOL, atol=1e-6)
+
+
+def test_multi_device_front_equals_single(aligners, models_dir):
+    """MultiDeviceAligner over every visible GPU (twice the same GPU when only one is visible): reads dealt by
+    shard_indices, results merged in input order — exactly what one handle returns"""
+    import torch
+    from dynamont_b200 import MultiDeviceAligner
+    from dynamont_b200.synth import materialize_model
+    path = materialize_model("rna002_5mer", models_dir)
+    sigs, seqs = _synth_batch(path, "rna002", 31, 60, 1400, 11, seed=4242)
+    single = aligners(path, "rna002").align_batch(sigs, seqs, True)
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    multi = MultiDeviceAligner(path, "rna002", devices=devices).align_batch(sigs, seqs, True)
+    for a, b in zip(single, multi):
+        assert a["Z"] == b["Z"] and np.array_equal(a["signal_positions"], b["signal_positions"])
+        assert np.array_equal(a["probabilities"], b["probabilities"])
