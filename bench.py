@@ -35,7 +35,7 @@ CONFIGS = {
     # c2 with a per-kmer sigma (what a trained model looks like): same kernels, the emission constants are per column anyway
     "c2v": ("rna004", "synthetic_rna004_9mer_varsd", 500, 5000, 30.0, "geometric", 100000),
     # config 4 (long-read stress): 50 kb reads of ~2 M samples, Gamma-4 dwell; 10 000 reads = 8 steps
-    "c4": ("rna004", "synthetic_rna004_9mer", 50000, 50000, 40.0, "gamma", 1280),
+    "c4": ("rna004", "synthetic_rna004_9mer", 50000, 50000, 40.0, "gamma", 2560),
     # config 5 (dynamont-train): one step = one pooled Baum-Welch iteration (expected counts of all reads, ONE all-reduce of
     # the 3*4^9+4 statistics over NCCL, M-step on the device); 1 M reads = 10 steps of 100 000 per GPU at 1 GPU
     "c5": ("rna004", "synthetic_rna004_9mer", 500, 5000, 30.0, "geometric", 100000),
@@ -383,44 +383,57 @@ def main():
         ar_ms.append(a0.elapsed_time(a1))
         return ok, kms, nl + 2, fb, rl
 
-    def step_device():
-        """One step: every batch through the C ABI with device-resident inputs.  Returns (#ok reads, kernel ms, launches)."""
-        if train:
-            return step_train()
-        ok, kms, nl, fb, rl = 0, 0.0, 0, 0, 0
-        rib = step_device.rib
-        for b in batches:
-            res, _, _, _ = al.align_packed(b["sig"].data_ptr(), b["sig_off"], b["bases"].data_ptr(), b["seq_off"],
-                                           not args.z_only, device=True)
-            tm = al.last_timing()
-            kms += tm["dp_ms"]
-            nl += tm["launches"]
-            fb += tm["log2_fallback_reads"]
-            rl += tm["lin_retry_reads"]
-            rib[0] += tm["ribbon_reads"]
-            rib[1] += tm["ribbon_faults"]
-            ok += sum(1 for i in range(b["sig_off"].size - 1) if res[i].status == 0)
-        return ok, kms, nl, fb, rl
+    from collections import deque
+    pending = deque()
+    acc = {"ok": 0, "kms": 0.0, "nl": 0, "fb": 0, "rl": 0}
 
-    dp_ms, launches, fallbacks, lin_retries = [], 0, 0, 0
+    def collect(item):
+        job, b = item
+        res, _, _, _ = al.wait(job)
+        tm = al.last_timing()
+        acc["kms"] += tm["dp_ms"]
+        acc["nl"] += tm["launches"]
+        acc["fb"] += tm["log2_fallback_reads"]
+        acc["rl"] += tm["lin_retry_reads"]
+        step_device.rib[0] += tm["ribbon_reads"]
+        step_device.rib[1] += tm["ribbon_faults"]
+        acc["ok"] += sum(1 for i in range(b["sig_off"].size - 1) if res[i].status == 0)
+
+    def step_device(drain=True):
+        """One step: every batch through the C ABI with device-resident inputs (dyn_align_submit_device / dyn_align_wait,
+        two batches in flight: the result copy + fan-out of a batch overlaps the kernels of the next).  The counters of the
+        completed batches accumulate in `acc`."""
+        if train:
+            ok, kms, nl, fb, rl = step_train()
+            acc["ok"] += ok; acc["kms"] += kms; acc["nl"] += nl; acc["fb"] += fb; acc["rl"] += rl
+            return
+        for b in batches:
+            pending.append((al.submit_packed(b["sig"].data_ptr(), b["sig_off"], b["bases"].data_ptr(), b["seq_off"],
+                                             not args.z_only, device=True), b))
+            if len(pending) >= 2:
+                collect(pending.popleft())
+        while drain and pending:
+            collect(pending.popleft())
+
     step_device.rib = [0, 0]
     for _ in range(args.warmup):
-        step_device()
+        step_device(True)
     step_device.rib = [0, 0]
+    for k_ in acc:
+        acc[k_] = 0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        n_ok, kms, nl, fb, rl_ = step_device()
-        lin_retries += rl_
-        dp_ms.append(kms)
-        launches += nl
-        fallbacks += fb
+    for i in range(args.steps):
+        step_device(i == args.steps - 1)
     ev1.record()
     barrier()
+    n_ok = acc["ok"] // args.steps
+    dp_ms = [acc["kms"] / args.steps]
+    launches, fallbacks, lin_retries = acc["nl"], acc["fb"], acc["rl"]
     ms = ev0.elapsed_time(ev1) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 

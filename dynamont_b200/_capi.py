@@ -32,7 +32,7 @@ EXPORTS = [
     "dyn_create", "dyn_destroy", "dyn_kmer_size", "dyn_num_kmers", "dyn_is_rna", "dyn_model", "dyn_set_model",
     "dyn_transitions", "dyn_count_segments", "dyn_read_cells", "dyn_batch_cells", "dyn_align_batch", "dyn_align_batch_f64",
     "dyn_align_batch_device", "dyn_train_batch", "dyn_status_message", "dyn_last_error", "dyn_last_timing",
-    "dyn_last_fallbacks", "dyn_last_lin_retries", "dyn_last_variant", "dyn_last_ribbon", "dyn_ribbon_fault_reasons", "dyn_align_submit", "dyn_align_wait", "dyn_train_accumulate", "dyn_train_mstep_device", "dyn_ntk_transitions", "dyn_ntk_prepass", "dyn_ntk_align", "dyn_ntk_align_batch", "dyn_preprocess_batch", "dyn_format_segments", "dyn_set_option", "dyn_set_stream",
+    "dyn_last_fallbacks", "dyn_last_lin_retries", "dyn_last_variant", "dyn_last_ribbon", "dyn_ribbon_fault_reasons", "dyn_align_submit", "dyn_align_submit_device", "dyn_align_wait", "dyn_train_accumulate", "dyn_train_mstep_device", "dyn_ntk_transitions", "dyn_ntk_prepass", "dyn_ntk_align", "dyn_ntk_align_batch", "dyn_preprocess_batch", "dyn_format_segments", "dyn_set_option", "dyn_set_stream",
 ]
 
 _libs: dict = {}
@@ -72,6 +72,8 @@ def load(path: str | None = None) -> C.CDLL:
     lib.dyn_align_batch_device.argtypes = [vp, C.c_void_p] + common
     lib.dyn_align_submit.argtypes = [vp, C.c_void_p] + common
     lib.dyn_align_submit.restype = C.c_int64
+    lib.dyn_align_submit_device.argtypes = [vp, C.c_void_p] + common
+    lib.dyn_align_submit_device.restype = C.c_int64
     lib.dyn_align_wait.argtypes = [vp, C.c_int64]
     lib.dyn_train_accumulate.argtypes = [vp, C.c_void_p, u64p, C.c_void_p, u64p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
     lib.dyn_train_mstep_device.argtypes = [vp, C.c_void_p, f64p]

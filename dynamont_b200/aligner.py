@@ -123,7 +123,8 @@ class Aligner:
         return res, seqpos, sigpos, prob
 
     # ---- asynchronous batches (dyn_align_submit / dyn_align_wait) -------------------------------------------------
-    def submit_packed(self, signal_ptr: int, sig_off, seq_ptr: int, seq_off, calc_probabilities: bool = True, keep=None):
+    def submit_packed(self, signal_ptr: int, sig_off, seq_ptr: int, seq_off, calc_probabilities: bool = True, keep=None,
+                      device: bool = False):
         """Start a batch of HOST-resident reads (float32 samples at ``signal_ptr``, ASCII bases at ``seq_ptr``) on one of
         the handle's two lanes and return a job; ``wait(job)`` returns what ``align_packed`` returns.  With two jobs in
         flight the copies and the result fan-out of neighbouring batches overlap the kernels.  ``keep``: any object that
@@ -136,7 +137,8 @@ class Aligner:
         seqpos = np.empty(max(nseg, 1), dtype=np.uint64)
         sigpos = np.empty(max(nseg, 1), dtype=np.uint64)
         prob = np.empty(max(nseg, 1), dtype=np.float64)
-        ticket = self._lib.dyn_align_submit(self._h, C.c_void_p(signal_ptr), sig_off.ctypes.data_as(u64p), C.c_void_p(seq_ptr),
+        fn = self._lib.dyn_align_submit_device if device else self._lib.dyn_align_submit
+        ticket = fn(self._h, C.c_void_p(signal_ptr), sig_off.ctypes.data_as(u64p), C.c_void_p(seq_ptr),
                                             seq_off.ctypes.data_as(u64p), n, int(calc_probabilities), res,
                                             seqpos.ctypes.data_as(u64p), sigpos.ctypes.data_as(u64p), prob.ctypes.data_as(f64p))
         if ticket < 0:

@@ -1866,8 +1866,8 @@ static dyn_aligner* lane_of(dyn_aligner* A, int64_t ticket)
 	return A->lane[li];
 }
 
-int64_t dyn_align_submit(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
-	uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
+static int64_t submit_impl(dyn_aligner* A, bool on_device, const float* signal, const uint64_t* sig_off, const char* seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
 	uint64_t* signal_positions, double* probabilities)
 {
 	try
@@ -1879,8 +1879,11 @@ int64_t dyn_align_submit(dyn_aligner* A, const float* signal, const uint64_t* si
 		A->jobs.push_back(j);
 		// the lane's own mutex serialises the calls that share it; the caller's buffers must stay valid until dyn_align_wait
 		j->th = std::thread([=]() {
-			j->rc = dyn_align_batch(l, signal, sig_off, seq, seq_off, n_reads, calc_probabilities, results, sequence_positions,
-				signal_positions, probabilities);
+			j->rc = on_device
+				? dyn_align_batch_device(l, signal, sig_off, seq, seq_off, n_reads, calc_probabilities, results, sequence_positions,
+					  signal_positions, probabilities)
+				: dyn_align_batch(l, signal, sig_off, seq, seq_off, n_reads, calc_probabilities, results, sequence_positions,
+					  signal_positions, probabilities);
 		});
 		return ticket;
 	}
@@ -1889,6 +1892,22 @@ int64_t dyn_align_submit(dyn_aligner* A, const float* signal, const uint64_t* si
 		A->last_error = e.what();
 		return -1;
 	}
+}
+
+int64_t dyn_align_submit(dyn_aligner* A, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
+	uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
+	uint64_t* signal_positions, double* probabilities)
+{
+	return submit_impl(A, false, signal, sig_off, seq, seq_off, n_reads, calc_probabilities, results, sequence_positions,
+		signal_positions, probabilities);
+}
+
+int64_t dyn_align_submit_device(dyn_aligner* A, const float* d_signal, const uint64_t* sig_off, const char* d_seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
+	uint64_t* signal_positions, double* probabilities)
+{
+	return submit_impl(A, true, d_signal, sig_off, d_seq, seq_off, n_reads, calc_probabilities, results, sequence_positions,
+		signal_positions, probabilities);
 }
 
 int dyn_align_wait(dyn_aligner* A, int64_t ticket)
@@ -1904,10 +1923,22 @@ int dyn_align_wait(dyn_aligner* A, int64_t ticket)
 		if (j->th.joinable()) j->th.join();
 		j->joined = true;
 	}
-	if (j->rc != 0)
+	dyn_aligner* l = A->lane[ticket % dyn_aligner::LANES];
+	if (j->rc != 0) A->last_error = l ? l->last_error : "dyn_align_wait: job failed";
+	else if (l)
 	{
-		dyn_aligner* l = A->lane[ticket % dyn_aligner::LANES];
-		A->last_error = l ? l->last_error : "dyn_align_wait: job failed";
+		// what dyn_last_timing / dyn_last_ribbon / dyn_last_fallbacks report after a wait: the lane's last batch
+		std::lock_guard<std::mutex> g(l->mu);
+		A->timing[0] = l->timing[0]; A->timing[1] = l->timing[1]; A->timing[2] = l->timing[2];
+		A->n_ribbon = l->n_ribbon; A->n_rib_fault = l->n_rib_fault; A->n_fallback = l->n_fallback; A->n_retry_lin = l->n_retry_lin;
+		A->last_variant = l->last_variant;
+		for (int i = 0; i < 16; ++i)
+		{
+			A->rib_reason[i] += l->rib_reason[i];
+			l->rib_reason[i] = 0;
+		}
+		A->rib_recs_used = l->rib_recs_used;
+		A->rib_last_two_level = l->rib_last_two_level;
 	}
 	return j->rc;
 }

@@ -193,6 +193,10 @@ int dyn_train_mstep_device(dyn_aligner*, const double* d_stats, double* transiti
 int64_t dyn_align_submit(dyn_aligner*, const float* signal, const uint64_t* sig_off, const char* seq, const uint64_t* seq_off,
 	uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
 	uint64_t* signal_positions, double* probabilities);
+/* the same with the samples and bases already resident in device memory (cf. dyn_align_batch_device) */
+int64_t dyn_align_submit_device(dyn_aligner*, const float* d_signal, const uint64_t* sig_off, const char* d_seq,
+	const uint64_t* seq_off, uint32_t n_reads, int calc_probabilities, dyn_read_result* results, uint64_t* sequence_positions,
+	uint64_t* signal_positions, double* probabilities);
 int dyn_align_wait(dyn_aligner*, int64_t ticket);
 
 /* instrumentation for bench.py: device time (ms, CUDA events on the launching stream) of the kernels of the
