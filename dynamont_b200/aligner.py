@@ -124,19 +124,24 @@ class Aligner:
 
     # ---- asynchronous batches (dyn_align_submit / dyn_align_wait) -------------------------------------------------
     def submit_packed(self, signal_ptr: int, sig_off, seq_ptr: int, seq_off, calc_probabilities: bool = True, keep=None,
-                      device: bool = False):
+                      device: bool = False, out=None):
         """Start a batch of HOST-resident reads (float32 samples at ``signal_ptr``, ASCII bases at ``seq_ptr``) on one of
         the handle's two lanes and return a job; ``wait(job)`` returns what ``align_packed`` returns.  With two jobs in
         flight the copies and the result fan-out of neighbouring batches overlap the kernels.  ``keep``: any object that
-        owns the input memory (kept alive until the job is waited for)."""
+        owns the input memory (kept alive until the job is waited for).  ``out``: optional (results, sequence_positions,
+        signal_positions, probabilities) buffers of a previous, completed job to write into (a streaming caller rotates a
+        few sets instead of allocating — and page-faulting — fresh result arrays for every batch)."""
         sig_off = np.ascontiguousarray(sig_off, dtype=np.uint64)
         seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
         n = sig_off.size - 1
-        res = (ReadResult * max(n, 1))()
         nseg = int(self._lib.dyn_count_segments(self._h, seq_off.ctypes.data_as(u64p), n))
-        seqpos = np.empty(max(nseg, 1), dtype=np.uint64)
-        sigpos = np.empty(max(nseg, 1), dtype=np.uint64)
-        prob = np.empty(max(nseg, 1), dtype=np.float64)
+        if out is not None and len(out[0]) >= max(n, 1) and out[1].size >= max(nseg, 1):
+            res, seqpos, sigpos, prob = out
+        else:
+            res = (ReadResult * max(n, 1))()
+            seqpos = np.empty(max(nseg, 1), dtype=np.uint64)
+            sigpos = np.empty(max(nseg, 1), dtype=np.uint64)
+            prob = np.empty(max(nseg, 1), dtype=np.float64)
         fn = self._lib.dyn_align_submit_device if device else self._lib.dyn_align_submit
         ticket = fn(self._h, C.c_void_p(signal_ptr), sig_off.ctypes.data_as(u64p), C.c_void_p(seq_ptr),
                                             seq_off.ctypes.data_as(u64p), n, int(calc_probabilities), res,

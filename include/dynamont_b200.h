@@ -60,7 +60,7 @@ typedef struct
 
 /* Replaces PyAligner's constructor / makeAligner (aligner_bindings.cpp:34-51,111-130) and
  * Aligner::Aligner (aligner.cpp:13-36).  pore: "rna002" | "rna004" | "dna_r9" | "dna_r10_260bps" |
- * "dna_r10_400bps"; mode: "basic" | "nt" (resquiggle/ntk: not built yet -> error); threads is accepted and
+ * "dna_r10_400bps"; mode: "basic" | "nt" -> NTAligner, "resquiggle" | "ntk" -> NTKAligner (served by dyn_ntk_align*); threads is accepted and
  * ignored exactly like the reference; band as in the reference (default 400);
  * device = CUDA ordinal or -1 for the current device.  Returns NULL and fills err on failure; err_kind is
  * set to 1 for the reference's std::invalid_argument cases (-> ValueError), 0 for runtime_error. */

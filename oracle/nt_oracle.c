@@ -7,7 +7,7 @@
  * /root/reference). It is written in (t, n) lattice coordinates with an explicit
  * per-row window instead of the reference's shifted band storage, but performs the
  * same floating-point operations in the same order, so results are bit-identical
- * (pinned against the compiled reference by tests/test_oracle_vs_reference.py and
+ * (pinned against the compiled reference by tests/test_oracle.py and
  * against tests/golden/*.npz which were produced by the compiled reference).
  *
  * PARITY PIN: the reference's own tests hold no golden vector for this path
