@@ -15,7 +15,7 @@ HDR = [os.path.join(CSRC, f) for f in ("dp_common.cuh", "dp_kernels.cuh", "dp_li
       [os.path.join(HERE, "..", "include", "dynamont_b200.h")]
 # translation units -> the headers each one depends on (beyond HDR); compiled in parallel, each only when stale
 UNITS = {
-    "engine.cu": [os.path.join(CSRC, "ntk_kernels.cuh")],
+    "engine.cu": [os.path.join(CSRC, "ntk_kernels.cuh"), os.path.join(CSRC, "ntk_prepass.cuh")],
     "ribbon.cu": [os.path.join(CSRC, "dp_ribbon.cuh")],
 }
 OBJDIR = os.path.join(CSRC, "_obj")

@@ -8,6 +8,7 @@
 #include "dp_kernels.cuh"
 #include "dp_linear.cuh"
 #include "ntk_kernels.cuh"
+#include "ntk_prepass.cuh"
 #include "ribbon.h"
 
 #include <algorithm>
@@ -2278,7 +2279,7 @@ namespace
 // device state of one resquiggle-mode read between the pre-pass and the sparse stages
 struct NtkRun
 {
-	DevBuf b_model, b_sig, b_kmers, b_lat, b_z, b_tn, b_tk, b_cnt, b_keys, b_sparse, b_seg;
+	DevBuf b_model, b_sig, b_kmers, b_lat, b_rows, b_z, b_tn, b_tk, b_cnt, b_keys, b_sparse, b_seg;
 	uint32_t T = 0, N = 0, K = 0, hp = 1, wn = 0, wk = 0;
 	uint64_t Kc = 0, total = 0;
 	double z[4] = {0, 0, 0, 0};
@@ -2286,7 +2287,7 @@ struct NtkRun
 	dyn::ntk::Consts consts;
 	void release(Rt& rt)
 	{
-		for (DevBuf* b : {&b_model, &b_sig, &b_kmers, &b_lat, &b_z, &b_tn, &b_tk, &b_cnt, &b_keys, &b_sparse, &b_seg}) b->release(rt);
+		for (DevBuf* b : {&b_model, &b_sig, &b_kmers, &b_lat, &b_rows, &b_z, &b_tn, &b_tk, &b_cnt, &b_keys, &b_sparse, &b_seg}) b->release(rt);
 	}
 };
 
@@ -2331,7 +2332,9 @@ int ntk_prepass_device(dyn_aligner* A, Rt& rt, const float* signal, uint64_t S, 
 	KmerModel* d_model = (KmerModel*)R.b_model.get(rt, K * sizeof(KmerModel));
 	double* d_sig = (double*)R.b_sig.get(rt, S * 8);
 	int32_t* d_kmers = (int32_t*)R.b_kmers.get(rt, Kc * 4);
-	double* d_lat = (double*)R.b_lat.get(rt, (size_t)5 * T * C * 8);
+	// forward lattice (M, E) + log posteriors: 3 x T x C doubles; two backward rows; per-row maxima and scales
+	double* d_lat = (double*)R.b_lat.get(rt, ((size_t)3 * T * C + 4 * C) * 8);
+	unsigned char* d_rows = (unsigned char*)R.b_rows.get(rt, (size_t)T * 24 + 64);
 	double* d_z = (double*)R.b_z.get(rt, 4 * 8);
 	uint32_t* d_tn = (uint32_t*)R.b_tn.get(rt, (size_t)T * wn * 4);
 	uint32_t* d_tk = (uint32_t*)R.b_tk.get(rt, (size_t)T * wk * 4);
@@ -2339,40 +2342,67 @@ int ntk_prepass_device(dyn_aligner* A, Rt& rt, const float* signal, uint64_t S, 
 	rt.h2d(d_model, km.data(), K * sizeof(KmerModel));
 	rt.h2d(d_sig, sig.data(), S * 8);
 	rt.h2d(d_kmers, kmers.data(), Kc * 4);
-	PrepassArgs pa;
-	pa.signal = d_sig; pa.kmers = d_kmers; pa.T = T; pa.N = N; pa.K = K; pa.hp = hp;
-	pa.c.model = d_model;
-	pa.c.half_log_2pi = 0.5 * std::log(2.0 * M_PI);
+	Consts cc;
+	cc.model = d_model;
+	cc.half_log_2pi = 0.5 * std::log(2.0 * M_PI);
+	cc.m = A->ntk_trans[16];
+	cc.e = A->ntk_trans[17];
 	// SPARSETHRESHOLD (NTK_aligner_api.cpp:17): the literal the reference ships, commented there as log(0.95)
 	// but numerically log10(0.95), i.e. a posterior mass of 0.97797
 	const double threshold = -0.02227639471;
 	const double EPS = 1e-8;
 	double* z = R.z;
+	// one dense pre-pass (ntk_prepass.cuh): forward lattice, backward rows + log posteriors, Zf / Zb
+	auto prepass = [&](int tk, uint32_t cols, double log_m, double log_e, double* zout) {
+		PreArgs pa;
+		pa.signal = d_sig; pa.kmers = d_kmers; pa.model = d_model; pa.half_log_2pi = cc.half_log_2pi;
+		pa.m = std::exp(log_m); pa.e = std::exp(log_e);
+		pa.T = T; pa.C = cols; pa.hp = hp; pa.tk = tk;
+		pa.fM = d_lat; pa.fE = d_lat + (size_t)T * cols; pa.LP = d_lat + (size_t)2 * T * cols; pa.brow = d_lat + (size_t)3 * T * cols;
+		pa.fmax = (unsigned long long*)d_rows; pa.bmax = pa.fmax + T;
+		pa.fexp = (int*)(pa.bmax + T); pa.bexp = pa.fexp + T;
+		pa.z = zout;
+		rt.zero(d_rows, (size_t)T * 24);
+		const uint32_t work = tk ? hp : cols;  // independent work items per row
+		if (work < 4096)
+		{
+			// small lattice: one CTA per direction walks the rows (reads are batched across streams)
+			k_pre_forward_cta<<<1, 1024, 0, rt.stream>>>(pa);
+			k_pre_backward_cta<<<1, 1024, 0, rt.stream>>>(pa);
+		}
+		else
+		{
+			// large lattice (9-mers: 65 536 work items, 262 144 cells per row): one launch per row over the whole GPU
+			const unsigned grid = (unsigned)std::min<uint32_t>((work + 255) / 256, (uint32_t)rt.sms * 8);
+			k_pre_init<<<grid, 256, 0, rt.stream>>>(pa, 1);
+			for (uint32_t t = 1; t < T; ++t) k_pre_forward_row<<<grid, 256, 0, rt.stream>>>(pa, t);
+			k_pre_init<<<grid, 256, 0, rt.stream>>>(pa, 0);
+			for (uint32_t t = T - 1; t-- > 0;) k_pre_backward_row<<<grid, 256, 0, rt.stream>>>(pa, t);
+		}
+		k_pre_z<<<2, 1024, 0, rt.stream>>>(pa);
+		CK_CUDA(cudaGetLastError());
+		return pa.LP;
+	};
 	// ---- TN (preProcTN, NTK:315-354)
-	pa.c.m = A->ntk_trans[14]; pa.c.e = A->ntk_trans[15];
-	pa.fM = d_lat; pa.fE = d_lat + (size_t)T * N; pa.bM = d_lat + (size_t)2 * T * N; pa.bE = d_lat + (size_t)3 * T * N;
-	pa.LP = d_lat + (size_t)4 * T * N; pa.z = d_z;
-	k_tn_fill<<<2, 1024, 0, rt.stream>>>(pa);
-	CK_CUDA(cudaGetLastError());
-	rt.d2h(z, d_z, 16);
-	rt.sync();
-	if (std::abs(z[0] - z[1]) / (double)((size_t)T * N) > EPS || std::isinf(z[0]) || std::isinf(z[1])) return DYN_NTK_TN_FAILED;
-	k_dense_logp<<<(unsigned)std::min<size_t>(((size_t)T * N + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * N, z[0]);  // Zf (NTK:336)
-	k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, N, wn, d_tn, threshold);
-	CK_CUDA(cudaGetLastError());
-	rt.sync();
+	{
+		const double* lp = prepass(0, N, A->ntk_trans[14], A->ntk_trans[15], d_z);
+		rt.d2h(z, d_z, 16);
+		rt.sync();
+		if (std::abs(z[0] - z[1]) / (double)((size_t)T * N) > EPS || std::isinf(z[0]) || std::isinf(z[1]) || std::isnan(z[0]) || std::isnan(z[1])) return DYN_NTK_TN_FAILED;
+		// LP = logP - Zf (NTK:336): folded into the threshold of the selection
+		k_row_mask<<<T, 256, 0, rt.stream>>>(lp, N, wn, d_tn, threshold + z[0]);
+		CK_CUDA(cudaGetLastError());
+		rt.sync();
+	}
 	// ---- TK (preProcTK, NTK:356-400)
-	pa.c.m = A->ntk_trans[16]; pa.c.e = A->ntk_trans[17];
-	pa.fM = d_lat; pa.fE = d_lat + (size_t)T * K; pa.bM = d_lat + (size_t)2 * T * K; pa.bE = d_lat + (size_t)3 * T * K;
-	pa.LP = d_lat + (size_t)4 * T * K; pa.z = d_z + 2;
-	k_tk_fill<<<2, 1024, 0, rt.stream>>>(pa);
-	CK_CUDA(cudaGetLastError());
-	rt.d2h(z + 2, d_z + 2, 16);
-	rt.sync();
-	if (std::abs(z[2] - z[3]) / (double)((size_t)T * K) > EPS || std::isinf(z[2]) || std::isinf(z[3])) return DYN_NTK_TK_FAILED;
-	k_dense_logp<<<(unsigned)std::min<size_t>(((size_t)T * K + 255) / 256, 4096), 256, 0, rt.stream>>>(pa, (size_t)T * K, z[3]);  // Zb (NTK:382)
-	k_row_mask<<<T, 256, 0, rt.stream>>>(pa.LP, K, wk, d_tk, threshold);
-	CK_CUDA(cudaGetLastError());
+	{
+		const double* lp = prepass(1, K, A->ntk_trans[16], A->ntk_trans[17], d_z + 2);
+		rt.d2h(z + 2, d_z + 2, 16);
+		rt.sync();
+		if (std::abs(z[2] - z[3]) / (double)((size_t)T * K) > EPS || std::isinf(z[2]) || std::isinf(z[3]) || std::isnan(z[2]) || std::isnan(z[3])) return DYN_NTK_TK_FAILED;
+		k_row_mask<<<T, 256, 0, rt.stream>>>(lp, K, wk, d_tk, threshold + z[3]);  // Zb (NTK:382)
+		CK_CUDA(cudaGetLastError());
+	}
 	// ---- keys (preProcTNK, NTK:402-441)
 	KeyArgs ka;
 	ka.tn = d_tn; ka.tk = d_tk; ka.kmers = d_kmers; ka.T = T; ka.N = N; ka.K = K; ka.wn = wn; ka.wk = wk;
@@ -2397,7 +2427,7 @@ int ntk_prepass_device(dyn_aligner* A, Rt& rt, const float* signal, uint64_t S, 
 	if (total) k_keys<true><<<(T + 127) / 128, 128, 0, rt.stream>>>(ka);
 	CK_CUDA(cudaGetLastError());
 	rt.sync();
-	R.consts = pa.c;
+	R.consts = cc;
 	return 0;
 }
 

@@ -2,12 +2,10 @@
 // kmer x signal (TK) two-state HMMs, their posterior-mass row masks and the sorted key list of the sparse
 // 5-state lattice (reference NTK_aligner_api.cpp:120-441).
 //
-// First correct CUDA path of this mode: FP64 log-space arithmetic that mirrors the reference operation by operation
-// (same association order, --fmad=false), one CTA per read with the lattice rows processed in sequence and the
-// columns spread over the threads; the four lattice arrays live in HBM (T x C doubles each).  The row masks are
-// what the sparse stages consume, so they are the parity surface of this file: membership is decided by a
-// descending stable selection with a sequential log-sum-exp, exactly like columnArgsort + the insertion loop of
-// preProcTN / preProcTK (:315-400).
+// The dense pre-passes themselves live in ntk_prepass.cuh (FP64 linear domain with per-row scaling).  This file holds the
+// shared helpers, the row-mask selection, the key list and the sparse 5-state stages.  The row masks are what the
+// sparse stages consume, so they are the parity surface: membership is decided by a descending stable selection with a
+// sequential log-sum-exp, with the semantics of columnArgsort + the insertion loop of preProcTN / preProcTK (:315-400).
 #pragma once
 
 #include "dp_common.cuh"
@@ -55,154 +53,6 @@ __device__ __forceinline__ double score_kmer(const Consts& c, double x, uint32_t
 	const double diff = x - km.mean;
 	const double z = diff / km.stdev;
 	return -0.5 * z * z - km.log_stdev - c.half_log_2pi;
-}
-
-struct PrepassArgs
-{
-	const double* signal;  // [S]
-	const int32_t* kmers;  // [N-1] kmer id of column n is kmers[n-1]
-	uint32_t T, N, K, hp;  // hp = 4^(k-1)
-	Consts c;
-	double *fM, *fE, *bM, *bE;  // [T][C], C = N (TN) or K (TK)
-	double* LP;                 // [T][C]
-	double* z;                  // [2] Zf, Zb
-};
-
-// ---- TN pre-pass (ppForTN / ppBackTN, NTK:197-251): dense T x N, no band ------------------------------------
-// grid = 2 CTAs: block 0 runs the forward recurrence, block 1 the backward one (they are independent)
-__global__ void __launch_bounds__(1024) k_tn_fill(PrepassArgs a)
-{
-	const uint32_t T = a.T, N = a.N;
-	const double NI = neg_inf();
-	const bool fwd = (blockIdx.x == 0);
-	{
-		double* M = fwd ? a.fM : a.bM;
-		double* E = fwd ? a.fE : a.bE;
-		for (size_t i = threadIdx.x; i < (size_t)T * N; i += blockDim.x)
-		{
-			M[i] = NI;
-			E[i] = NI;
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) E[fwd ? 0 : (size_t)T * N - 1] = 0.0;
-		__syncthreads();
-	}
-	if (fwd)
-	for (uint32_t t = 1; t < T; ++t)
-	{
-		const double x = a.signal[t - 1];
-		const double* pM = a.fM + (size_t)(t - 1) * N;
-		const double* pE = a.fE + (size_t)(t - 1) * N;
-		double* cM = a.fM + (size_t)t * N;
-		double* cE = a.fE + (size_t)t * N;
-		for (uint32_t n = 1 + threadIdx.x; n < N; n += blockDim.x)
-		{
-			const double sc = score_kmer(a.c, x, (uint32_t)a.kmers[n - 1]);
-			cM[n] = pE[n - 1] + sc + a.c.m;
-			cE[n] = log_plus(pM[n] + sc, pE[n] + sc + a.c.e);
-		}
-		__syncthreads();
-	}
-	else
-	for (uint32_t t = T - 1; t-- > 0;)
-	{
-		const double x = a.signal[t];
-		const double* nM = a.bM + (size_t)(t + 1) * N;
-		const double* nE = a.bE + (size_t)(t + 1) * N;
-		double* cM = a.bM + (size_t)t * N;
-		double* cE = a.bE + (size_t)t * N;
-		for (uint32_t n = threadIdx.x; n < N; n += blockDim.x)
-		{
-			double ext = NI;
-			if (n + 1 < N) ext = nM[n + 1] + score_kmer(a.c, x, (uint32_t)a.kmers[n]) + a.c.m;
-			if (n > 0)
-			{
-				const double sc = score_kmer(a.c, x, (uint32_t)a.kmers[n - 1]);
-				cM[n] = nE[n] + sc;
-				ext = log_plus(ext, nE[n] + sc + a.c.e);
-			}
-			cE[n] = ext;
-		}
-		__syncthreads();
-	}
-	if (threadIdx.x == 0)
-	{
-		if (fwd) a.z[0] = a.fE[(size_t)T * N - 1];  // Zf (NTK:328)
-		else a.z[1] = a.bE[0];                      // Zb (NTK:329)
-	}
-}
-
-// ---- TK pre-pass (ppForTK / ppBackTK, NTK:253-313): two-state HMM over the de-Bruijn graph of all K kmers ----
-// grid = 2 CTAs: block 0 forward, block 1 backward
-__global__ void __launch_bounds__(1024) k_tk_fill(PrepassArgs a)
-{
-	const uint32_t T = a.T, K = a.K, hp = a.hp;
-	const double NI = neg_inf();
-	const bool fwd = (blockIdx.x == 0);
-	{
-		double* M = fwd ? a.fM : a.bM;
-		double* E = fwd ? a.fE : a.bE;
-		for (size_t i = threadIdx.x; i < (size_t)T * K; i += blockDim.x)
-		{
-			M[i] = NI;
-			E[i] = NI;
-		}
-		__syncthreads();
-		for (uint32_t k = threadIdx.x; k < K; k += blockDim.x) E[(fwd ? 0 : (size_t)(T - 1) * K) + k] = 0.0;
-		__syncthreads();
-	}
-	if (fwd)
-	for (uint32_t t = 1; t < T; ++t)
-	{
-		const double x = a.signal[t - 1];
-		const double* pM = a.fM + (size_t)(t - 1) * K;
-		const double* pE = a.fE + (size_t)(t - 1) * K;
-		double* cM = a.fM + (size_t)t * K;
-		double* cE = a.fE + (size_t)t * K;
-		for (uint32_t k = threadIdx.x; k < K; k += blockDim.x)
-		{
-			double mat = NI;
-			const double sc = score_kmer(a.c, x, k);
-			for (uint32_t pre = k / 4; pre < K; pre += hp) mat = log_plus(mat, pE[pre] + sc + a.c.m);  // predecessorKmer(k, j)
-			cM[k] = mat;
-			cE[k] = log_plus(pM[k] + sc, pE[k] + sc + a.c.e);
-		}
-		__syncthreads();
-	}
-	else
-	for (uint32_t t = T - 1; t-- > 0;)
-	{
-		const double x = a.signal[t];
-		const double* nM = a.bM + (size_t)(t + 1) * K;
-		const double* nE = a.bE + (size_t)(t + 1) * K;
-		double* cM = a.bM + (size_t)t * K;
-		double* cE = a.bE + (size_t)t * K;
-		for (uint32_t k = threadIdx.x; k < K; k += blockDim.x)
-		{
-			double ext = NI;
-			const uint32_t s0 = (k % hp) * 4;  // successorKmer(k, 0)
-			for (uint32_t suc = s0; suc < s0 + 4; ++suc) ext = log_plus(ext, nM[suc] + score_kmer(a.c, x, suc) + a.c.m);
-			const double sc = score_kmer(a.c, x, k);
-			cM[k] = nE[k] + sc;
-			cE[k] = log_plus(ext, nE[k] + sc + a.c.e);
-		}
-		__syncthreads();
-	}
-	if (threadIdx.x == 0)
-	{
-		// sequential log-sum-exp in the reference's order (NTK:372-376)
-		double Z = NI;
-		const size_t TK = (size_t)T * K;
-		for (uint32_t k = 0; k < K; ++k) Z = log_plus(Z, fwd ? a.fE[TK - 1 - k] : a.bE[k]);
-		a.z[fwd ? 0 : 1] = Z;
-	}
-}
-
-// dense logP (NTK:179-195): LP = logPlus(fM + bM - Z, fE + bE - Z)
-__global__ void k_dense_logp(PrepassArgs a, size_t size, double Z)
-{
-	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (size_t)gridDim.x * blockDim.x)
-		a.LP[i] = log_plus(a.fM[i] + a.bM[i] - Z, a.fE[i] + a.bE[i] - Z);
 }
 
 // Row masks (NTK:343-353, 389-399): take the columns of row t in order of LP descending (stable: ties -> smaller
