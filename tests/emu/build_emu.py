@@ -15,6 +15,8 @@ DEPS = [os.path.join(CSRC, f) for f in ("engine.cu", "dp_common.cuh", "dp_kernel
 
 
 def build(force: bool = False) -> str:
+    if os.environ.get("DYN_EMU_LIB"):  # tools/emu_asan.sh: a sanitizer build of the same sources
+        return os.environ["DYN_EMU_LIB"]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)

@@ -28,6 +28,12 @@ CASES = [  # name, pore, model, length, spb, seed, want end-to-end
     # config 3 is 9-mer: one polyA-prefixed 9-mer read WITH an end-to-end alignment (reference: ~25 s, 1.7 GB for T ~ 150)
     ("ntk_rna004_9mer_polyA", "rna004", "synthetic_rna004_9mer", 24, 9, 205, True),
 ]
+# a 9-mer read at T ~ 1000 (the dense TK lattice alone is 5 x 1000 x 262144 doubles = 10.5 GB in the reference, minutes of
+# CPU): written to its own file by `python tools/make_golden_ntk.py big`
+BIG = [("ntk_rna004_9mer_T1000", "rna004", "synthetic_rna004_9mer", 90, 12, 206, True)]
+OUT_NAME = "ntk_golden.npz"
+if len(sys.argv) > 1 and sys.argv[1] == "big":
+    CASES, OUT_NAME = BIG, "ntk_golden_9mer_T1000.npz"
 
 
 def csr(mask):
@@ -64,5 +70,5 @@ for name, pore, model, L, spb, seed, e2e in CASES:
         out[name + "/polishes"] = np.array(a["polishes"])
         msg += " align Z=%.6f segments=%d" % (a["Z"], len(a["states"]))
     print(name, msg)
-np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ntk_golden.npz"), **out)
-print("written", os.path.getsize(os.path.join(ROOT, "tests", "golden", "ntk_golden.npz")), "bytes")
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", OUT_NAME), **out)
+print("written", os.path.getsize(os.path.join(ROOT, "tests", "golden", OUT_NAME)), "bytes")
