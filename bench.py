@@ -154,13 +154,17 @@ def gen_reads_torch(cfg, n, seed, device):
 _W = {}
 
 
-def _cpu_init(model_path, pore, kind):
+def _cpu_init(model_path, pore, kind, train=False):
     import oracle
     _W["al"] = oracle.Reference(model_path, pore) if kind == "reference" else oracle.Oracle(model_path, pore)
+    _W["train"] = train
 
 
 def _cpu_align(item):
     sig, seq = item
+    if _W.get("train"):
+        # config 5: the reference's per-read Baum-Welch (NTAligner::train, NT:567-639), what dynamont-train's workers run
+        return len(_W["al"].train(sig, seq)["emission_model"]["mean"])
     r = _W["al"].align(sig, seq, True)
     return len(r["signal_positions"])
 
@@ -184,11 +188,11 @@ def cpu_pool_plan(cfg, sample):
     return kind, procs, sample
 
 
-def run_cpu_sample(cfg, kind, procs, reads, model_path):
-    """Wall time of aligning `reads` with `procs` single-threaded worker processes (segment.py:304-324 shape)."""
+def run_cpu_sample(cfg, kind, procs, reads, model_path, train=False):
+    """Wall time of aligning (training on) `reads` with `procs` single-threaded worker processes (segment.py:304-324 shape)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    with ctx.Pool(procs, initializer=_cpu_init, initargs=(model_path, cfg[0], kind)) as pool:
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(model_path, cfg[0], kind, train)) as pool:
         pool.map(_cpu_align, reads[:procs], chunksize=1)  # construct aligners / warm caches (untimed)
         t0 = time.perf_counter()
         list(pool.imap_unordered(_cpu_align, reads, chunksize=1))
@@ -278,7 +282,7 @@ def main():
             _parent_handle = oracle.Reference(model_path, pore)  # noqa: F841
         times = []
         for i in range(args.warmup + args.steps):
-            dt = run_cpu_sample(cfg, kind, procs, reads, model_path)
+            dt = run_cpu_sample(cfg, kind, procs, reads, model_path, train)
             if i >= args.warmup:
                 times.append(dt)
         dt = float(np.mean(times))
@@ -291,7 +295,7 @@ def main():
             "config": {"workload": workload, "reads_per_step": len(reads), "cells_per_step": int(cells)},
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": procs, "kind": kind,
                              "sample": f"{len(reads)} reads of the workload per step, one single-threaded process per core "
-                                       f"({procs} processes), align(calc_probabilities=True)",
+                                       f"({procs} processes), " + ("train()" if train else "align(calc_probabilities=True)"),
                              "reads_per_s": len(reads) / dt},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
@@ -305,7 +309,7 @@ def main():
             kind, procs, sample = cpu_pool_plan(cfg, args.cpu_sample)
             model_path, reads = gen_reads_numpy(cfg, sample, args.seed + 17)
             cells = cells_of(reads, model_path, pore)
-            dt = run_cpu_sample(cfg, kind, procs, reads, model_path)
+            dt = run_cpu_sample(cfg, kind, procs, reads, model_path, train)
             cpu_baseline = {"value": cells / dt / 1e9, "unit": "GCUPS", "cores": procs, "kind": kind,
                             "sample": f"{len(reads)} reads of the workload, one single-threaded process per core "
                                       f"({procs} processes), align(calc_probabilities=True), {dt:.1f} s wall",
