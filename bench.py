@@ -41,6 +41,11 @@ CONFIGS = {
     "c5": ("rna004", "synthetic_rna004_9mer", 500, 5000, 30.0, "geometric", 100000),
 }
 TRAIN_CONFIGS = {"c5"}
+# config 3 (resquiggle / NTK mode with kmer polishing): its own code path and its own unit (run_ntk below).  The 9-mer
+# pore needs the dense T x 4^9 pre-pass: reads of ~60 bases at 12.5 samples/base (T ~ 750) are what fits a line that ends
+# in minutes; the 5-mer line beside it uses realistic 1 kb reads.  The reference throws for every input in this mode
+# (SURVEY.md F2); its repaired build needs ~4 min and 10 GB for ONE such 9-mer read, so no CPU arm is run here.
+NTK_CONFIGS = {"c3"}
 MODELS_DIR = os.path.join(ROOT, "tests", "golden", "_models")
 
 
@@ -67,7 +72,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + sorted(NTK_CONFIGS))
     ap.add_argument("--em-iterations", type=int, default=0, help="c5: (unused; every step is one EM iteration)")
     ap.add_argument("--reads", type=int, default=0, help="reads per step per GPU (0 = config default)")
     ap.add_argument("--batch", type=int, default=20000, help="reads per C-ABI call (a step runs ceil(reads/batch) calls)")
@@ -256,8 +261,68 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def run_ntk(args):
+    """--config c3: resquiggle mode, dyn_ntk_align_batch (pre-passes + sparse 5-state stages, reads on a pool of CUDA streams).
+    Unit of work: dense pre-pass cells T*N + T*K per read (never mixed with basic-mode GCUPS)."""
+    import torch
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import PORE_INFO, materialize_model, native_model, synth_read
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lines = {}
+    for tag, pore, model, length, spb, n in (("k9", "rna004", "synthetic_rna004_9mer", 60, 12.5, args.reads or 32),
+                                             ("k5", "dna_r9", "rna004_5mer", 1000, 12.5, args.reads or 32)):
+        path = materialize_model(model, MODELS_DIR)
+        nm, ns = native_model(path, pore)
+        k = PORE_INFO[pore][1]
+        rng = np.random.default_rng(args.seed + 31 * rank + (9 if tag == "k9" else 5))
+        reads = [synth_read(rng, nm, ns, k, length, spb) for _ in range(n)]
+        sigs, seqs = [r[0].astype(np.float32) for r in reads], [r[1] for r in reads]
+        al = Aligner(path, pore, mode="resquiggle", device=local_rank)
+        cells = sum((s.size + 1) * (len(q) - k + 2) + (s.size + 1) * 4 ** k for s, q in zip(sigs, seqs))
+        for _ in range(max(1, args.warmup)):
+            al.align_batch(sigs[:4], seqs[:4], True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ok = 0
+        for _ in range(args.steps):
+            res = al.align_batch(sigs, seqs, True)
+            ok = sum(isinstance(r, dict) for r in res)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        lines[tag] = {"reads": n, "reads_ok": ok, "read_length": length, "samples_per_read": int(np.mean([s.size for s in sigs])),
+                      "dense_cells_per_step": int(cells), "ms_per_step": dt * 1e3, "reads_per_s": n / dt,
+                      "g_dense_cells_per_s": cells / dt / 1e9}
+    if rank == 0:
+        k9 = lines["k9"]
+        print(json.dumps({
+            "metric": "ntk_dense_gcups", "value": k9["g_dense_cells_per_s"] * world, "unit": "G dense pre-pass cells/s (T*N + T*K)",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": k9["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "reads_per_s": k9["reads_per_s"] * world,
+            "config": {"workload": "c3: resquiggle (NTK) mode with kmer polishing, 9-mer pore (rna004 synthetic model), polyA-prefixed reads "
+                                   "of 60 b at 12.5 samples/base; beside it 5-mer reads of 1 kb", "k9": k9, "k5": lines["k5"],
+                       "timing": "host wall clock around dyn_ntk_align_batch (H2D, kernels on a pool of streams, D2H), per rank"},
+            "roofline": None, "cpu_baseline": None,
+            "note": "no reference arm: the unmodified reference throws in this mode (SURVEY.md F2); the repaired reference needs "
+                    "~4 min and 10 GB for one 9-mer read of 865 samples (tools/make_golden_ntk.py big) = 0.004 reads/s per host core"}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if args.config in NTK_CONFIGS:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference throws for every input in resquiggle mode (SURVEY.md F2)"}))
+            return
+        return run_ntk(args)
     cfg = CONFIGS[args.config]
     pore, model, lo, hi, spb, dwell, default_reads = cfg
     rank = int(os.environ.get("RANK", "0"))

@@ -528,7 +528,7 @@ DYN_DEV void slide_up(RWarp<RC>& w, Fw<RC::CPL>& f, TrainAcc<RC::CPL>& ta, const
 //                             MODE 2: training statistics (xprev = x[t-1], the sample the posteriors of row t weigh, NT:509-512)
 //   STEP: forward recurrence to row t+1 (NT:141-150)
 // hdr_row / recs: where row t's header / the records go.  Returns the posterior mass of this lane's cells.
-template <class RC, int MODE, bool STEP>
+template <class RC, int MODE, bool STEP, bool MASS = true>
 DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<RC::CPL>& ta, uint32_t* hdr_row, float* recs,
 	float thr, float x, float xprev, const float (&bc)[RC::CPL], const float (&bn)[RC::CPL], float m1, float e2)
 {
@@ -547,7 +547,7 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 		PE[j] = f.fE[j] * bc[j];
 		// bM[t][n] = bE[t+1][n] * p(t,n) (NT:200); the last row has no match state
 		PM[j] = STEP ? f.fM[j] * (bn[j] * p[j]) : 0.0f;
-		msum += PM[j] + PE[j];
+		if (MASS) msum += PM[j] + PE[j];
 	}
 	if (MODE == 1)
 	{
@@ -827,7 +827,10 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 #pragma unroll
 				for (int j = 0; j < C; ++j) bn[j] = rows[(k + 1) * ROWF + j * 32];
 				const float x = __shfl_sync(FULL, xg, k);
-				macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * RC::HDRW, recs, thr, x, xprev, bc, bn, m1, e2);
+				// the posterior mass is measured on the group's last row: offsets and the posterior factor are fixed inside
+				// a group, so a lane that lost its values or whose factor left the float range shows there
+				if (k == 7) macc += fwd_row<RC, MODE, true, true>(w, f, rs, ta, hdr_g + k * RC::HDRW, recs, thr, x, xprev, bc, bn, m1, e2);
+				else fwd_row<RC, MODE, true, false>(w, f, rs, ta, hdr_g + k * RC::HDRW, recs, thr, x, xprev, bc, bn, m1, e2);
 				xprev = x;
 #pragma unroll
 				for (int j = 0; j < C; ++j) bc[j] = bn[j];
@@ -855,7 +858,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		// ---- group boundary: state row 8g+8 ------------------------------------------------------------------
 		// closed loop: the posterior mass of every row is 1; a row that lost mass is a fault, the mean deviation (slow
 		// common-mode FP32 drift) is folded into the posterior factor of the next group
-		const float cnt = (g < gl) ? (float)nr : (float)(nr + 1);
+		const float cnt = (g < gl && !clip) ? 1.0f : ((g < gl) ? (float)nr : (float)(nr + 1));  // rows whose mass was summed
 		const float mass = warp_sum(macc, lane);
 		macc = 0.0f;
 		if (!(fabsf(mass - cnt) <= RIB_MASS_TOL) && !fault) { fault = 5; RIB_DBG("p2 g=%d mass=%g of %g\n", g, mass, cnt); }

@@ -2593,7 +2593,21 @@ int dyn_ntk_align_batch(dyn_aligner* A, const float* signal, const uint64_t* sig
 	{
 		// Reads are independent: a pool of host threads, each with its own CUDA stream and its own (reused) device
 		// buffers, pulls reads from a queue, so that the small per-read grids of many reads overlap on the device.
-		const int workers = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(concurrency > 0 ? concurrency : 32), n_reads));
+		int workers = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(concurrency > 0 ? concurrency : 32), n_reads));
+		{
+			// every read in flight holds its dense pre-pass lattice (3 x T x max(N, K) doubles): 9-mers need 6.3 GB per 1000
+			// samples, so the pool is as wide as the free HBM allows
+			uint64_t maxS = 0, maxL = 0;
+			for (uint32_t r = 0; r < n_reads; ++r)
+			{
+				maxS = std::max<uint64_t>(maxS, sig_off[r + 1] - sig_off[r]);
+				maxL = std::max<uint64_t>(maxL, seq_off[r + 1] - seq_off[r]);
+			}
+			const double per_read = 24.0 * (double)(maxS + 1) * (double)std::max<uint64_t>(A->K, maxL) * 1.15 + 64e6;
+			A->rt.bind();
+			const double fit = 0.6 * (double)A->rt.free_bytes() / per_read;
+			workers = (int)std::max(1.0, std::min((double)workers, fit));
+		}
 		std::atomic<uint32_t> next(0);
 		std::vector<std::string> errors(workers);
 		auto work = [&](int wi) {

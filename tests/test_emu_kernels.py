@@ -21,18 +21,25 @@ def emu_lib():
     return build_emu.build()
 
 
-def _aligner(lib, case, variant=0, band=400, arith=0):
+def _aligner(lib, case, variant=0, band=400, arith=0, ribbon=None):
+    """variant >= 0: that build variant of the FULL-BAND kernels with the ribbon tier switched off (so that the tiers behind
+    the ribbon keep their coverage); variant -1: the library default (ribbon tier first)."""
     from dynamont_b200 import Aligner
     al = Aligner(case.model_path, case.pore, band=band, _lib_path=lib)
     al.set_option("variant", variant)
     al.set_option("arith", arith)  # 0: linear-domain kernels (+ log2-domain fallback), 1: log2-domain kernels only
+    if ribbon is None:
+        ribbon = 2 if variant < 0 else 0
+    al.set_option("ribbon", ribbon)
     return al
 
 
+@pytest.mark.parametrize("tier", ["ribbon", "ribbon4", "full_band"])
 @pytest.mark.parametrize("case", [c for c in load_golden() if c.name in SMALL], ids=lambda c: c.name)
-def test_emulated_align_matches_reference(case, emu_lib):
-    al = _aligner(emu_lib, case)
+def test_emulated_align_matches_reference(case, tier, emu_lib):
+    al = _aligner(emu_lib, case, ribbon={"ribbon": 2, "ribbon4": 4, "full_band": 0}[tier])
     r = al.align(case.signal, case.sequence, True)
+    assert (al.last_timing()["ribbon_reads"] == 1) == (tier != "full_band")
     check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
     assert al.align(case.signal, case.sequence, False)["Z"] == r["Z"]
 

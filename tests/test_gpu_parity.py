@@ -257,3 +257,19 @@ def test_multi_device_front_equals_single(aligners, models_dir):
     for a, b in zip(single, multi):
         assert a["Z"] == b["Z"] and np.array_equal(a["signal_positions"], b["signal_positions"])
         assert np.array_equal(a["probabilities"], b["probabilities"])
+
+
+@pytest.mark.parametrize("case", load_golden(), ids=lambda c: c.name)
+def test_full_band_tiers_match_reference_golden(case):
+    """the tiers behind the ribbon (round 1's full-band kernels) on their own: ribbon switched off"""
+    from dynamont_b200 import Aligner
+    al = Aligner(case.model_path, case.pore)
+    al.set_option("ribbon", 0)
+    r = al.align(case.signal, case.sequence, True)
+    assert al.last_timing()["ribbon_reads"] == 0
+    check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    per_read, pooled = al.train_batch([case.signal], [case.sequence], per_read_model=True)
+    km = case.train_kmers
+    heavy = case.stat_w > 1e-3
+    np.testing.assert_allclose(pooled["w"][km][heavy], case.stat_w[heavy], rtol=TRAIN_RTOL)
+    np.testing.assert_allclose(per_read[0]["emission_model"]["stdev"][km][heavy], case.train_stdev[heavy], rtol=TRAIN_RTOL, atol=1e-6)
