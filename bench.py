@@ -276,7 +276,7 @@ def run_ntk(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lines = {}
     for tag, pore, model, length, spb, n in (("k9", "rna004", "synthetic_rna004_9mer", 60, 12.5, args.reads or 32),
-                                             ("k5", "dna_r9", "rna004_5mer", 1000, 12.5, args.reads or 32)):
+                                             ("k5", "dna_r9", "rna004_5mer", 1000, 12.5, args.reads or 192)):
         path = materialize_model(model, MODELS_DIR)
         nm, ns = native_model(path, pore)
         k = PORE_INFO[pore][1]

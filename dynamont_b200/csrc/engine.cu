@@ -2593,7 +2593,7 @@ int dyn_ntk_align_batch(dyn_aligner* A, const float* signal, const uint64_t* sig
 	{
 		// Reads are independent: a pool of host threads, each with its own CUDA stream and its own (reused) device
 		// buffers, pulls reads from a queue, so that the small per-read grids of many reads overlap on the device.
-		int workers = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(concurrency > 0 ? concurrency : 32), n_reads));
+		int workers = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)(concurrency > 0 ? concurrency : 64), n_reads));
 		{
 			// every read in flight holds its dense pre-pass lattice (3 x T x max(N, K) doubles): 9-mers need 6.3 GB per 1000
 			// samples, so the pool is as wide as the free HBM allows

@@ -57,17 +57,115 @@ __device__ __forceinline__ double score_kmer(const Consts& c, double x, uint32_t
 
 // Row masks (NTK:343-353, 389-399): take the columns of row t in order of LP descending (stable: ties -> smaller
 // index first, -inf last) until the sequential log-sum-exp of the taken values reaches SPARSETHRESHOLD (NTK:17: -0.02227639471 = log10(0.95), a mass of 0.978).
-// One CTA per row; every round finds the largest remaining value with a block-wide arg-max.
+// One CTA per row.
+//   compact path (the normal case): the columns within 40 nats of the row maximum — everything else adds < 1e-12 of
+//   the mass of the largest column, and the selection stops at 0.978 of the row's mass — are gathered into shared memory
+//   (<= RM_CAP of them), sorted once by (value descending, index ascending) with a bitonic network, and one thread runs
+//   the reference's sequential log-sum-exp over the sorted list.  A 9-mer row (262 144 columns) is read twice instead of
+//   once per selected column.
+//   rounds path (fallback: more than RM_CAP candidates, an all -inf row, or the candidates do not reach the threshold):
+//   every round finds the largest remaining value of the whole row with a block-wide arg-max.
+constexpr int RM_CAP = 2048;
+
+__device__ __forceinline__ bool rm_before(double va, uint32_t ia, double vb, uint32_t ib) { return va > vb || (va == vb && ia < ib); }
+
 __global__ void __launch_bounds__(256) k_row_mask(const double* LP, uint32_t C, uint32_t words, uint32_t* mask, double threshold)
 {
-	__shared__ double s_val[256];
-	__shared__ uint32_t s_idx[256];
-	__shared__ int s_stop;
+	__shared__ double s_val[RM_CAP];
+	__shared__ uint32_t s_idx[RM_CAP];
+	__shared__ double s_red[8];
+	__shared__ int s_n, s_stop;
 	const uint32_t t = blockIdx.x;
 	const double* row = LP + (size_t)t * C;
 	uint32_t* m = mask + (size_t)t * words;
 	for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) m[i] = 0u;
+	if (threadIdx.x == 0) s_n = 0;
+	// row maximum
+	double mx = neg_inf();
+	for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) mx = fmax(mx, row[i]);
+	for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
 	__syncthreads();
+	mx = s_red[0];
+	for (int w = 1; w < 8; ++w) mx = fmax(mx, s_red[w]);
+	bool compact = !isinf(mx);
+	if (compact)
+	{
+		const double cut = mx - 40.0;
+		for (uint32_t i = threadIdx.x; i < C; i += blockDim.x)
+		{
+			const double v = row[i];
+			if (v >= cut)
+			{
+				const int pos = atomicAdd(&s_n, 1);
+				if (pos < RM_CAP)
+				{
+					s_val[pos] = v;
+					s_idx[pos] = i;
+				}
+			}
+		}
+		__syncthreads();
+		compact = s_n <= RM_CAP;
+	}
+	if (compact)
+	{
+		const int n = s_n;
+		int np2 = 1;
+		while (np2 < n) np2 <<= 1;
+		for (int i = n + threadIdx.x; i < np2; i += blockDim.x)
+		{
+			s_val[i] = neg_inf();
+			s_idx[i] = 0xffffffffu;  // padding sorts last
+		}
+		__syncthreads();
+		// bitonic sort, "before" = larger value, then smaller index
+		for (int k = 2; k <= np2; k <<= 1)
+			for (int j = k >> 1; j > 0; j >>= 1)
+			{
+				for (int i = threadIdx.x; i < np2; i += blockDim.x)
+				{
+					const int l = i ^ j;
+					if (l > i)
+					{
+						const bool up = (i & k) == 0;
+						const double va = s_val[i], vb = s_val[l];
+						const uint32_t ia = s_idx[i], ib = s_idx[l];
+						const bool swap = up ? rm_before(vb, ib, va, ia) : rm_before(va, ia, vb, ib);
+						if (swap)
+						{
+							s_val[i] = vb; s_idx[i] = ib;
+							s_val[l] = va; s_idx[l] = ia;
+						}
+					}
+				}
+				__syncthreads();
+			}
+		if (threadIdx.x == 0)
+		{
+			double sum = neg_inf();
+			int reached = 0;
+			for (int k = 0; k < n; ++k)
+			{
+				const uint32_t i = s_idx[k];
+				m[i >> 5] |= 1u << (i & 31);
+				sum = log_plus(sum, s_val[k]);
+				if (sum >= threshold) { reached = 1; break; }
+			}
+			if (!reached && n < (int)C)
+			{
+				// the candidates do not carry the threshold mass: start over with the rounds below
+				for (int k = 0; k < n; ++k) m[s_idx[k] >> 5] = 0u;
+			}
+			s_stop = reached || n >= (int)C;
+		}
+		__syncthreads();
+		if (s_stop) return;
+		__syncthreads();
+	}
+	// ---- rounds path
+	double* r_val = s_val;      // [256]
+	uint32_t* r_idx = s_idx;    // [256]
 	double sum = neg_inf();
 	uint32_t taken = 0;
 	while (true)
@@ -81,30 +179,30 @@ __global__ void __launch_bounds__(256) k_row_mask(const double* LP, uint32_t C, 
 			const double v = row[i];
 			if (bi == 0xffffffffu || v > bv) { bv = v; bi = i; }
 		}
-		s_val[threadIdx.x] = bv;
-		s_idx[threadIdx.x] = bi;
+		r_val[threadIdx.x] = bv;
+		r_idx[threadIdx.x] = bi;
 		__syncthreads();
 		for (int o = 128; o; o >>= 1)
 		{
 			if ((int)threadIdx.x < o)
 			{
-				const uint32_t oi = s_idx[threadIdx.x + o];
-				const double ov = s_val[threadIdx.x + o];
-				const uint32_t mi = s_idx[threadIdx.x];
-				const double mv = s_val[threadIdx.x];
+				const uint32_t oi = r_idx[threadIdx.x + o];
+				const double ov = r_val[threadIdx.x + o];
+				const uint32_t mi = r_idx[threadIdx.x];
+				const double mv = r_val[threadIdx.x];
 				if (oi != 0xffffffffu && (mi == 0xffffffffu || ov > mv || (ov == mv && oi < mi)))
 				{
-					s_val[threadIdx.x] = ov;
-					s_idx[threadIdx.x] = oi;
+					r_val[threadIdx.x] = ov;
+					r_idx[threadIdx.x] = oi;
 				}
 			}
 			__syncthreads();
 		}
 		if (threadIdx.x == 0)
 		{
-			const uint32_t i = s_idx[0];
+			const uint32_t i = r_idx[0];
 			m[i >> 5] |= 1u << (i & 31);
-			sum = log_plus(sum, s_val[0]);
+			sum = log_plus(sum, r_val[0]);
 			++taken;
 			s_stop = (sum >= threshold || taken >= C) ? 1 : 0;
 		}
