@@ -254,6 +254,7 @@ class Aligner:
         out = {int(i): int(v) for i, v in enumerate(r[:13]) if v}
         out["records_per_row"] = float(r[13]) / 1000.0
         out["two_level_checkpoints"] = bool(r[14])
+        out["records_free_layout"] = int(r[14]) == 2  # long reads: path posteriors from a second forward sweep
         return out
 
     def last_timing(self):

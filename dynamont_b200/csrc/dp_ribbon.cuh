@@ -528,14 +528,18 @@ DYN_DEV void slide_up(RWarp<RC>& w, Fw<RC::CPL>& f, TrainAcc<RC::CPL>& ta, const
 //                             MODE 2: training statistics (xprev = x[t-1], the sample the posteriors of row t weigh, NT:509-512)
 //   STEP: forward recurrence to row t+1 (NT:141-150)
 // hdr_row / recs: where row t's header / the records go.  Returns the posterior mass of this lane's cells.
+//   MODE 3: as MODE 1 without records (the row header holds the C decision words only); MODE 4: the gather sweep that
+//   follows the traceback of MODE 3 — `cell` = path cell of row t (column | match state << 31), whose posterior goes to
+//   hdr_row[0] (= pp[t]); no posterior-Viterbi state.
 template <class RC, int MODE, bool STEP, bool MASS = true>
 DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<RC::CPL>& ta, uint32_t* hdr_row, float* recs,
-	float thr, float x, float xprev, const float (&bc)[RC::CPL], const float (&bn)[RC::CPL], float m1, float e2)
+	float thr, float x, float xprev, const float (&bc)[RC::CPL], const float (&bn)[RC::CPL], float m1, float e2, uint32_t cell = 0u)
 {
 	constexpr int C = RC::CPL;
+	constexpr bool VIT = (MODE == 1 || MODE == 3);
 	const int lane = w.lane;
 	// the values the right lane needs are those of the previous row: send them first, consume them last
-	const float vlraw = (MODE == 1) ? __shfl_sync(FULL, f.VE[C - 1], (lane + 31) & 31) : 0.0f;
+	const float vlraw = VIT ? __shfl_sync(FULL, f.VE[C - 1], (lane + 31) & 31) : 0.0f;
 	const float flraw = STEP ? __shfl_sync(FULL, f.fE[C - 1], (lane + 31) & 31) : 0.0f;
 	float p[C], PM[C], PE[C];
 #pragma unroll
@@ -549,7 +553,7 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 		PM[j] = STEP ? f.fM[j] * (bn[j] * p[j]) : 0.0f;
 		if (MASS) msum += PM[j] + PE[j];
 	}
-	if (MODE == 1)
+	if (VIT)
 	{
 		// posterior-Viterbi fill (NT:357-362) as a max-product, in place from the highest slot down;
 		// decision bit set <=> the E state of this cell is entered from E (the test of NT:448 at fill time)
@@ -564,8 +568,22 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 			const float left = (j > 0) ? f.VE[j - 1] : vl;
 			f.VM[j] = left * PM[j];
 			f.VE[j] = vmx * PE[j];
-			lmax = lin::max3f(lmax, PM[j], PE[j]);
+			if (MODE == 1) lmax = lin::max3f(lmax, PM[j], PE[j]);
 		}
+		if (MODE == 3)
+		{
+			if (lane == 0)
+			{
+				if (C == 2) *reinterpret_cast<uint2*>(hdr_row) = make_uint2(bits[0], bits[C - 1]);
+				else
+				{
+#pragma unroll
+					for (int j = 0; j < C; ++j) hdr_row[j] = bits[j];
+				}
+			}
+		}
+		else
+		{
 		// sparse posterior records: one per lane that holds a posterior above the threshold (NaN counts as hot)
 		const bool hot = !(lmax <= thr);
 		const unsigned hm = __ballot_sync(FULL, hot);
@@ -599,6 +617,19 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 			for (int q = 0; q < RC::HDRW / 4; ++q) dst[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
 		}
 		rs.n += __popc(hm);
+		}
+	}
+	else if (MODE == 4)
+	{
+		// the posterior of the path cell: the lane that holds its ring slot writes it
+		const int q = (int)((cell & 0x7fffffffu) % (uint32_t)RC::SLOTS);
+		const int ql = q / C, jq = q - ql * C;
+		const bool isM = (cell >> 31) != 0u;
+		float pv = 0.0f;
+#pragma unroll
+		for (int j = 0; j < C; ++j)
+			if (j == jq) pv = isM ? PM[j] : PE[j];
+		if (lane == ql && cell != 0xffffffffu) *reinterpret_cast<float*>(hdr_row) = pv;
 	}
 	else
 	{
@@ -698,7 +729,9 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	float ckM[C], ckE[C];
 	int ckO;
 	float x8;
+	uint32_t cg8 = 0xffffffffu;  // MODE 4: path cells of rows 8g .. 8g+8 (lanes 0 .. 8)
 	int mid_next;
+	constexpr int HDRS = (MODE == 3) ? C : RC::HDRW;  // words per row header
 	int* const ring_ob = reinterpret_cast<int*>(sc.ring + (size_t)SG * RC::CKF);
 	// two-level checkpoints: replay the backward pass over the super-group that starts at group g0 and park the group
 	// checkpoints in the ring (the emission window travels up to the super-group's last group and back down to g0's)
@@ -755,6 +788,12 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		ckO = TL ? ring_ob[(size_t)(g % SG) * 32 + lane] : reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)g * 32 + lane];
 		const int i = 8 * g + (lane & 7);
 		x8 = (i < S) ? w.sig[i] : 0.0f;
+		if (MODE == 4)
+		{
+			// (read before this group's posteriors overwrite the same words: the stores depend on these values)
+			const int r = 8 * g + (lane & 15);
+			cg8 = ((lane & 15) <= 8 && r <= S) ? __float_as_uint(sc.pp[r]) : 0xffffffffu;
+		}
 		mid_next = (g < gl) ? (int)sc.sched[g + 1].x : 0;
 	};
 	if (TL) replay(0);
@@ -773,6 +812,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			break;
 		}
 		const float xg = x8;
+		const uint32_t cgq = cg8;
 		const int midn = mid_next;
 		// ---- step a: recompute the backward rows 8g+nr .. 8g of this group into shared memory, scaled by the group's
 		// posterior factor kap = 2^(OF + OB - Z2) (forward offsets are fixed inside a group)
@@ -815,7 +855,9 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		if (g < gl && !(TL && (g + 1) % SG == 0)) prefetch(g + 1);
 
 		// ---- step b: forward rows 8g .. 8g+nr-1 -------------------------------------------------------------
-		uint32_t* const hdr_g = sc.hdr + (size_t)(8 * g) * RC::HDRW;
+		// where row 8g+k's header goes (MODE 4: its path posterior)
+		uint32_t* const hdr_g = (MODE == 4) ? reinterpret_cast<uint32_t*>(sc.pp) + (size_t)(8 * g) : sc.hdr + (size_t)(8 * g) * HDRS;
+		constexpr int HSTR = (MODE == 4) ? 1 : HDRS;
 		float bc[C], bn[C];
 #pragma unroll
 		for (int j = 0; j < C; ++j) bc[j] = rows[j * 32];
@@ -829,8 +871,9 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 				const float x = __shfl_sync(FULL, xg, k);
 				// the posterior mass is measured on the group's last row: offsets and the posterior factor are fixed inside
 				// a group, so a lane that lost its values or whose factor left the float range shows there
-				if (k == 7) macc += fwd_row<RC, MODE, true, true>(w, f, rs, ta, hdr_g + k * RC::HDRW, recs, thr, x, xprev, bc, bn, m1, e2);
-				else fwd_row<RC, MODE, true, false>(w, f, rs, ta, hdr_g + k * RC::HDRW, recs, thr, x, xprev, bc, bn, m1, e2);
+				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, k) : 0u;
+				if (k == 7) macc += fwd_row<RC, MODE, true, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
+				else fwd_row<RC, MODE, true, false>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
 				xprev = x;
 #pragma unroll
 				for (int j = 0; j < C; ++j) bc[j] = bn[j];
@@ -844,14 +887,19 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 #pragma unroll
 				for (int j = 0; j < C; ++j) bn[j] = rows[(k + 1) * ROWF + j * 32];
 				const float x = __shfl_sync(FULL, xg, k);
-				macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * RC::HDRW, recs, thr, x, xprev, bc, bn, m1, e2);
+				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, k) : 0u;
+				macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
 				if (clip) clip_row<RC>(w, f.fM, f.fE, mid, 8u * (uint32_t)g + (uint32_t)k + 1u);  // f now holds row t+1
 				xprev = x;
 #pragma unroll
 				for (int j = 0; j < C; ++j) bc[j] = bn[j];
 			}
 			// last row T-1: posteriors, Viterbi, bits, records; no forward step, no match posterior
-			if (g == gl) macc += fwd_row<RC, MODE, false>(w, f, rs, ta, hdr_g + nr * RC::HDRW, recs, thr, 0.0f, xprev, bc, bn, m1, e2);
+			if (g == gl)
+			{
+				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, nr) : 0u;
+				macc += fwd_row<RC, MODE, false>(w, f, rs, ta, hdr_g + nr * HSTR, recs, thr, 0.0f, xprev, bc, bn, m1, e2, cell);
+			}
 		}
 		__syncwarp();
 
@@ -898,7 +946,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			f.OF = nO;
 			f.sL = lin::pow2i(__shfl_sync(FULL, nO, (lane + 31) & 31) - nO);
 		}
-		if (MODE == 1)
+		if (MODE == 1 || MODE == 3)
 		{
 			float lm = 0.0f;
 #pragma unroll
@@ -966,7 +1014,9 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 // ------------------------------------------------------------------------------------------------------
 // pass 3: traceback over the decision bits (NT:383-456), posterior of every path cell, per-segment medians
 // ------------------------------------------------------------------------------------------------------
-template <class RC>
+// GA (records-free layout, MODE 3): the row header is the C decision words; the path cell of every row (column | match
+// state << 31) is left in pp[] for the gather sweep, which replaces it by its posterior; the medians follow that sweep.
+template <class RC, bool GA = false>
 DYN_DEV bool traceback_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs& args, const ReadDesc& rd)
 {
 	constexpr int C = RC::CPL;
@@ -985,6 +1035,13 @@ DYN_DEV bool traceback_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		const uint32_t row = (uint32_t)cbase + lane;
 		// every lane holds the header of one row of the chunk
 		uint32_t h[HDRW];
+		if (GA)
+		{
+			h[0] = h[1] = 0u;
+#pragma unroll
+			for (int jj = 0; jj < C; ++jj) h[2 + jj] = (row < T && row >= 1) ? sc.hdr[(size_t)row * C + jj] : 0u;
+		}
+		else
 		{
 			const uint4* src = reinterpret_cast<const uint4*>(sc.hdr + (size_t)row * HDRW);
 #pragma unroll
@@ -1036,7 +1093,11 @@ DYN_DEV bool traceback_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			if ((int)row >= tstar && (int)row <= t) mycell = (uint32_t)n;
 			t = tstar - 1;
 		}
-		if (mycell != 0xffffffffu)
+		if (GA)
+		{
+			if (mycell != 0xffffffffu) sc.pp[row] = __uint_as_float(mycell);
+		}
+		else if (mycell != 0xffffffffu)
 		{
 			const uint32_t col = mycell & 0x7fffffffu;
 			const bool isM = (mycell >> 31) != 0;
@@ -1055,7 +1116,7 @@ DYN_DEV bool traceback_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	if (!((n == 0) && !inM)) return false;
 	__threadfence_block();
 	__syncwarp();
-	segment_medians_impl(w.lane, w.T, w.N, sc, args, rd);
+	if (!GA) segment_medians_impl(w.lane, w.T, w.N, sc, args, rd);
 	return true;
 }
 
@@ -1106,6 +1167,28 @@ DYN_DEV void ribbon_read(const BatchArgs& args, const ReadDesc& rd, uint32_t rid
 			__threadfence_block();
 			__syncwarp();
 			if (!rib::traceback_pass<RC>(w, sc, args, rd)) fault = 11;
+		}
+		if (!fault && MODE == 3)
+		{
+			// records-free layout (long reads): traceback over the decision bits, then a second forward sweep that evaluates
+			// the posterior of every path cell (bit-identical to what MODE 1 would have recorded), then the medians
+			__threadfence_block();
+			__syncwarp();
+			if (!rib::traceback_pass<RC, true>(w, sc, args, rd)) fault = 11;
+			if (!fault)
+			{
+				__threadfence_block();
+				__syncwarp();
+				double xm, xe;
+				const double dz3 = rib::forward_pass<RC, 4, TL>(w, sc, args, rd.pc_off, smem_raw, Z2, nrec, overflow, xm, xe, fault);
+				if (!fault && !(fabs(dz3) <= lin::LIN_Z_TOL)) fault = 9;
+				if (!fault)
+				{
+					__threadfence_block();
+					__syncwarp();
+					segment_medians_impl(w.lane, w.T, w.N, sc, args, rd);
+				}
+			}
 		}
 	}
 	if (fault)

@@ -725,6 +725,8 @@ struct dyn_aligner
 	double rib_recs_per_row = 2.5;   // lane records per lattice row budgeted (measured use: 1.2; a read that needs more faults to the full-band kernels)
 	int rib_min_bw = 0;        // reads whose half band is narrower than this skip the ribbon tier (0: none; the band is clipped exactly inside the window)
 	int rib_two_level = -1;    // checkpoints of every 8th group only: -1 when the scratch would not fit otherwise, 0 never, 1 always
+	int rib_gather = -1;       // records-free scratch + second forward sweep for the path posteriors (implies two-level):
+	                           // -1 when the resident warps' scratch would not fit otherwise, 0 never, 1 always
 	double rib_last_two_level = 0;
 	double rib_recs_used = 0;  // lane records per lattice row the last batch actually wrote (align mode)
 	int rib_bps = 0;           // resident CTAs (of 4 warps) per SM of the ribbon kernels; 0: the build's default
@@ -1101,6 +1103,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	A.n_rib_fault = 0;
 	A.ribbon_ms = 0.0;
 	int launches = 1;
+	// reads the ribbon kernels lost COMPLETELY (every value of a group underflowed, or Zb is not finite): the same FP32
+	// linear arithmetic over the full band cannot hold them either, they go straight to the log2-domain tier
+	std::vector<uint32_t> direct_log2;
 
 	// ---- tier 0: the ribbon kernels (dp_ribbon.cuh) -----------------------------------------------------------
 	// every read whose reference band leaves room for the window; what they cannot represent (ST_LIN_FAULT) and the
@@ -1126,15 +1131,19 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			size_t per_slot = 0, o_sch = 0, o_ck = 0, o_ob = 0, o_hdr = 0, o_rec = 0, o_pp = 0;
 			uint64_t rcap = 0;
 			size_t o_ring = 0;
-			bool two_level = false;
+			bool two_level = false, gather = false;
 			if (mode != 0)
 			{
 				const size_t budget = (size_t)((double)(rt.free_bytes() + (A.root ? A.root : &A)->d_rib_scratch.cap) * A.mem_fraction);
 				// checkpoints of every group (640 B per 8 rows at 2 columns per lane) unless the scratch of the resident warps
 				// would not fit: then only every 8th group's, the others replayed in pass 2 (long reads; A.rib_two_level forces)
-				for (int pass = 0; pass < 2; ++pass)
+				// ... and if that does not fit either (config 4: 2 M rows), the records-free layout: row header = the decision
+				// words, no posterior records; the path posteriors come from a second forward sweep after the traceback
+				// (23 instead of 71 bytes per lattice row)
+				for (int pass = 0; pass < 3; ++pass)
 				{
-					two_level = (A.rib_two_level > 0) || (A.rib_two_level < 0 && pass == 1);
+					gather = (mode == 1) && ((A.rib_gather > 0) || (A.rib_gather < 0 && pass == 2));
+					two_level = gather || (A.rib_two_level > 0) || (A.rib_two_level < 0 && pass >= 1);
 					const size_t ngr = (size_t)maxTr / rg.ck + 2;
 					const size_t nck = two_level ? ngr / 8 + 2 : ngr;
 					size_t o = 0;
@@ -1142,7 +1151,14 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 					o_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
 					o_ob = o; o = align_up(o + nck * 32 * 4, 256);
 					o_ring = o; o = align_up(o + (two_level ? 8 * ((size_t)rg.ckf * 4 + 128) : 0), 256);
-					if (mode == 1)
+					if (mode == 1 && gather)
+					{
+						rcap = 0;
+						o_hdr = o; o = align_up(o + ((size_t)maxTr + 32) * rg.cpl * 4, 256);
+						o_rec = o;
+						o_pp = o; o = align_up(o + ((size_t)maxTr + 32) * 4, 256);
+					}
+					else if (mode == 1)
 					{
 						rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64 + 9 * 32;
 						o_hdr = o; o = align_up(o + ((size_t)maxTr + 32) * rg.hdrw * 4, 256);
@@ -1150,12 +1166,17 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 						o_pp = o; o = align_up(o + ((size_t)maxTr + 32) * 4, 256);
 					}
 					per_slot = o;
-					if (A.rib_two_level >= 0 || budget / per_slot >= gridw) break;
+					if (budget / per_slot >= gridw) break;  // every resident warp gets its scratch: take this layout
+					// is a smaller layout allowed?
+					if (pass == 0 && A.rib_two_level == 0 && A.rib_gather <= 0) break;
+					if (pass == 0 && A.rib_two_level > 0 && A.rib_gather == 0) break;
+					if (pass == 1 && (A.rib_gather == 0 || mode != 1)) break;
 				}
 				const size_t fit = std::max<size_t>(1, budget / per_slot);
 				if (tm.on)
-					fprintf(stderr, "[dyn timing] ribbon scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit%s\n",
-						per_slot / 1048576.0, gridw, budget / 1073741824.0, fit, two_level ? " (two-level checkpoints)" : "");
+					fprintf(stderr, "[dyn timing] ribbon scratch: %.1f MB per resident warp x %u wanted, budget %.1f GB -> %zu fit%s%s\n",
+						per_slot / 1048576.0, gridw, budget / 1073741824.0, fit, two_level ? " (two-level checkpoints)" : "",
+						gather ? " (records-free, gather sweep)" : "");
 				gridw = (unsigned)std::min<size_t>(gridw, fit);
 			}
 			{
@@ -1206,10 +1227,10 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			}
 			rt.mark_on(6, R.rt);
 #ifndef DYN_HOST_EMU
-			const int le = rib::launch((void*)R.rt.stream, rb, gridw, mode, A.ribbon, A.rib_bps, two_level);
+			const int le = rib::launch((void*)R.rt.stream, rb, gridw, gather ? 3 : mode, A.ribbon, A.rib_bps, two_level);
 			if (le != 0) throw std::runtime_error(std::string("CUDA error launching the ribbon kernel: ") + cudaGetErrorString((cudaError_t)le));
 #else
-			rib::launch(nullptr, rb, gridw, mode, A.ribbon, A.rib_bps, two_level);
+			rib::launch(nullptr, rb, gridw, gather ? 3 : mode, A.ribbon, A.rib_bps, two_level);
 #endif
 			rt.mark_on(7, R.rt);
 			if (cross) rt.wait_self(7);
@@ -1229,15 +1250,17 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 						nrec += (double)res.out[r].nrec;
 						nrow += (double)res.desc[r].S;
 					}
-				A.rib_last_two_level = two_level ? 1.0 : 0.0;
+				A.rib_last_two_level = gather ? 2.0 : (two_level ? 1.0 : 0.0);
 				A.rib_recs_used = nrow > 0 ? nrec / nrow : 0.0;
 			}
 			for (uint32_t r : rorder)
 				if (res.out[r].status == ST_LIN_FAULT)
 				{
-					rest.push_back(r);
+					const uint32_t why = res.out[r].nrec;
+					if (why == 1u || why == 12u) direct_log2.push_back(r);
+					else rest.push_back(r);
 					++A.n_rib_fault;
-					++A.rib_reason[std::min<uint32_t>(res.out[r].nrec, 15u)];
+					++A.rib_reason[std::min<uint32_t>(why, 15u)];
 					if (mode == 2)
 					{
 						// columns the read flushed before its fault was detected: the full-band kernels accumulate
@@ -1253,6 +1276,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			order.swap(rest);
 			maxT = 0;
 			for (uint32_t r : order) maxT = std::max(maxT, res.desc[r].S + 1);
+			for (uint32_t r : direct_log2) maxT = std::max(maxT, res.desc[r].S + 1);
 			if (!order.empty())
 			{
 				A.h2d_staged(d_order, order.data(), order.size() * 4);
@@ -1263,13 +1287,13 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	}
 
 	double fallback_ms = 0.0, main_ms = 0.0;
-	if (!order.empty())
+	if (!order.empty() || !direct_log2.empty())
 	{
 	const bool lin_first = (A.arith == 0);
 	// ---- scratch: one slot per resident warp, sized for the longest read --------------------------------------
 	// Z-only runs the backward pass alone: <= 128 registers and no shared memory, i.e. 16 single-warp CTAs per SM
 	const int resident = (mode == 0) ? 16 : MINB;
-	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * (A.warps_per_sm > 0 ? A.warps_per_sm : resident), order.size());
+	unsigned grid = (unsigned)std::min<size_t>((size_t)rt.sms * (A.warps_per_sm > 0 ? A.warps_per_sm : resident), order.size() + direct_log2.size());
 	size_t per_slot = 0;
 	uint64_t rec_cap = 0;
 	size_t o_ck = 0, o_ob = 0, o_bits = 0, o_rp = 0, o_rec = 0, o_pn = 0, o_pp = 0;
@@ -1336,9 +1360,12 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	const bool lin = (A.arith == 0);
 	tm.lap("enqueue");
 	rt.mark(2);
-	launch_align<CFG, MINB, CFGLIN, MINB_FB, WPC>(rt, ba, grid, mode, lin);
+	if (!order.empty())
+	{
+		launch_align<CFG, MINB, CFGLIN, MINB_FB, WPC>(rt, ba, grid, mode, lin);
+		++launches;
+	}
 	rt.mark(3);
-	++launches;
 	if (lin)
 	{
 		// reads the FP32 linear arithmetic could not represent (ST_LIN_FAULT) are re-run in the log2 domain
@@ -1372,6 +1399,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				again.swap(still);
 			}
 		}
+		again.insert(again.end(), direct_log2.begin(), direct_log2.end());
 		if (!again.empty())
 		{
 			A.n_fallback = again.size();
@@ -2731,6 +2759,7 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	else if (k == "rib_recs_per_row") A->rib_recs_per_row = value;
 	else if (k == "rib_bps") A->rib_bps = (int)value;
 	else if (k == "rib_two_level") A->rib_two_level = (int)value;
+	else if (k == "rib_gather") A->rib_gather = (int)value;
 	else if (k == "rib_min_bw") A->rib_min_bw = (int)value;
 	else return -1;
 	return 0;

@@ -63,6 +63,11 @@ int launch_t(cudaStream_t stream, const BatchArgs& args, unsigned n_warps, int m
 	const unsigned ctas = (n_warps + WPB - 1) / WPB;
 	if (mode == 0) k_ribbon<RC, 0, BPS, false><<<ctas, 32 * WPB, 0, stream>>>(args);
 	else if (mode == 1) k_ribbon<RC, 1, BPS, TL><<<ctas, 32 * WPB, smem, stream>>>(args);
+	else if (mode == 3)
+	{
+		if constexpr (TL) k_ribbon<RC, 3, BPS, true><<<ctas, 32 * WPB, smem, stream>>>(args);
+		else return (int)cudaErrorInvalidValue;  // the records-free layout is built for two-level checkpoints only
+	}
 	else k_ribbon<RC, 2, BPS, TL><<<ctas, 32 * WPB, smem, stream>>>(args);
 	return (int)cudaGetLastError();
 }
@@ -73,6 +78,11 @@ int launch_t(void*, const BatchArgs& args, unsigned n_warps, int mode)
 	const size_t smem = RC::SMEM_BYTES;
 	if (mode == 0) simt::launch(n_warps, smem, [&]() { worker<RC, 0, false>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 	else if (mode == 1) simt::launch(n_warps, smem, [&]() { worker<RC, 1, TL>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+	else if (mode == 3)
+	{
+		if constexpr (TL) simt::launch(n_warps, smem, [&]() { worker<RC, 3, true>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+		else return -1;
+	}
 	else simt::launch(n_warps, smem, [&]() { worker<RC, 2, TL>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 	return 0;
 }

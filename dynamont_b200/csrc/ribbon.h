@@ -27,7 +27,9 @@ struct Geometry
 // cpl: 2 or 4.  Returns false for an unsupported width.
 bool geometry(int cpl, int bps, Geometry& g);  // bps: resident CTAs per SM (0 = default)
 
-// n_warps resident warps (one scratch slot each, args.slots[0 .. n_warps)); mode 0: Z only, 1: align, 2: train.
+// n_warps resident warps (one scratch slot each, args.slots[0 .. n_warps)); mode 0: Z only, 1: align, 2: train,
+// 3: align with the records-free scratch layout (row header = decision words only; the path posteriors are evaluated by a
+// second forward sweep after the traceback; needs two_level).
 // Returns 0 or the cudaError_t of the launch.
 // two_level: checkpoints of every 8th group only (dp_ribbon.cuh SG), the rest replayed into a per-warp ring in pass 2
 int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps, bool two_level);

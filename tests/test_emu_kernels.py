@@ -257,6 +257,32 @@ def test_emulated_ribbon_two_level_checkpoints_identical(emu_lib):
     assert np.array_equal(out[0][1]["w"], out[1][1]["w"]) and np.array_equal(out[0][1]["xx"], out[1][1]["xx"])
 
 
+def test_emulated_ribbon_records_free_layout_identical(emu_lib):
+    """ribbon kernels, records-free scratch (long reads: row header = decision words, no posterior records, the path
+    posteriors from a second forward sweep after the traceback): same segments, same Z, and the same posteriors as the
+    record layout — bit for bit where the record layout kept the cell (posterior above its 2^-16 record threshold)"""
+    for name in ("rna002_band", "rna002_short", "rna004_9mer"):
+        cases = [c for c in load_golden() if c.name == name]
+        if not cases:
+            continue
+        case = cases[0]
+        out = {}
+        for ga in (0, 1):
+            al = _aligner(emu_lib, case, -1)
+            al.set_option("rib_gather", ga)
+            r = al.align(case.signal, case.sequence, True)
+            tm = al.last_timing()
+            assert tm["ribbon_reads"] == 1 and tm["ribbon_faults"] == 0
+            assert al.ribbon_fault_reasons()["records_free_layout"] == bool(ga)
+            check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+            out[ga] = r
+        assert out[0]["Z"] == out[1]["Z"]
+        assert np.array_equal(out[0]["signal_positions"], out[1]["signal_positions"])
+        kept = out[0]["probabilities"] > 2.0 ** -15
+        assert np.array_equal(out[0]["probabilities"][kept], out[1]["probabilities"][kept])
+        np.testing.assert_allclose(out[0]["probabilities"], out[1]["probabilities"], atol=2.0 ** -15)
+
+
 def test_emulated_ribbon_clips_the_reference_band_exactly(emu_lib):
     """the ribbon kernels clip every row to the reference band (NT:96-106) when the window reaches beyond it: a read whose
     band is narrower than the window, a read whose alignment drifts to the band edge (3 samples per base), and a band so

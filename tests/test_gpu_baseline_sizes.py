@@ -91,6 +91,32 @@ def test_c4_10kb_gamma_dwell_read_vs_reference(models_dir):
     print("c4 10 kb: %d/%d borders identical, max |dp| %.2e" % (same, seg, dp))
 
 
+def test_c4_records_free_layout_vs_reference_and_record_layout(models_dir):
+    """config 4's scratch layout (chosen by the engine when the resident warps' record buffers would not fit: two-level
+    checkpoints, row header = decision words, path posteriors from a second forward sweep after the traceback), forced
+    here on a 10 kb Gamma-dwell read and two c2-sized reads: parity against the reference, and identical to the record layout"""
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import materialize_model
+    path = materialize_model("synthetic_rna004_9mer", models_dir)
+    reads = _reads(path, "rna004", [(10000, 40)], seed=20264000, dwell="gamma") + \
+        _reads(path, "rna004", [(700, 30), (3000, 30)], seed=20264001)
+    al = Aligner(path, "rna004")
+    al.set_option("rib_gather", 1)
+    same, seg, dp = _compare(al, _checker(path, "rna004"), reads, "c4 records-free")
+    tm = al.last_timing()
+    assert tm["ribbon_reads"] == 3 and tm["ribbon_faults"] == 0 and al.ribbon_fault_reasons()["records_free_layout"]
+    got = al.align_batch([s for s, _ in reads], [q for _, q in reads], True, raise_errors=True)
+    al2 = Aligner(path, "rna004")
+    al2.set_option("rib_gather", 0)
+    ref = al2.align_batch([s for s, _ in reads], [q for _, q in reads], True, raise_errors=True)
+    assert not al2.ribbon_fault_reasons()["records_free_layout"]
+    for a, b in zip(got, ref):
+        assert a["Z"] == b["Z"] and np.array_equal(a["signal_positions"], b["signal_positions"])
+        kept = b["probabilities"] > 2.0 ** -15   # the record layout drops posteriors below its 2^-16 record threshold
+        assert np.array_equal(a["probabilities"][kept], b["probabilities"][kept])
+    print("c4 records-free: %d/%d borders identical, max |dp| %.2e" % (same, seg, dp))
+
+
 def test_unrounded_float64_signal_vs_reference(models_dir):
     """A float64 signal that is NOT FP32-representable (what (x - shift) / scale produces): the C ABI takes float64
     (dyn_align_batch_f64, as aligner_bindings.cpp:111-147 does) and rounds to FP32 on the way to the device; the
