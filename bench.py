@@ -525,6 +525,12 @@ def main():
             hb.copy_(b["bases"])
             host.append((hs, hb, b["sig_off"], b["seq_off"]))
         torch.cuda.synchronize()
+        # the end-to-end phase owns the device: the resident copies of the inputs go (the C ABI stages its own per batch)
+        for b in batches:
+            b.pop("sig", None)
+            b.pop("bases", None)
+        del d_sig, d_bas
+        torch.cuda.empty_cache()
 
         # the call a streaming user makes: dyn_align_submit / dyn_align_wait (Aligner.submit_packed / wait), two batches in
         # flight, so that the H2D copy of the next batch and the D2H copy + fan-out of the previous one overlap the kernels
@@ -615,15 +621,23 @@ def main():
     alg_per_cell = 6.0 if train else 4.0
     alg_mufu = alg_per_cell * cells / dp_s / 1e9
     rows = float(n_samples)
+    rib_info = al.ribbon_fault_reasons()
     if ribbon_on:
-        # executed: 3 passes x 64 ring slots per row x 1 MUFU
-        exe_mufu = 3.0 * 64.0 * rows / dp_s / 1e9
+        # executed: sweeps x 64 ring slots per row x 1 MUFU.  3 sweeps (backward, recomputation, forward); two-level checkpoints
+        # replay the backward sweep once more; the records-free layout of long reads adds a second recomputation + forward
+        # sweep (and its replay) for the path posteriors
+        sweeps = 7.0 if rib_info.get("records_free_layout") else (4.0 if rib_info.get("two_level_checkpoints") else 3.0)
+        exe_mufu = sweeps * 64.0 * rows / dp_s / 1e9
         kern = "k_ribbon<RCfg<2>,%d,5> (ribbon: 63-column window that follows the probability mass, groups of 8 rows, linear-domain FP32 " \
-               "block floating point, 1 MUFU per evaluated cell-update, 3 passes)" % (2 if train else 1)
+               "block floating point, 1 MUFU per evaluated cell-update, %d sweeps%s)" % (
+                   3 if rib_info.get("records_free_layout") else (2 if train else 1), int(sweeps),
+                   "; long reads: two-level checkpoints, records-free scratch, path posteriors from a second forward sweep"
+                   if rib_info.get("records_free_layout") else "")
     else:
         exe_mufu = (3.0 if lin else 6.0) * cells / dp_s / 1e9
         kern = kernel_label(al.last_timing()["variant"], lin)
-    ck = counters.get("train" if train else "align", {}) if ribbon_on else {}
+    ck_key = "train" if train else ("align_records_free" if rib_info.get("records_free_layout") else "align")
+    ck = counters.get(ck_key, {}) if ribbon_on else {}
     traffic = ck.get("dram_bytes_per_row") * rows / max(1, len(batches)) if ck.get("dram_bytes_per_row") else None
     roofline = {
         "bound": "sfu",
@@ -636,7 +650,7 @@ def main():
         "kernel_ms": dp_ms_all, "lattice_rows_per_s": 3.0 * rows / dp_s,
         "log2_fallback_reads": int(fallbacks), "lin_retry_reads": int(lin_retries),
         "ribbon_reads": int(step_device.rib[0]), "ribbon_fault_reads": int(step_device.rib[1]),
-        "ribbon_fault_reasons": al.ribbon_fault_reasons(),
+        "ribbon_fault_reasons": rib_info,
         "issue": {"source": ck.get("source"), "warp_instructions_per_lattice_row": ck.get("instr_per_row"),
                   "issue_slots_busy_pct": ck.get("issue_busy_pct"), "xu_pipe_pct": ck.get("xu_pct"),
                   "achieved_warp_instr_per_s": (ck.get("instr_per_row") * rows / dp_s) if ck.get("instr_per_row") else None,

@@ -43,6 +43,12 @@ using namespace dyn;
 				__FILE__ + ":" + std::to_string(__LINE__));                                         \
 	} while (0)
 
+// device memory exhausted: run_batch releases the shared ribbon scratch pool and retries once
+struct DevOom : std::runtime_error
+{
+	using std::runtime_error::runtime_error;
+};
+
 struct Rt
 {
 	cudaStream_t stream = nullptr;
@@ -84,8 +90,13 @@ struct Rt
 	void* dmalloc(size_t n)
 	{
 		void* p = nullptr;
-		if (async_alloc) CK_CUDA(cudaMallocAsync(&p, n ? n : 1, stream));
-		else CK_CUDA(cudaMalloc(&p, n ? n : 1));
+		const cudaError_t e = async_alloc ? cudaMallocAsync(&p, n ? n : 1, stream) : cudaMalloc(&p, n ? n : 1);
+		if (e == cudaErrorMemoryAllocation)
+		{
+			cudaGetLastError();  // not sticky: clear it
+			throw DevOom("CUDA error: out of memory allocating " + std::to_string(n >> 20) + " MB of device memory");
+		}
+		CK_CUDA(e);
 		return p;
 	}
 	void dfree(void* p)
@@ -1473,7 +1484,39 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	}
 }
 
+void run_batch_variant(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
+	double* pooled, double* per_read_w);
+
 void run_batch(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
+	double* pooled, double* per_read_w)
+{
+#ifndef DYN_HOST_EMU
+	try
+	{
+		run_batch_variant(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w);
+	}
+	catch (const DevOom&)
+	{
+		// The ribbon scratch pool is sized from the memory that is free when a batch needs it (92 %); buffers allocated
+		// later (another lane's inputs, a larger batch) can then fail.  Give the pool back — nothing enqueued may still use
+		// it: compute_mu keeps the lanes from enqueueing, the root's stream is drained — and run the batch once more; the
+		// pool is re-sized from what is free then.
+		dyn_aligner& R = A.root ? *A.root : A;
+		{
+			std::lock_guard<std::mutex> cl(R.compute_mu);
+			R.rt.sync();
+			A.rt.sync();
+			R.d_rib_scratch.release(R.rt);
+			A.d_scratch.release(A.rt);
+		}
+		run_batch_variant(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w);
+	}
+#else
+	run_batch_variant(A, io, mode, res, sigpos_h, prob_h, pooled, per_read_w);
+#endif
+}
+
+void run_batch_variant(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, uint32_t* sigpos_h, double* prob_h,
 	double* pooled, double* per_read_w)
 {
 	int v = A.variant;
@@ -2307,7 +2350,7 @@ namespace
 // device state of one resquiggle-mode read between the pre-pass and the sparse stages
 struct NtkRun
 {
-	DevBuf b_model, b_sig, b_kmers, b_lat, b_rows, b_z, b_tn, b_tk, b_cnt, b_keys, b_sparse, b_seg;
+	DevBuf b_model, b_sig, b_kmers, b_lat, b_rows, b_z, b_tn, b_tk, b_cnt, b_keys, b_sparse, b_seg, b_wide;
 	uint32_t T = 0, N = 0, K = 0, hp = 1, wn = 0, wk = 0;
 	uint64_t Kc = 0, total = 0;
 	double z[4] = {0, 0, 0, 0};
@@ -2315,7 +2358,7 @@ struct NtkRun
 	dyn::ntk::Consts consts;
 	void release(Rt& rt)
 	{
-		for (DevBuf* b : {&b_model, &b_sig, &b_kmers, &b_lat, &b_rows, &b_z, &b_tn, &b_tk, &b_cnt, &b_keys, &b_sparse, &b_seg}) b->release(rt);
+		for (DevBuf* b : {&b_model, &b_sig, &b_kmers, &b_lat, &b_rows, &b_z, &b_tn, &b_tk, &b_cnt, &b_keys, &b_sparse, &b_seg, &b_wide}) b->release(rt);
 	}
 };
 
@@ -2428,7 +2471,27 @@ int ntk_prepass_device(dyn_aligner* A, Rt& rt, const float* signal, uint64_t S, 
 		rt.d2h(z + 2, d_z + 2, 16);
 		rt.sync();
 		if (std::abs(z[2] - z[3]) / (double)((size_t)T * K) > EPS || std::isinf(z[2]) || std::isinf(z[3]) || std::isnan(z[2]) || std::isnan(z[3])) return DYN_NTK_TK_FAILED;
-		k_row_mask<<<T, 256, 0, rt.stream>>>(lp, K, wk, d_tk, threshold + z[3]);  // Zb (NTK:382)
+		if (K >= 4 * RM_CHUNK)
+		{
+			// wide rows (9-mers): row maximum and candidate compaction over (row, chunk) CTAs, one CTA per row for the sort +
+			// sequential log-sum-exp; k_row_mask only for the rows that path leaves undecided
+			const size_t o_max = 0, o_cnt = align_up(o_max + (size_t)T * 8, 256), o_todo = align_up(o_cnt + (size_t)T * 4, 256),
+						 o_val = align_up(o_todo + (size_t)T * 4, 256), o_idx = align_up(o_val + (size_t)T * RM_CAP * 8, 256),
+						 o_end = o_idx + (size_t)T * RM_CAP * 4;
+			unsigned char* d_w = (unsigned char*)R.b_wide.get(rt, o_end);
+			rt.zero(d_w, o_val);
+			rt.zero(d_tk, (size_t)T * wk * 4);
+			WideMaskArgs wa;
+			wa.LP = lp; wa.C = K; wa.T = T; wa.words = wk; wa.mask = d_tk; wa.threshold = threshold + z[3];  // Zb (NTK:382)
+			wa.rowmax = (unsigned long long*)(d_w + o_max); wa.cnt = (uint32_t*)(d_w + o_cnt); wa.todo = (uint32_t*)(d_w + o_todo);
+			wa.cval = (double*)(d_w + o_val); wa.cidx = (uint32_t*)(d_w + o_idx);
+			const dim3 g2((K + RM_CHUNK - 1) / RM_CHUNK, T);
+			k_wide_rowmax<<<g2, 256, 0, rt.stream>>>(wa);
+			k_wide_candidates<<<g2, 256, 0, rt.stream>>>(wa);
+			k_wide_select<<<T, 256, 0, rt.stream>>>(wa);
+			k_row_mask<<<T, 256, 0, rt.stream>>>(lp, K, wk, d_tk, wa.threshold, wa.todo);
+		}
+		else k_row_mask<<<T, 256, 0, rt.stream>>>(lp, K, wk, d_tk, threshold + z[3]);  // Zb (NTK:382)
 		CK_CUDA(cudaGetLastError());
 	}
 	// ---- keys (preProcTNK, NTK:402-441)

@@ -69,13 +69,16 @@ constexpr int RM_CAP = 2048;
 
 __device__ __forceinline__ bool rm_before(double va, uint32_t ia, double vb, uint32_t ib) { return va > vb || (va == vb && ia < ib); }
 
-__global__ void __launch_bounds__(256) k_row_mask(const double* LP, uint32_t C, uint32_t words, uint32_t* mask, double threshold)
+// rows_todo (may be null): only the rows with rows_todo[t] != 0 (the wide-row path's leftovers)
+__global__ void __launch_bounds__(256) k_row_mask(const double* LP, uint32_t C, uint32_t words, uint32_t* mask, double threshold,
+	const uint32_t* rows_todo = nullptr)
 {
 	__shared__ double s_val[RM_CAP];
 	__shared__ uint32_t s_idx[RM_CAP];
 	__shared__ double s_red[8];
 	__shared__ int s_n, s_stop;
 	const uint32_t t = blockIdx.x;
+	if (rows_todo && rows_todo[t] == 0u) return;
 	const double* row = LP + (size_t)t * C;
 	uint32_t* m = mask + (size_t)t * words;
 	for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) m[i] = 0u;
@@ -209,6 +212,136 @@ __global__ void __launch_bounds__(256) k_row_mask(const double* LP, uint32_t C, 
 		__syncthreads();
 		if (s_stop) break;
 		__syncthreads();
+	}
+}
+
+// ---- wide rows (9-mers: 262 144 columns): the same selection with the whole GPU on the two sweeps over the row ---------
+// One CTA per row leaves a 2 MB row to 256 threads (264 ms for the 634 rows of a 60-base read); here the row maximum and
+// the candidate compaction run over (row, chunk) CTAs, and only the sort + sequential log-sum-exp of the <= RM_CAP
+// candidates is one CTA per row.  Rows the compact path cannot decide (more than RM_CAP candidates, all -inf, threshold
+// not reached) are flagged and go through k_row_mask (rows_todo).
+constexpr uint32_t RM_CHUNK = 8192;
+
+__device__ __forceinline__ unsigned long long rm_key(double v)
+{
+	const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+	return (b >> 63) ? ~b : (b | 0x8000000000000000ull);  // monotone in v (-inf lowest)
+}
+__device__ __forceinline__ double rm_unkey(unsigned long long k)
+{
+	return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+struct WideMaskArgs
+{
+	const double* LP;
+	uint32_t C, T, words;
+	uint32_t* mask;               // [T][words], zeroed by the host
+	double threshold;
+	unsigned long long* rowmax;   // [T] rm_key of the row maximum, zeroed by the host
+	uint32_t* cnt;                // [T] candidates found, zeroed by the host
+	double* cval;                 // [T][RM_CAP]
+	uint32_t* cidx;               // [T][RM_CAP]
+	uint32_t* todo;               // [T] 1: the row needs k_row_mask
+};
+
+__global__ void __launch_bounds__(256) k_wide_rowmax(WideMaskArgs a)
+{
+	__shared__ double s_red[8];
+	const uint32_t t = blockIdx.y, c0 = blockIdx.x * RM_CHUNK, c1 = min(c0 + RM_CHUNK, a.C);
+	const double* row = a.LP + (size_t)t * a.C;
+	double mx = neg_inf();
+	for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) mx = fmax(mx, row[i]);
+	for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		for (int w = 1; w < 8; ++w) mx = fmax(mx, s_red[w]);
+		atomicMax(&a.rowmax[t], rm_key(mx));
+	}
+}
+
+__global__ void __launch_bounds__(256) k_wide_candidates(WideMaskArgs a)
+{
+	const uint32_t t = blockIdx.y, c0 = blockIdx.x * RM_CHUNK, c1 = min(c0 + RM_CHUNK, a.C);
+	const double* row = a.LP + (size_t)t * a.C;
+	const double mx = rm_unkey(a.rowmax[t]);
+	if (isinf(mx) || isnan(mx)) return;
+	const double cut = mx - 40.0;
+	for (uint32_t i = c0 + threadIdx.x; i < c1; i += blockDim.x)
+	{
+		const double v = row[i];
+		if (v >= cut)
+		{
+			const uint32_t pos = atomicAdd(&a.cnt[t], 1u);
+			if (pos < (uint32_t)RM_CAP)
+			{
+				a.cval[(size_t)t * RM_CAP + pos] = v;
+				a.cidx[(size_t)t * RM_CAP + pos] = i;
+			}
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256) k_wide_select(WideMaskArgs a)
+{
+	__shared__ double s_val[RM_CAP];
+	__shared__ uint32_t s_idx[RM_CAP];
+	const uint32_t t = blockIdx.x;
+	const int n = (int)a.cnt[t];
+	if (n == 0 || n > RM_CAP)
+	{
+		if (threadIdx.x == 0) a.todo[t] = 1u;
+		return;
+	}
+	int np2 = 1;
+	while (np2 < n) np2 <<= 1;
+	for (int i = threadIdx.x; i < np2; i += blockDim.x)
+	{
+		s_val[i] = (i < n) ? a.cval[(size_t)t * RM_CAP + i] : neg_inf();
+		s_idx[i] = (i < n) ? a.cidx[(size_t)t * RM_CAP + i] : 0xffffffffu;  // padding sorts last
+	}
+	__syncthreads();
+	// bitonic sort, "before" = larger value, then smaller index (the order the atomics filled the list in does not matter)
+	for (int k = 2; k <= np2; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1)
+		{
+			for (int i = threadIdx.x; i < np2; i += blockDim.x)
+			{
+				const int l = i ^ j;
+				if (l > i)
+				{
+					const bool up = (i & k) == 0;
+					const double va = s_val[i], vb = s_val[l];
+					const uint32_t ia = s_idx[i], ib = s_idx[l];
+					const bool swap = up ? rm_before(vb, ib, va, ia) : rm_before(va, ia, vb, ib);
+					if (swap)
+					{
+						s_val[i] = vb; s_idx[i] = ib;
+						s_val[l] = va; s_idx[l] = ia;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	if (threadIdx.x == 0)
+	{
+		uint32_t* m = a.mask + (size_t)t * a.words;
+		double sum = neg_inf();
+		int reached = 0, k = 0;
+		for (; k < n; ++k)
+		{
+			const uint32_t i = s_idx[k];
+			m[i >> 5] |= 1u << (i & 31);
+			sum = log_plus(sum, s_val[k]);
+			if (sum >= a.threshold) { reached = 1; break; }
+		}
+		if (!reached && n < (int)a.C)
+		{
+			// the candidates do not carry the threshold mass: k_row_mask starts over (it zeroes the row's mask itself)
+			a.todo[t] = 1u;
+		}
 	}
 }
 
