@@ -111,6 +111,24 @@ DYN_DEV float warp_sum(float v, int lane)
 	return v;
 }
 
+// packed FP32x2 arithmetic (sm_100a FMUL2 / FFMA2: one issue slot for two lattice columns; the kernels are bound by issue
+// slots).  Plain IEEE round-to-nearest per component: bit-identical to the scalar instructions they replace.
+#ifndef DYN_HOST_EMU
+DYN_DEV float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+DYN_DEV float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else
+DYN_DEV float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+DYN_DEV float2 fma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+
+// a copy of v in a register of its own: a value used straight out of a 128-bit load stays tied to that load's register
+// quad, and the FFMA2 that wants it as half of an aligned pair then pays two moves per lattice row
+#ifndef DYN_HOST_EMU
+DYN_DEV float untie(float v) { return __fadd_rn(v, 0.0f); }  // (v is a positive constant: no -0 to lose)
+#else
+DYN_DEV float untie(float v) { return v; }
+#endif
+
 DYN_DEV int fexp(float v) { return ((__float_as_int(v) >> 23) & 0xff) - 127; }
 DYN_DEV bool is_alive(float v) { return v > 0.0f && v < 3.0e38f; }
 
@@ -156,11 +174,20 @@ struct RWarp
 	uint32_t T, N, S;
 	int bw_ref;       // the reference's half band width (NT:243)
 	double ratio;
+	float ratio_f;
 	const float* sig;
 	const PosConst* pc;
-	float a[C], b[C], c[C];  // log2 N(x; mu, sigma) = c - (x*a - b)^2 of the column in each ring slot (dead slot: c = CNEG)
+	// log2 N(x; mu, sigma) = c - (x*a - b)^2 of the column in each ring slot (dead slot: c = CNEG), kept as a, -b, -c so that
+	// a pair of columns is two FFMA2: z = x*a + (-b), -e = z*z + (-c)
+	float a[C], nb[C], nc[C];
 
-	DYN_DEV float emis(int j, float x) const { return emis2(x, a[j], b[j], c[j]); }
+	// emission probabilities 2^e of the slot pair h (slots 2h, 2h+1) for sample x
+	DYN_DEV float2 emis_pair(int h, float2 x2) const
+	{
+		const float2 z = fma2(x2, make_float2(a[2 * h], a[2 * h + 1]), make_float2(nb[2 * h], nb[2 * h + 1]));
+		const float2 ne = fma2(z, z, make_float2(nc[2 * h], nc[2 * h + 1]));  // = -fma(-z, z, c) exactly
+		return make_float2(ex2(-ne.x), ex2(-ne.y));
+	}
 	// lattice column held by ring slot q when the window starts at column lo (may be negative)
 	DYN_DEV static int col_of_slot(int q, int lo) { return lo + pmod(q - lo, RC::SLOTS); }
 	DYN_DEV void set_dead(int j)
@@ -170,8 +197,8 @@ struct RWarp
 			if (jj == j)
 			{
 				a[jj] = 0.0f;
-				b[jj] = 0.0f;
-				c[jj] = CNEG;
+				nb[jj] = 0.0f;
+				nc[jj] = -CNEG;
 			}
 	}
 	DYN_DEV void set_col(int j, const PosConst& v)
@@ -180,9 +207,9 @@ struct RWarp
 		for (int jj = 0; jj < C; ++jj)
 			if (jj == j)
 			{
-				a[jj] = v.a;
-				b[jj] = v.b;
-				c[jj] = v.c;
+				a[jj] = untie(v.a);
+				nb[jj] = -v.b;
+				nc[jj] = -v.c;
 			}
 	}
 	// emission constants of every column of the window centred at mid; everything else dead
@@ -197,15 +224,15 @@ struct RWarp
 			if (n >= 0 && n <= nlast)
 			{
 				const PosConst v = pc[n];
-				a[j] = v.a;
-				b[j] = v.b;
-				c[j] = v.c;
+				a[j] = untie(v.a);
+				nb[j] = -v.b;
+				nc[j] = -v.c;
 			}
 			else
 			{
 				a[j] = 0.0f;
-				b[j] = 0.0f;
-				c[j] = CNEG;
+				nb[j] = 0.0f;
+				nc[j] = -CNEG;
 			}
 		}
 	}
@@ -251,6 +278,12 @@ template <class RC>
 DYN_DEV bool group_needs_clip(const RWarp<RC>& w, int mid, int g)
 {
 	const uint32_t t0 = 8u * (uint32_t)g, t1 = min(t0 + 8u, w.T - 1u);
+	// cheap FP32 estimate of the band centre first (t * ratio < 2^17 for any read that fits the device: off by << 1 column);
+	// the exact double-precision centres of the reference only when the window is within two columns of the band's edge
+	const float c0 = (float)t0 * w.ratio_f;
+	const int lo_room = (mid - RC::HW) - ((int)c0 - w.bw_ref), hi_room = ((int)c0 + w.bw_ref) - (mid + RC::HW);
+	// (the estimate is within one column of band_mid(t0); the centre moves <= 5 columns over the group's rows: ratio <= 1/2)
+	if (lo_room > 8 && hi_room > 3) return false;
 	const int m0 = (int)band_mid(t0, w.ratio), m1 = (int)band_mid(t1, w.ratio);  // band centres are non-decreasing in t
 	return (mid + RC::HW > m0 + w.bw_ref) || (mid - RC::HW < m1 - w.bw_ref);
 }
@@ -279,28 +312,31 @@ DYN_DEV void clip_row(const RWarp<RC>& w, float (&p)[RC::CPL], float (&q)[RC::CP
 template <class RC>
 DYN_DEV void bwd_row(const RWarp<RC>& w, Bw<RC::CPL>& b, float x, float m1, float e2)
 {
-	constexpr int C = RC::CPL;
-	float p[C], A[C];
-	// A[n] = bM[t+1][n] * p(t,n) * m1 is consumed by column n-1; slot 0 first: its shuffle has the rest of the row to complete
-	p[0] = ex2(w.emis(0, x));
-	A[0] = b.bM[0] * (p[0] * m1);
-	const float Araw = __shfl_sync(FULL, A[0], (w.lane + 1) & 31);
+	constexpr int C = RC::CPL, H = C / 2;
+	static_assert(C % 2 == 0, "columns per lane come in pairs (FMUL2 / FFMA2)");
+	const float2 x2 = make_float2(x, x), m2 = make_float2(m1, m1), e22 = make_float2(e2, e2);
+	float2 p[H], A[H];
+	// A[n] = bM[t+1][n] * p(t,n) * m1 is consumed by column n-1; pair 0 first: its shuffle has the rest of the row to complete
+	p[0] = w.emis_pair(0, x2);
+	A[0] = mul2(make_float2(b.bM[0], b.bM[1]), mul2(p[0], m2));
+	const float Araw = __shfl_sync(FULL, A[0].x, (w.lane + 1) & 31);
 #pragma unroll
-	for (int j = 1; j < C; ++j)
+	for (int h = 1; h < H; ++h)
 	{
-		p[j] = ex2(w.emis(j, x));
-		A[j] = b.bM[j] * (p[j] * m1);
+		p[h] = w.emis_pair(h, x2);
+		A[h] = mul2(make_float2(b.bM[2 * h], b.bM[2 * h + 1]), mul2(p[h], m2));
 	}
 #pragma unroll
-	for (int j = 0; j + 1 < C; ++j)
+	for (int h = 0; h < H; ++h)
 	{
-		const float nm = b.bE[j] * p[j];   // bM[t][n] = bE[t+1][n] * p            (NT:200)
-		b.bE[j] = fmaf(nm, e2, A[j + 1]);  //                                      (NT:194,201,204)
-		b.bM[j] = nm;
+		const float2 nm = mul2(make_float2(b.bE[2 * h], b.bE[2 * h + 1]), p[h]);  // bM[t][n] = bE[t+1][n] * p           (NT:200)
+		const float2 in = make_float2(A[h].y, (h + 1 < H) ? A[(h + 1 < H) ? h + 1 : h].x : Araw * b.sR);
+		const float2 ne = fma2(nm, e22, in);                                        //                                     (NT:194,201,204)
+		b.bM[2 * h] = nm.x;
+		b.bM[2 * h + 1] = nm.y;
+		b.bE[2 * h] = ne.x;
+		b.bE[2 * h + 1] = ne.y;
 	}
-	const float nml = b.bE[C - 1] * p[C - 1];
-	b.bM[C - 1] = nml;
-	b.bE[C - 1] = fmaf(nml, e2, Araw * b.sR);
 }
 
 // window one column down (backward direction): the top column retires, the column below the window takes the dead slot
@@ -423,6 +459,7 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 		const float xg = x8;
 		if (g > 0) x8 = w.sig[8 * (g - 1) + (lane & 7)];
 		const bool clip = group_needs_clip<RC>(w, mid, g);
+		__syncwarp();  // (the compiler then knows the warp is converged: plain SHFL instead of WARPSYNC + SHFL + ENDCOLLECTIVE per row)
 		if (g < gl && !clip)
 		{
 #pragma unroll
@@ -539,19 +576,30 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 	constexpr bool VIT = (MODE == 1 || MODE == 3);
 	const int lane = w.lane;
 	// the values the right lane needs are those of the previous row: send them first, consume them last
+	constexpr int H = C / 2;
 	const float vlraw = VIT ? __shfl_sync(FULL, f.VE[C - 1], (lane + 31) & 31) : 0.0f;
 	const float flraw = STEP ? __shfl_sync(FULL, f.fE[C - 1], (lane + 31) & 31) : 0.0f;
-	float p[C], PM[C], PE[C];
-#pragma unroll
-	for (int j = 0; j < C; ++j) p[j] = STEP ? ex2(w.emis(j, x)) : 0.0f;
+	const float2 x2 = make_float2(x, x);
+	float2 p[H];
+	float PM[C], PE[C];
 	float msum = 0.0f;
 #pragma unroll
-	for (int j = 0; j < C; ++j)
+	for (int h = 0; h < H; ++h)
 	{
-		PE[j] = f.fE[j] * bc[j];
+		p[h] = STEP ? w.emis_pair(h, x2) : make_float2(0.0f, 0.0f);
+		const float2 pe = mul2(make_float2(f.fE[2 * h], f.fE[2 * h + 1]), make_float2(bc[2 * h], bc[2 * h + 1]));
 		// bM[t][n] = bE[t+1][n] * p(t,n) (NT:200); the last row has no match state
-		PM[j] = STEP ? f.fM[j] * (bn[j] * p[j]) : 0.0f;
-		if (MASS) msum += PM[j] + PE[j];
+		const float2 pm = STEP ? mul2(make_float2(f.fM[2 * h], f.fM[2 * h + 1]), mul2(make_float2(bn[2 * h], bn[2 * h + 1]), p[h]))
+		                       : make_float2(0.0f, 0.0f);
+		PE[2 * h] = pe.x;
+		PE[2 * h + 1] = pe.y;
+		PM[2 * h] = pm.x;
+		PM[2 * h + 1] = pm.y;
+		if (MASS)
+		{
+			msum += pm.x + pe.x;
+			msum += pm.y + pe.y;
+		}
 	}
 	if (VIT)
 	{
@@ -560,15 +608,24 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 		const float vl = vlraw * f.sV;
 		unsigned bits[C];
 		float lmax = 0.0f;
+		float vmx[C], left[C];
 #pragma unroll
 		for (int j = C - 1; j >= 0; --j)
 		{
-			const float vmx = fmaxf(f.VM[j], f.VE[j]);
+			vmx[j] = fmaxf(f.VM[j], f.VE[j]);
 			bits[j] = __ballot_sync(FULL, f.VM[j] < f.VE[j]);
-			const float left = (j > 0) ? f.VE[j - 1] : vl;
-			f.VM[j] = left * PM[j];
-			f.VE[j] = vmx * PE[j];
+			left[j] = (j > 0) ? f.VE[j - 1] : vl;
 			if (MODE == 1) lmax = lin::max3f(lmax, PM[j], PE[j]);
+		}
+#pragma unroll
+		for (int h = 0; h < H; ++h)
+		{
+			const float2 vm = mul2(make_float2(left[2 * h], left[2 * h + 1]), make_float2(PM[2 * h], PM[2 * h + 1]));
+			const float2 ve = mul2(make_float2(vmx[2 * h], vmx[2 * h + 1]), make_float2(PE[2 * h], PE[2 * h + 1]));
+			f.VM[2 * h] = vm.x;
+			f.VM[2 * h + 1] = vm.y;
+			f.VE[2 * h] = ve.x;
+			f.VE[2 * h + 1] = ve.y;
 		}
 		if (MODE == 3)
 		{
@@ -650,13 +707,20 @@ DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<
 	if (STEP)
 	{
 		const float fl = flraw * f.sL;
+		const float2 m2 = make_float2(m1, m1), e22 = make_float2(e2, e2);
+		float left[C];
 #pragma unroll
-		for (int j = C - 1; j >= 0; --j)
+		for (int j = 0; j < C; ++j) left[j] = (j > 0) ? f.fE[j - 1] : fl;
+#pragma unroll
+		for (int h = 0; h < H; ++h)
 		{
-			const float left = (j > 0) ? f.fE[j - 1] : fl;
-			const float ne = fmaf(f.fE[j], e2, f.fM[j]) * p[j];  // (fM + fE*e2) * p    (NT:146-150, e1 = 1)
-			f.fM[j] = left * (p[j] * m1);                        // fE[t][n-1] * p * m1  (NT:143)
-			f.fE[j] = ne;
+			const float2 fe = make_float2(f.fE[2 * h], f.fE[2 * h + 1]);
+			const float2 ne = mul2(fma2(fe, e22, make_float2(f.fM[2 * h], f.fM[2 * h + 1])), p[h]);  // (fM + fE*e2) * p    (NT:146-150, e1 = 1)
+			const float2 nm = mul2(make_float2(left[2 * h], left[2 * h + 1]), mul2(p[h], m2));       // fE[t][n-1] * p * m1  (NT:143)
+			f.fM[2 * h] = nm.x;
+			f.fM[2 * h + 1] = nm.y;
+			f.fE[2 * h] = ne.x;
+			f.fE[2 * h + 1] = ne.y;
 		}
 	}
 	return msum;
@@ -677,7 +741,23 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	const int lane = w.lane;
 	const int S = (int)w.S;
 	const int gl = (S - 1) >> 3;
-	float* const rows = reinterpret_cast<float*>(smem_raw) + lane;  // row k, slot j: rows[k * ROWF + j * 32]
+	// row k, slot pair h (slots 2h, 2h+1) of this lane: rows2[(k * H2 + h) * 32] — one 64-bit shared-memory access per pair
+	constexpr int H2 = C / 2;
+	float2* const rows2 = reinterpret_cast<float2*>(smem_raw) + lane;
+	auto put_row = [&](int k, const Bw<C>& bb, float kp) {
+		const float2 k2 = make_float2(kp, kp);
+#pragma unroll
+		for (int h = 0; h < H2; ++h) rows2[(k * H2 + h) * 32] = mul2(make_float2(bb.bE[2 * h], bb.bE[2 * h + 1]), k2);
+	};
+	auto get_row = [&](int k, float (&dst)[C]) {
+#pragma unroll
+		for (int h = 0; h < H2; ++h)
+		{
+			const float2 v = rows2[(k * H2 + h) * 32];
+			dst[2 * h] = v.x;
+			dst[2 * h + 1] = v.y;
+		}
+	};
 	float* const recs = static_cast<float*>(sc.recs);
 	Fw<C> f;
 	Bw<C> b;
@@ -826,29 +906,26 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		b.sR = lin::pow2i(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
 		const float kap = lin::kappa(f.OF, b.OB, Z2i, c0);
 		const bool clip = group_needs_clip<RC>(w, mid, g);
+		__syncwarp();  // (as in pass 1)
 		if (g < gl && !clip)
 		{
-#pragma unroll
-			for (int j = 0; j < C; ++j) rows[8 * ROWF + j * 32] = b.bE[j] * kap;
+			put_row(8, b, kap);
 #pragma unroll
 			for (int k = 7; k >= 0; --k)
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
-#pragma unroll
-				for (int j = 0; j < C; ++j) rows[k * ROWF + j * 32] = b.bE[j] * kap;
+				put_row(k, b, kap);
 			}
 		}
 		else
 		{
-#pragma unroll
-			for (int j = 0; j < C; ++j) rows[nr * ROWF + j * 32] = b.bE[j] * kap;
+			put_row(nr, b, kap);
 #pragma unroll 1
 			for (int k = nr - 1; k >= 0; --k)
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
 				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, 8u * (uint32_t)g + (uint32_t)k);
-#pragma unroll
-				for (int j = 0; j < C; ++j) rows[k * ROWF + j * 32] = b.bE[j] * kap;
+				put_row(k, b, kap);
 			}
 		}
 		__syncwarp();
@@ -859,15 +936,13 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		uint32_t* const hdr_g = (MODE == 4) ? reinterpret_cast<uint32_t*>(sc.pp) + (size_t)(8 * g) : sc.hdr + (size_t)(8 * g) * HDRS;
 		constexpr int HSTR = (MODE == 4) ? 1 : HDRS;
 		float bc[C], bn[C];
-#pragma unroll
-		for (int j = 0; j < C; ++j) bc[j] = rows[j * 32];
+		get_row(0, bc);
 		if (g < gl && !clip)
 		{
 #pragma unroll
 			for (int k = 0; k < 8; ++k)
 			{
-#pragma unroll
-				for (int j = 0; j < C; ++j) bn[j] = rows[(k + 1) * ROWF + j * 32];
+				get_row(k + 1, bn);
 				const float x = __shfl_sync(FULL, xg, k);
 				// the posterior mass is measured on the group's last row: offsets and the posterior factor are fixed inside
 				// a group, so a lane that lost its values or whose factor left the float range shows there
@@ -884,8 +959,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 #pragma unroll 1
 			for (int k = 0; k < nr; ++k)
 			{
-#pragma unroll
-				for (int j = 0; j < C; ++j) bn[j] = rows[(k + 1) * ROWF + j * 32];
+				get_row(k + 1, bn);
 				const float x = __shfl_sync(FULL, xg, k);
 				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, k) : 0u;
 				macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
@@ -917,7 +991,11 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			ta.sM = ta.sE = 0.0f;
 		}
 		if (g == gl) break;
+#ifndef DYN_HOST_EMU
+		c0 *= __fdividef(cnt, mass);  // (mass is 1 +- 1e-4: the fast reciprocal is exact to 2 ulp, and both sweeps use it)
+#else
 		c0 *= cnt / mass;
+#endif
 		// forward values: renormalise (own maximum -> [1, 2), at most RDC below the row's largest lane), window guard,
 		// range guard (largest forward x largest backward value of the row against Z)
 		{
@@ -1132,6 +1210,7 @@ DYN_DEV void ribbon_read(const BatchArgs& args, const ReadDesc& rd, uint32_t rid
 	w.N = rd.N;
 	w.bw_ref = (int)rd.bw;
 	w.ratio = rd.ratio;
+	w.ratio_f = (float)rd.ratio;
 	w.sig = args.signal + rd.sig_off;
 	w.pc = args.pc + rd.pc_off;
 

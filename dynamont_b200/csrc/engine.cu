@@ -1268,7 +1268,9 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				if (res.out[r].status == ST_LIN_FAULT)
 				{
 					const uint32_t why = res.out[r].nrec;
-					if (why == 1u || why == 12u) direct_log2.push_back(r);
+					// ... and so do long reads whatever the reason: a full-band tier is one warp for seconds per read
+					// (config 4: ~3 s per tier for 2 M rows), not worth two attempts that usually fail for the same reason
+					if (why == 1u || why == 12u || res.desc[r].S > 400000u) direct_log2.push_back(r);
 					else rest.push_back(r);
 					++A.n_rib_fault;
 					++A.rib_reason[std::min<uint32_t>(why, 15u)];
@@ -2476,19 +2478,19 @@ int ntk_prepass_device(dyn_aligner* A, Rt& rt, const float* signal, uint64_t S, 
 			// wide rows (9-mers): row maximum and candidate compaction over (row, chunk) CTAs, one CTA per row for the sort +
 			// sequential log-sum-exp; k_row_mask only for the rows that path leaves undecided
 			const size_t o_max = 0, o_cnt = align_up(o_max + (size_t)T * 8, 256), o_todo = align_up(o_cnt + (size_t)T * 4, 256),
-						 o_val = align_up(o_todo + (size_t)T * 4, 256), o_idx = align_up(o_val + (size_t)T * RM_CAP * 8, 256),
-						 o_end = o_idx + (size_t)T * RM_CAP * 4;
+						 o_val = align_up(o_todo + (size_t)T * 4, 256), o_idx = align_up(o_val + (size_t)T * RM_WIDE_CAP * 8, 256),
+						 o_end = o_idx + (size_t)T * RM_WIDE_CAP * 4;
 			unsigned char* d_w = (unsigned char*)R.b_wide.get(rt, o_end);
 			rt.zero(d_w, o_val);
 			rt.zero(d_tk, (size_t)T * wk * 4);
 			WideMaskArgs wa;
 			wa.LP = lp; wa.C = K; wa.T = T; wa.words = wk; wa.mask = d_tk; wa.threshold = threshold + z[3];  // Zb (NTK:382)
 			wa.rowmax = (unsigned long long*)(d_w + o_max); wa.cnt = (uint32_t*)(d_w + o_cnt); wa.todo = (uint32_t*)(d_w + o_todo);
-			wa.cval = (double*)(d_w + o_val); wa.cidx = (uint32_t*)(d_w + o_idx);
+			wa.cap = RM_WIDE_CAP; wa.cval = (double*)(d_w + o_val); wa.cidx = (uint32_t*)(d_w + o_idx);
 			const dim3 g2((K + RM_CHUNK - 1) / RM_CHUNK, T);
 			k_wide_rowmax<<<g2, 256, 0, rt.stream>>>(wa);
 			k_wide_candidates<<<g2, 256, 0, rt.stream>>>(wa);
-			k_wide_select<<<T, 256, 0, rt.stream>>>(wa);
+			k_wide_select<<<T, 1024, 0, rt.stream>>>(wa);
 			k_row_mask<<<T, 256, 0, rt.stream>>>(lp, K, wk, d_tk, wa.threshold, wa.todo);
 		}
 		else k_row_mask<<<T, 256, 0, rt.stream>>>(lp, K, wk, d_tk, threshold + z[3]);  // Zb (NTK:382)

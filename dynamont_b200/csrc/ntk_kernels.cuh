@@ -217,10 +217,11 @@ __global__ void __launch_bounds__(256) k_row_mask(const double* LP, uint32_t C, 
 
 // ---- wide rows (9-mers: 262 144 columns): the same selection with the whole GPU on the two sweeps over the row ---------
 // One CTA per row leaves a 2 MB row to 256 threads (264 ms for the 634 rows of a 60-base read); here the row maximum and
-// the candidate compaction run over (row, chunk) CTAs, and only the sort + sequential log-sum-exp of the <= RM_CAP
-// candidates is one CTA per row.  Rows the compact path cannot decide (more than RM_CAP candidates, all -inf, threshold
-// not reached) are flagged and go through k_row_mask (rows_todo).
+// the candidate compaction run over (row, chunk) CTAs, and only the sort + sequential log-sum-exp of the candidates
+// (<= cap per row, RM_WIDE_CAP by default) is one CTA per row.  Rows the compact path cannot decide (more candidates than
+// that, all -inf, threshold not reached) are flagged and go through k_row_mask (rows_todo).
 constexpr uint32_t RM_CHUNK = 8192;
+constexpr uint32_t RM_WIDE_CAP = 65536;
 
 __device__ __forceinline__ unsigned long long rm_key(double v)
 {
@@ -240,8 +241,9 @@ struct WideMaskArgs
 	double threshold;
 	unsigned long long* rowmax;   // [T] rm_key of the row maximum, zeroed by the host
 	uint32_t* cnt;                // [T] candidates found, zeroed by the host
-	double* cval;                 // [T][RM_CAP]
-	uint32_t* cidx;               // [T][RM_CAP]
+	uint32_t cap;                 // candidates kept per row (a power of two)
+	double* cval;                 // [T][cap]
+	uint32_t* cidx;               // [T][cap]
 	uint32_t* todo;               // [T] 1: the row needs k_row_mask
 };
 
@@ -275,51 +277,69 @@ __global__ void __launch_bounds__(256) k_wide_candidates(WideMaskArgs a)
 		if (v >= cut)
 		{
 			const uint32_t pos = atomicAdd(&a.cnt[t], 1u);
-			if (pos < (uint32_t)RM_CAP)
+			if (pos < a.cap)
 			{
-				a.cval[(size_t)t * RM_CAP + pos] = v;
-				a.cidx[(size_t)t * RM_CAP + pos] = i;
+				a.cval[(size_t)t * a.cap + pos] = v;
+				a.cidx[(size_t)t * a.cap + pos] = i;
 			}
 		}
 	}
 }
 
-__global__ void __launch_bounds__(256) k_wide_select(WideMaskArgs a)
+// one CTA per row: sort the row's candidates by (value descending, index ascending) — in shared memory when there are
+// <= RM_CAP of them, in place in their (L2-resident) global list otherwise — then the reference's sequential log-sum-exp
+__global__ void __launch_bounds__(1024) k_wide_select(WideMaskArgs a)
 {
 	__shared__ double s_val[RM_CAP];
 	__shared__ uint32_t s_idx[RM_CAP];
 	const uint32_t t = blockIdx.x;
-	const int n = (int)a.cnt[t];
-	if (n == 0 || n > RM_CAP)
+	const uint32_t n = a.cnt[t];
+	if (n == 0u || n > a.cap)
 	{
 		if (threadIdx.x == 0) a.todo[t] = 1u;
 		return;
 	}
-	int np2 = 1;
+	uint32_t np2 = 1;
 	while (np2 < n) np2 <<= 1;
-	for (int i = threadIdx.x; i < np2; i += blockDim.x)
+	double* val = a.cval + (size_t)t * a.cap;
+	uint32_t* idx = a.cidx + (size_t)t * a.cap;
+	if (np2 <= (uint32_t)RM_CAP)
 	{
-		s_val[i] = (i < n) ? a.cval[(size_t)t * RM_CAP + i] : neg_inf();
-		s_idx[i] = (i < n) ? a.cidx[(size_t)t * RM_CAP + i] : 0xffffffffu;  // padding sorts last
+		for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x)
+		{
+			s_val[i] = (i < n) ? val[i] : neg_inf();
+			s_idx[i] = (i < n) ? idx[i] : 0xffffffffu;  // padding sorts last
+		}
+		val = s_val;
+		idx = s_idx;
+	}
+	else
+	{
+		// (cap is a power of two >= np2: the padding fits)
+		for (uint32_t i = n + threadIdx.x; i < np2; i += blockDim.x)
+		{
+			val[i] = neg_inf();
+			idx[i] = 0xffffffffu;
+		}
 	}
 	__syncthreads();
 	// bitonic sort, "before" = larger value, then smaller index (the order the atomics filled the list in does not matter)
-	for (int k = 2; k <= np2; k <<= 1)
-		for (int j = k >> 1; j > 0; j >>= 1)
+	for (uint32_t k = 2; k <= np2; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1)
 		{
-			for (int i = threadIdx.x; i < np2; i += blockDim.x)
+			for (uint32_t i = threadIdx.x; i < np2; i += blockDim.x)
 			{
-				const int l = i ^ j;
+				const uint32_t l = i ^ j;
 				if (l > i)
 				{
 					const bool up = (i & k) == 0;
-					const double va = s_val[i], vb = s_val[l];
-					const uint32_t ia = s_idx[i], ib = s_idx[l];
+					const double va = val[i], vb = val[l];
+					const uint32_t ia = idx[i], ib = idx[l];
 					const bool swap = up ? rm_before(vb, ib, va, ia) : rm_before(va, ia, vb, ib);
 					if (swap)
 					{
-						s_val[i] = vb; s_idx[i] = ib;
-						s_val[l] = va; s_idx[l] = ia;
+						val[i] = vb; idx[i] = ib;
+						val[l] = va; idx[l] = ia;
 					}
 				}
 			}
@@ -329,15 +349,15 @@ __global__ void __launch_bounds__(256) k_wide_select(WideMaskArgs a)
 	{
 		uint32_t* m = a.mask + (size_t)t * a.words;
 		double sum = neg_inf();
-		int reached = 0, k = 0;
-		for (; k < n; ++k)
+		int reached = 0;
+		for (uint32_t k = 0; k < n; ++k)
 		{
-			const uint32_t i = s_idx[k];
+			const uint32_t i = idx[k];
 			m[i >> 5] |= 1u << (i & 31);
-			sum = log_plus(sum, s_val[k]);
+			sum = log_plus(sum, val[k]);
 			if (sum >= a.threshold) { reached = 1; break; }
 		}
-		if (!reached && n < (int)a.C)
+		if (!reached && n < a.C)
 		{
 			// the candidates do not carry the threshold mass: k_row_mask starts over (it zeroes the row's mask itself)
 			a.todo[t] = 1u;

@@ -231,6 +231,11 @@ inline int __float_as_int(float f)
 	memcpy(&i, &f, 4);
 	return i;
 }
+struct float2
+{
+	float x, y;
+};
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct float4
 {
 	float x, y, z, w;
