@@ -722,6 +722,7 @@ struct dyn_aligner
 	int fwd_fast = 1;  // linear-domain pass 2: branch-free row body for groups of rows without a band slide
 	bool uniform = false;  // every kmer has the same sigma (set by upload_table): the Cfg::UNI kernels apply
 	float uni_a = 0.0f, uni_c = 0.0f;
+	bool ntk_pool_used = false;  // dyn_ntk_align_batch raised the release threshold of the device's memory pool
 	bool ntk = false; // resquiggle (NTK) mode: only the pre-pass stages are built (dyn_ntk_prepass)
 	double ntk_trans[18] = {0};  // log a1,a2,p1-3,s1-3,e1-4,i1,i2, then log ntMatch/ntExtend for TN and TK (NTK:35-104)
 	int arith = 0;    // 0: linear-domain kernels, reads with an FP32 range fault re-run in the log2 domain; 1: log2 domain only
@@ -1680,6 +1681,17 @@ void dyn_destroy(dyn_aligner* A)
 			b->release(A->rt);
 		A->h_sigpos.release(A->rt);
 		A->h_prob.release(A->rt);
+#ifndef DYN_HOST_EMU
+		if (A->ntk_pool_used)
+		{
+			cudaMemPool_t pool_h;
+			if (cudaDeviceGetDefaultMemPool(&pool_h, A->rt.device) == cudaSuccess)
+			{
+				cudaDeviceSynchronize();
+				cudaMemPoolTrimTo(pool_h, 0);
+			}
+		}
+#endif
 		A->rt.fini();
 	}
 	catch (...)
@@ -2700,6 +2712,18 @@ int dyn_ntk_align_batch(dyn_aligner* A, const float* signal, const uint64_t* sig
 			A->rt.bind();
 			const double fit = 0.6 * (double)A->rt.free_bytes() / per_read;
 			workers = (int)std::max(1.0, std::min((double)workers, fit));
+		}
+		{
+			// the workers' buffers are stream-ordered allocations: keep what they free in the device's pool between calls (by
+			// default the pool gives everything back at the next synchronisation, and every call would map tens of GB again —
+			// that, not the kernels, was 90 % of a 9-mer batch); dyn_destroy trims the pool
+			cudaMemPool_t pool_h;
+			if (cudaDeviceGetDefaultMemPool(&pool_h, A->rt.device) == cudaSuccess)
+			{
+				uint64_t keep = ~0ull;
+				cudaMemPoolSetAttribute(pool_h, cudaMemPoolAttrReleaseThreshold, &keep);
+				A->ntk_pool_used = true;
+			}
 		}
 		std::atomic<uint32_t> next(0);
 		std::vector<std::string> errors(workers);
