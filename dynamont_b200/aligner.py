@@ -255,6 +255,7 @@ class Aligner:
         out["records_per_row"] = float(r[13]) / 1000.0
         out["two_level_checkpoints"] = bool(r[14])
         out["records_free_layout"] = int(r[14]) == 2  # long reads: path posteriors from a second forward sweep
+        out["kept_by_log2_ribbon"] = int(r[15])         # of the reads counted above: re-run by the log2-domain ribbon, not handed on
         return out
 
     def last_timing(self):

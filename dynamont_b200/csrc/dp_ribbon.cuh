@@ -48,9 +48,14 @@ namespace dyn
 namespace rib
 {
 
-template <int C_>
+// LOG_: the same passes in the LOG2 DOMAIN (stored value L = log2(true value) - lane offset, "zero" = NEG, sums by
+// log-sum-exp on MUFU): the tier for reads the linear-domain ribbon cannot represent — an alignment that leaves the
+// reference band is forced through emissions of 2^-600 per row, which no FP32 product survives.  Rows run one by one with
+// a lane-local renormalisation after every row; align only, records-free layout (MODE 0 / 3 / 4).
+template <int C_, bool LOG_ = false>
 struct RCfg
 {
+	static constexpr bool LOGD = LOG_;
 	static constexpr int CPL = C_;
 	static constexpr int SLOTS = 32 * C_;
 	static constexpr int HW = (SLOTS - 2) / 2;  // live columns of a group: [mid - HW, mid + HW]; one ring slot stays dead
@@ -59,7 +64,8 @@ struct RCfg
 	static constexpr int ROWF = C_ * 32;        // floats per shared-memory row
 	static constexpr int HDRW = (2 + C_ + 3) / 4 * 4;  // words of a row header: first record, hot-lane mask, C decision words
 	static constexpr int RECF = (2 * C_ + 3) / 4 * 4;  // floats of a lane record: C match + C extend posteriors
-	static constexpr size_t SMEM_BYTES = (size_t)(GR + 1) * ROWF * 4;  // backward rows 8g .. 8g+8 of the current group
+	// backward rows 8g .. 8g+8 of the current group (log2 domain: + the lane offsets in force for every row)
+	static constexpr size_t SMEM_BYTES = (size_t)(GR + 1) * (ROWF * 4 + (LOG_ ? 32 * 4 : 0));
 };
 
 #if defined(DYN_HOST_EMU) && defined(DYN_RIB_DEBUG)
@@ -132,6 +138,16 @@ DYN_DEV float untie(float v) { return v; }
 DYN_DEV int fexp(float v) { return ((__float_as_int(v) >> 23) & 0xff) - 127; }
 DYN_DEV bool is_alive(float v) { return v > 0.0f && v < 3.0e38f; }
 
+// the two arithmetic domains behind one set of passes
+template <class RC> DYN_DEV float zero_v() { return RC::LOGD ? NEG : 0.0f; }
+template <class RC> DYN_DEV float one_v() { return RC::LOGD ? 0.0f : 1.0f; }
+template <class RC> DYN_DEV bool alive(float v) { return RC::LOGD ? (v > DEADT) : is_alive(v); }
+template <class RC> DYN_DEV int vexp(float v) { return RC::LOGD ? (int)floorf(v) : fexp(v); }  // floor(log2(value))
+// value expressed against an offset that is d smaller (d = old offset - new offset)
+template <class RC> DYN_DEV float rescale(float v, int d, float pw) { return RC::LOGD ? v + (float)d : v * pw; }
+// factor that converts a neighbour lane's value into this lane's scale (dn = neighbour's offset - own offset)
+template <class RC> DYN_DEV float nb_factor(int dn) { return RC::LOGD ? (float)dn : lin::pow2i(dn); }
+
 template <int C>
 struct Bw
 {
@@ -181,6 +197,12 @@ struct RWarp
 	// a pair of columns is two FFMA2: z = x*a + (-b), -e = z*z + (-c)
 	float a[C], nb[C], nc[C];
 
+	// log2 emission of slot j (dead slot: -1e25)
+	DYN_DEV float emis_log(int j, float x) const
+	{
+		const float z = fmaf(x, a[j], nb[j]);
+		return -fmaf(z, z, nc[j]);
+	}
 	// emission probabilities 2^e of the slot pair h (slots 2h, 2h+1) for sample x
 	DYN_DEV float2 emis_pair(int h, float2 x2) const
 	{
@@ -239,14 +261,14 @@ struct RWarp
 };
 
 template <int C>
-DYN_DEV void zero_slot(float (&p)[C], float (&q)[C], int j)
+DYN_DEV void zero_slot(float (&p)[C], float (&q)[C], int j, float z = 0.0f)
 {
 #pragma unroll
 	for (int jj = 0; jj < C; ++jj)
 		if (jj == j)
 		{
-			p[jj] = 0.0f;
-			q[jj] = 0.0f;
+			p[jj] = z;
+			q[jj] = z;
 		}
 }
 
@@ -300,8 +322,8 @@ DYN_DEV void clip_row(const RWarp<RC>& w, float (&p)[RC::CPL], float (&q)[RC::CP
 		const int col = RWarp<RC>::col_of_slot(w.lane * RC::CPL + j, mid - RC::HW);
 		if (col < lo || col > hi)
 		{
-			p[j] = 0.0f;
-			q[j] = 0.0f;
+			p[j] = zero_v<RC>();
+			q[j] = zero_v<RC>();
 		}
 	}
 }
@@ -314,6 +336,27 @@ DYN_DEV void bwd_row(const RWarp<RC>& w, Bw<RC::CPL>& b, float x, float m1, floa
 {
 	constexpr int C = RC::CPL, H = C / 2;
 	static_assert(C % 2 == 0, "columns per lane come in pairs (FMUL2 / FFMA2)");
+	if constexpr (RC::LOGD)
+	{
+		// log2 domain (m1, e2 = log2 transition scores): products are sums, the one sum of the recurrence is a log-sum-exp
+		float e[C], A[C];
+#pragma unroll
+		for (int j = 0; j < C; ++j)
+		{
+			e[j] = w.emis_log(j, x);
+			A[j] = b.bM[j] + (e[j] + m1);
+		}
+		const float Araw = __shfl_sync(FULL, A[0], (w.lane + 1) & 31);
+#pragma unroll
+		for (int j = 0; j < C; ++j)
+		{
+			const float nm = b.bE[j] + e[j];
+			const float in = (j + 1 < C) ? A[(j + 1 < C) ? j + 1 : j] : Araw + b.sR;
+			b.bE[j] = logplus2(nm + e2, in);
+			b.bM[j] = nm;
+		}
+		return;
+	}
 	const float2 x2 = make_float2(x, x), m2 = make_float2(m1, m1), e22 = make_float2(e2, e2);
 	float2 p[H], A[H];
 	// A[n] = bM[t+1][n] * p(t,n) * m1 is consumed by column n-1; pair 0 first: its shuffle has the rest of the row to complete
@@ -348,7 +391,7 @@ DYN_DEV void slide_down(RWarp<RC>& w, Bw<RC::CPL>& b, int& mid)
 	if (hi < (int)w.N)
 		with_slot<C>(w.lane, pmod(hi, RC::SLOTS), [&](int j) {
 			w.set_dead(j);
-			zero_slot<C>(b.bM, b.bE, j);
+			zero_slot<C>(b.bM, b.bE, j, zero_v<RC>());
 		});
 	const int nl = mid - 1 - RC::HW;
 	{
@@ -358,7 +401,7 @@ DYN_DEV void slide_down(RWarp<RC>& w, Bw<RC::CPL>& b, int& mid)
 		if (nl >= 0) v = w.pc[nl];
 		with_slot<C>(w.lane, pmod(nl, RC::SLOTS), [&](int j) {
 			w.set_col(j, v);
-			zero_slot<C>(b.bM, b.bE, j);
+			zero_slot<C>(b.bM, b.bE, j, zero_v<RC>());
 		});
 	}
 	--mid;
@@ -395,8 +438,30 @@ DYN_DEV void bwd_stats(const Bw<RC::CPL>& b, int& cand, int& kmax)
 	float lm = b.bE[0];
 #pragma unroll
 	for (int j = 1; j < RC::CPL; ++j) lm = fmaxf(lm, b.bE[j]);
-	cand = is_alive(lm) ? b.OB + fexp(lm) : NONE;
+	cand = alive<RC>(lm) ? b.OB + vexp<RC>(lm) : NONE;
 	kmax = warp_max_int(cand);
+}
+
+// log2 domain: after every row a lane takes the integer part of its largest value into its offset (no cross-lane
+// traffic except the neighbour's new offset), so the stored values stay in [0, 1) where FP32 resolves 1e-7
+template <class RC>
+DYN_DEV void lane_renorm_b(const RWarp<RC>& w, Bw<RC::CPL>& b)
+{
+	float lm = NEG;
+#pragma unroll
+	for (int j = 0; j < RC::CPL; ++j) lm = lin::max3f(lm, b.bM[j], b.bE[j]);
+	if (lm > DEADT)
+	{
+		const float d = floorf(lm);
+#pragma unroll
+		for (int j = 0; j < RC::CPL; ++j)
+		{
+			b.bM[j] -= d;
+			b.bE[j] -= d;
+		}
+		b.OB += (int)d;
+	}
+	b.sR = (float)(__shfl_sync(FULL, b.OB, (w.lane + 1) & 31) - b.OB);
 }
 
 template <class RC>
@@ -412,13 +477,13 @@ DYN_DEV void bwd_boundary(RWarp<RC>& w, Bw<RC::CPL>& b, int cand, int kmax, int&
 #pragma unroll
 	for (int j = 0; j < C; ++j)
 	{
-		b.bM[j] *= scl;
-		b.bE[j] *= scl;
+		b.bM[j] = rescale<RC>(b.bM[j], b.OB - nO, scl);
+		b.bE[j] = rescale<RC>(b.bE[j], b.OB - nO, scl);
 	}
 	b.OB = nO;
 #pragma unroll 1
 	while (mid > target) slide_down<RC>(w, b, mid);
-	b.sR = lin::pow2i(__shfl_sync(FULL, nO, (w.lane + 1) & 31) - nO);
+	b.sR = nb_factor<RC>(__shfl_sync(FULL, nO, (w.lane + 1) & 31) - nO);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -428,7 +493,7 @@ template <class RC, bool STORE, bool TL>
 DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs& args, int& fault)
 {
 	constexpr int C = RC::CPL;
-	const float m1 = args.m1_lin, e2 = args.e2_lin;
+	const float m1 = RC::LOGD ? args.m1 : args.m1_lin, e2 = RC::LOGD ? args.e2 : args.e2_lin;
 	const int lane = w.lane;
 	const int G = args.rib_guard;
 	const int S = (int)w.S;
@@ -437,12 +502,12 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 	int mid = (int)w.N - 1;  // = the reference's band centre of row T-1
 	w.load_window(mid);
 #pragma unroll
-	for (int j = 0; j < C; ++j) b.bM[j] = b.bE[j] = 0.0f;
+	for (int j = 0; j < C; ++j) b.bM[j] = b.bE[j] = zero_v<RC>();
 	{
 		const int q = pmod((int)w.N - 1, RC::SLOTS);
-		with_slot<C>(lane, q, SetOne<C>{b.bE, 1.0f});  // bE[T-1][N-1] = 1 (NT:170)
+		with_slot<C>(lane, q, SetOne<C>{b.bE, one_v<RC>()});  // bE[T-1][N-1] = 1 (NT:170)
 		b.OB = (lane == q / C) ? 0 : -RDC;
-		b.sR = lin::pow2i(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
+		b.sR = nb_factor<RC>(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
 	}
 	if (STORE)
 	{
@@ -460,7 +525,7 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 		if (g > 0) x8 = w.sig[8 * (g - 1) + (lane & 7)];
 		const bool clip = group_needs_clip<RC>(w, mid, g);
 		__syncwarp();  // (the compiler then knows the warp is converged: plain SHFL instead of WARPSYNC + SHFL + ENDCOLLECTIVE per row)
-		if (g < gl && !clip)
+		if (!RC::LOGD && g < gl && !clip)
 		{
 #pragma unroll
 			for (int k = 7; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
@@ -472,6 +537,7 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
 				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, 8u * (uint32_t)g + (uint32_t)k);
+				if (RC::LOGD) lane_renorm_b<RC>(w, b);
 			}
 		}
 		if (g == 0) break;
@@ -497,7 +563,7 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 	if (mid > RC::HW && !fault) { fault = 4; RIB_DBG("p1 end mid=%d\n", mid); }
 	if (fault) return NAN;
 	// Zb = bE[0][0] (NT:286): column 0 is ring slot 0 = lane 0, j 0
-	const double z = log2((double)b.bE[0]) + (double)b.OB;
+	const double z = (RC::LOGD ? (double)b.bE[0] : log2((double)b.bE[0])) + (double)b.OB;
 	return shfl_f64(z, 0);
 }
 
@@ -537,8 +603,8 @@ DYN_DEV void slide_up(RWarp<RC>& w, Fw<RC::CPL>& f, TrainAcc<RC::CPL>& ta, const
 		with_slot<C>(w.lane, pmod(lo, RC::SLOTS), [&](int j) {
 			if (MODE == 2) flush_slot<RC>(args, pc_off, ta, j, lo);
 			w.set_dead(j);
-			zero_slot<C>(f.fM, f.fE, j);
-			zero_slot<C>(f.VM, f.VE, j);
+			zero_slot<C>(f.fM, f.fE, j, zero_v<RC>());
+			zero_slot<C>(f.VM, f.VE, j, zero_v<RC>());
 		});
 	const int nh = mid + 1 + RC::HW;
 	if (nh < (int)w.N)
@@ -546,8 +612,8 @@ DYN_DEV void slide_up(RWarp<RC>& w, Fw<RC::CPL>& f, TrainAcc<RC::CPL>& ta, const
 		const PosConst v = w.pc[nh];
 		with_slot<C>(w.lane, pmod(nh, RC::SLOTS), [&](int j) {
 			w.set_col(j, v);
-			zero_slot<C>(f.fM, f.fE, j);
-			zero_slot<C>(f.VM, f.VE, j);
+			zero_slot<C>(f.fM, f.fE, j, zero_v<RC>());
+			zero_slot<C>(f.VM, f.VE, j, zero_v<RC>());
 			if (MODE == 2)
 			{
 #pragma unroll
@@ -568,6 +634,106 @@ DYN_DEV void slide_up(RWarp<RC>& w, Fw<RC::CPL>& f, TrainAcc<RC::CPL>& ta, const
 //   MODE 3: as MODE 1 without records (the row header holds the C decision words only); MODE 4: the gather sweep that
 //   follows the traceback of MODE 3 — `cell` = path cell of row t (column | match state << 31), whose posterior goes to
 //   hdr_row[0] (= pp[t]); no posterior-Viterbi state.
+// The same row in the log2 domain (MODE 3: fill, decision words only; MODE 4: gather).  f, bc, bn hold log2 values against
+// their lane offsets; kc / kn = (OF + OB(row t / t+1) - floor(Z2)) + log2 c0 of this lane, so that fE + bc + kc and
+// fM + bn + e + kn ARE the log2 posteriors.  m1, e2: log2 transition scores.
+template <class RC, int MODE, bool STEP>
+DYN_DEV float fwd_row_log(const RWarp<RC>& w, Fw<RC::CPL>& f, uint32_t* hdr_row, float x, const float (&bc)[RC::CPL],
+	const float (&bn)[RC::CPL], float kc, float kn, float m1, float e2, uint32_t cell)
+{
+	constexpr int C = RC::CPL;
+	static_assert(MODE == 3 || MODE == 4, "the log2-domain ribbon aligns with the records-free layout only");
+	const int lane = w.lane;
+	const float vlraw = (MODE == 3) ? __shfl_sync(FULL, f.VE[C - 1], (lane + 31) & 31) : NEG;
+	const float flraw = STEP ? __shfl_sync(FULL, f.fE[C - 1], (lane + 31) & 31) : NEG;
+	float e[C], PM[C], PE[C];
+	float msum = 0.0f;
+#pragma unroll
+	for (int j = 0; j < C; ++j)
+	{
+		e[j] = STEP ? w.emis_log(j, x) : 0.0f;
+		PE[j] = f.fE[j] + (bc[j] + kc);
+		PM[j] = STEP ? f.fM[j] + ((bn[j] + e[j]) + kn) : NEG;  // bM[t][n] = bE[t+1][n] * p(t,n) (NT:200); no match state in the last row
+		msum += ex2(PM[j]) + ex2(PE[j]);
+	}
+	if (MODE == 3)
+	{
+		// posterior-Viterbi fill (NT:357-362) as a max-SUM of log2 posteriors; the decision bits as in the linear domain
+		const float vl = vlraw + f.sV;
+		unsigned bits[C];
+		float vmx[C], left[C];
+#pragma unroll
+		for (int j = C - 1; j >= 0; --j)
+		{
+			vmx[j] = fmaxf(f.VM[j], f.VE[j]);
+			bits[j] = __ballot_sync(FULL, f.VM[j] < f.VE[j]);
+			left[j] = (j > 0) ? f.VE[(j > 0) ? j - 1 : 0] : vl;
+		}
+#pragma unroll
+		for (int j = 0; j < C; ++j)
+		{
+			f.VM[j] = fmaxf(left[j] + PM[j], NEG);
+			f.VE[j] = fmaxf(vmx[j] + PE[j], NEG);
+		}
+		if (lane == 0)
+		{
+			if (C == 2) *reinterpret_cast<uint2*>(hdr_row) = make_uint2(bits[0], bits[C - 1]);
+			else
+			{
+#pragma unroll
+				for (int j = 0; j < C; ++j) hdr_row[j] = bits[j];
+			}
+		}
+	}
+	else
+	{
+		const int q = (int)((cell & 0x7fffffffu) % (uint32_t)RC::SLOTS);
+		const int ql = q / C, jq = q - ql * C;
+		const bool isM = (cell >> 31) != 0u;
+		float pv = NEG;
+#pragma unroll
+		for (int j = 0; j < C; ++j)
+			if (j == jq) pv = isM ? PM[j] : PE[j];
+		if (lane == ql && cell != 0xffffffffu) *reinterpret_cast<float*>(hdr_row) = ex2(pv);
+	}
+	if (STEP)
+	{
+		const float fl = flraw + f.sL;
+		float left[C];
+#pragma unroll
+		for (int j = 0; j < C; ++j) left[j] = (j > 0) ? f.fE[(j > 0) ? j - 1 : 0] : fl;
+#pragma unroll
+		for (int j = 0; j < C; ++j)
+		{
+			const float ne = logplus2(f.fE[j] + e2, f.fM[j]) + e[j];  // (fM + fE*e2) * p    (NT:146-150, e1 = 1)
+			f.fM[j] = fmaxf(left[j] + (e[j] + m1), NEG);              // fE[t][n-1] * p * m1  (NT:143)
+			f.fE[j] = fmaxf(ne, NEG);
+		}
+	}
+	return msum;
+}
+
+// the forward counterpart of lane_renorm_b
+template <class RC>
+DYN_DEV void lane_renorm_f(const RWarp<RC>& w, Fw<RC::CPL>& f)
+{
+	float lm = NEG;
+#pragma unroll
+	for (int j = 0; j < RC::CPL; ++j) lm = lin::max3f(lm, f.fM[j], f.fE[j]);
+	if (lm > DEADT)
+	{
+		const float d = floorf(lm);
+#pragma unroll
+		for (int j = 0; j < RC::CPL; ++j)
+		{
+			f.fM[j] -= d;
+			f.fE[j] -= d;
+		}
+		f.OF += (int)d;
+	}
+	f.sL = (float)(__shfl_sync(FULL, f.OF, (w.lane + 31) & 31) - f.OF);
+}
+
 template <class RC, int MODE, bool STEP, bool MASS = true>
 DYN_DEV float fwd_row(const RWarp<RC>& w, Fw<RC::CPL>& f, RowSink& rs, TrainAcc<RC::CPL>& ta, uint32_t* hdr_row, float* recs,
 	float thr, float x, float xprev, const float (&bc)[RC::CPL], const float (&bn)[RC::CPL], float m1, float e2, uint32_t cell = 0u)
@@ -735,7 +901,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	constexpr int C = RC::CPL;
 	constexpr int ROWF = RC::ROWF;
 	constexpr int HW = RC::HW;
-	const float m1 = args.m1_lin, e2 = args.e2_lin;
+	const float m1 = RC::LOGD ? args.m1 : args.m1_lin, e2 = RC::LOGD ? args.e2 : args.e2_lin;
 	const float thr = args.thr_rib;
 	const int G = args.rib_guard;
 	const int lane = w.lane;
@@ -744,7 +910,16 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	// row k, slot pair h (slots 2h, 2h+1) of this lane: rows2[(k * H2 + h) * 32] — one 64-bit shared-memory access per pair
 	constexpr int H2 = C / 2;
 	float2* const rows2 = reinterpret_cast<float2*>(smem_raw) + lane;
+	// log2 domain: the rows are stored as they are, next to the lane offset in force for each (it changes row by row)
+	int* const rows_ob = reinterpret_cast<int*>(smem_raw + (size_t)(RC::GR + 1) * ROWF * 4) + lane;
 	auto put_row = [&](int k, const Bw<C>& bb, float kp) {
+		if (RC::LOGD)
+		{
+#pragma unroll
+			for (int h = 0; h < H2; ++h) rows2[(k * H2 + h) * 32] = make_float2(bb.bE[2 * h], bb.bE[2 * h + 1]);
+			rows_ob[k * 32] = bb.OB;
+			return;
+		}
 		const float2 k2 = make_float2(kp, kp);
 #pragma unroll
 		for (int h = 0; h < H2; ++h) rows2[(k * H2 + h) * 32] = mul2(make_float2(bb.bE[2 * h], bb.bE[2 * h + 1]), k2);
@@ -777,7 +952,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 #pragma unroll
 	for (int j = 0; j < C; ++j)
 	{
-		f.fM[j] = f.fE[j] = f.VM[j] = f.VE[j] = 0.0f;
+		f.fM[j] = f.fE[j] = f.VM[j] = f.VE[j] = zero_v<RC>();
 		ta.gw[j] = ta.gx[j] = ta.gxx[j] = 0.0f;
 		ta.mu[j] = 0.0f;
 	}
@@ -799,11 +974,11 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	f.OV = (lane == 0) ? 0 : -RDCV;
 	if (lane == 0)
 	{
-		f.fE[0] = 1.0f;
-		f.VE[0] = 1.0f;
+		f.fE[0] = one_v<RC>();
+		f.VE[0] = one_v<RC>();
 	}
-	f.sL = lin::pow2i(__shfl_sync(FULL, f.OF, (lane + 31) & 31) - f.OF);
-	f.sV = lin::pow2i(__shfl_sync(FULL, f.OV, (lane + 31) & 31) - f.OV);
+	f.sL = nb_factor<RC>(__shfl_sync(FULL, f.OF, (lane + 31) & 31) - f.OF);
+	f.sV = nb_factor<RC>(__shfl_sync(FULL, f.OV, (lane + 31) & 31) - f.OV);
 
 	// checkpoint / samples / next window centre of the group ahead are requested one group early
 	float ckM[C], ckE[C];
@@ -825,7 +1000,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			b.bE[j] = cf[(C + j) * 32 + lane];
 		}
 		b.OB = reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)(gs / SG) * 32 + lane];
-		b.sR = lin::pow2i(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
+		b.sR = nb_factor<RC>(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
 		int mr = (int)sc.sched[gs].x;
 		if (gs != g0) w.load_window(mr);
 		ckpt_put<RC>(sc.ring, ring_ob, (uint32_t)(gs % SG), lane, b);
@@ -836,7 +1011,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			const float xr = (i < S) ? w.sig[i] : 0.0f;
 			const int target = (int)sc.sched[gp - 1].x;
 			const bool clipr = group_needs_clip<RC>(w, mr, gp);
-			if (gp < gl && !clipr)
+			if (!RC::LOGD && gp < gl && !clipr)
 			{
 #pragma unroll
 				for (int k = 7; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
@@ -848,6 +1023,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 				{
 					bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
 					if (clipr) clip_row<RC>(w, b.bM, b.bE, mr, 8u * (uint32_t)gp + (uint32_t)k);
+					if (RC::LOGD) lane_renorm_b<RC>(w, b);
 				}
 			}
 			int cand, kmax;
@@ -903,11 +1079,12 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			b.bE[j] = ckE[j];
 		}
 		b.OB = ckO;
-		b.sR = lin::pow2i(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
-		const float kap = lin::kappa(f.OF, b.OB, Z2i, c0);
+		b.sR = nb_factor<RC>(__shfl_sync(FULL, b.OB, (lane + 1) & 31) - b.OB);
+		const float kap = RC::LOGD ? 0.0f : lin::kappa(f.OF, b.OB, Z2i, c0);
+		const float c0l = RC::LOGD ? lg2(c0) : 0.0f;  // log2 domain: the closed-loop correction as a summand
 		const bool clip = group_needs_clip<RC>(w, mid, g);
 		__syncwarp();  // (as in pass 1)
-		if (g < gl && !clip)
+		if (!RC::LOGD && g < gl && !clip)
 		{
 			put_row(8, b, kap);
 #pragma unroll
@@ -925,6 +1102,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
 				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, 8u * (uint32_t)g + (uint32_t)k);
+				if (RC::LOGD) lane_renorm_b<RC>(w, b);
 				put_row(k, b, kap);
 			}
 		}
@@ -937,7 +1115,8 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		constexpr int HSTR = (MODE == 4) ? 1 : HDRS;
 		float bc[C], bn[C];
 		get_row(0, bc);
-		if (g < gl && !clip)
+		int obc = RC::LOGD ? rows_ob[0] : 0, obn = 0;
+		if (!RC::LOGD && g < gl && !clip)
 		{
 #pragma unroll
 			for (int k = 0; k < 8; ++k)
@@ -962,8 +1141,16 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 				get_row(k + 1, bn);
 				const float x = __shfl_sync(FULL, xg, k);
 				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, k) : 0u;
-				macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
+				if constexpr (RC::LOGD)
+				{
+					obn = rows_ob[(k + 1) * 32];
+					const float kc = (float)(f.OF + obc - Z2i) + c0l, kn = (float)(f.OF + obn - Z2i) + c0l;
+					macc += fwd_row_log<RC, MODE, true>(w, f, hdr_g + k * HSTR, x, bc, bn, kc, kn, m1, e2, cell);
+					obc = obn;
+				}
+				else macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
 				if (clip) clip_row<RC>(w, f.fM, f.fE, mid, 8u * (uint32_t)g + (uint32_t)k + 1u);  // f now holds row t+1
+				if constexpr (RC::LOGD) lane_renorm_f<RC>(w, f);
 				xprev = x;
 #pragma unroll
 				for (int j = 0; j < C; ++j) bc[j] = bn[j];
@@ -972,7 +1159,12 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			if (g == gl)
 			{
 				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, nr) : 0u;
-				macc += fwd_row<RC, MODE, false>(w, f, rs, ta, hdr_g + nr * HSTR, recs, thr, 0.0f, xprev, bc, bn, m1, e2, cell);
+				if constexpr (RC::LOGD)
+				{
+					const float kc = (float)(f.OF + obc - Z2i) + c0l;
+					macc += fwd_row_log<RC, MODE, false>(w, f, hdr_g + nr * HSTR, 0.0f, bc, bn, kc, kc, m1, e2, cell);
+				}
+				else macc += fwd_row<RC, MODE, false>(w, f, rs, ta, hdr_g + nr * HSTR, recs, thr, 0.0f, xprev, bc, bn, m1, e2, cell);
 			}
 		}
 		__syncwarp();
@@ -980,7 +1172,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		// ---- group boundary: state row 8g+8 ------------------------------------------------------------------
 		// closed loop: the posterior mass of every row is 1; a row that lost mass is a fault, the mean deviation (slow
 		// common-mode FP32 drift) is folded into the posterior factor of the next group
-		const float cnt = (g < gl && !clip) ? 1.0f : ((g < gl) ? (float)nr : (float)(nr + 1));  // rows whose mass was summed
+		const float cnt = (!RC::LOGD && g < gl && !clip) ? 1.0f : ((g < gl) ? (float)nr : (float)(nr + 1));  // rows whose mass was summed
 		const float mass = warp_sum(macc, lane);
 		macc = 0.0f;
 		if (!(fabsf(mass - cnt) <= RIB_MASS_TOL) && !fault) { fault = 5; RIB_DBG("p2 g=%d mass=%g of %g\n", g, mass, cnt); }
@@ -999,17 +1191,18 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		// forward values: renormalise (own maximum -> [1, 2), at most RDC below the row's largest lane), window guard,
 		// range guard (largest forward x largest backward value of the row against Z)
 		{
-			float lm = 0.0f, bm = 0.0f;
+			float lm = zero_v<RC>(), bm = zero_v<RC>();
 #pragma unroll
 			for (int j = 0; j < C; ++j)
 			{
 				lm = lin::max3f(lm, f.fM[j], f.fE[j]);
 				bm = fmaxf(bm, bc[j]);  // row 8g+8, times kap = b / Z * 2^OF
 			}
-			const int cand = is_alive(lm) ? f.OF + fexp(lm) : NONE;
+			const int cand = alive<RC>(lm) ? f.OF + vexp<RC>(lm) : NONE;
 			const int kmax = warp_max_int(cand);
-			const int kb = warp_max_int(is_alive(bm) ? fexp(bm) - f.OF : NONE);
-			if ((kmax == NONE || kb == NONE || kmax + kb > lin::LIN_GUARD_BITS) && !fault) { fault = 6; RIB_DBG("p2 g=%d range kmax=%d kb=%d\n", g, kmax, kb); }
+			// (the range guard is about what a flushed cell can have carried: nothing is flushed in the log2 domain)
+			const int kb = RC::LOGD ? 0 : warp_max_int(is_alive(bm) ? fexp(bm) - f.OF : NONE);
+			if ((kmax == NONE || kb == NONE || (!RC::LOGD && kmax + kb > lin::LIN_GUARD_BITS)) && !fault) { fault = 6; RIB_DBG("p2 g=%d range kmax=%d kb=%d\n", g, kmax, kb); }
 			int first, last;
 			mass_extent<RC>(cand, kmax, mid, G, first, last);
 			if ((first == 0 || last == 31) && !fault) { fault = 7; RIB_DBG("p2 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
@@ -1018,18 +1211,18 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 #pragma unroll
 			for (int j = 0; j < C; ++j)
 			{
-				f.fM[j] *= scl;
-				f.fE[j] *= scl;
+				f.fM[j] = rescale<RC>(f.fM[j], f.OF - nO, scl);
+				f.fE[j] = rescale<RC>(f.fE[j], f.OF - nO, scl);
 			}
 			f.OF = nO;
-			f.sL = lin::pow2i(__shfl_sync(FULL, nO, (lane + 31) & 31) - nO);
+			f.sL = nb_factor<RC>(__shfl_sync(FULL, nO, (lane + 31) & 31) - nO);
 		}
 		if (MODE == 1 || MODE == 3)
 		{
-			float lm = 0.0f;
+			float lm = zero_v<RC>();
 #pragma unroll
 			for (int j = 0; j < C; ++j) lm = lin::max3f(lm, f.VM[j], f.VE[j]);
-			const int cand = is_alive(lm) ? f.OV + fexp(lm) - lin::E0V : NONE;
+			const int cand = alive<RC>(lm) ? f.OV + vexp<RC>(lm) - lin::E0V : NONE;
 			const int kmax = warp_max_int(cand);
 			// every posterior-Viterbi score underflowed (or is NaN): the decision bits from here on would be meaningless
 			if (kmax == NONE && !fault) { fault = 8; RIB_DBG("p2 g=%d viterbi dead\n", g); }
@@ -1038,11 +1231,11 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 #pragma unroll
 			for (int j = 0; j < C; ++j)
 			{
-				f.VM[j] *= scl;
-				f.VE[j] *= scl;
+				f.VM[j] = rescale<RC>(f.VM[j], f.OV - nO, scl);
+				f.VE[j] = rescale<RC>(f.VE[j], f.OV - nO, scl);
 			}
 			f.OV = nO;
-			f.sV = lin::pow2i(__shfl_sync(FULL, nO, (lane + 31) & 31) - nO);
+			f.sV = nb_factor<RC>(__shfl_sync(FULL, nO, (lane + 31) & 31) - nO);
 		}
 		if (fault) break;
 		// move to the window of the next group
@@ -1056,10 +1249,10 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		}
 	}
 	// Zf = fE[T-1][N-1] (NT:285)
-	float v = 0.0f;
+	float v = zero_v<RC>();
 	with_slot<C>(lane, pmod((int)w.N - 1, RC::SLOTS), GetOne<C>{f.fE, v});
 	const int ql = pmod((int)w.N - 1, RC::SLOTS) / C;
-	double dz = log2((double)v) + (double)f.OF - Z2;
+	double dz = (RC::LOGD ? (double)v : log2((double)v)) + (double)f.OF - Z2;
 	dz = shfl_f64(dz, ql);
 	RIB_DBG("p2 end dz=%g fault=%d\n", dz, fault);
 	fault = warp_max_int(fault);

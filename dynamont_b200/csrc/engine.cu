@@ -52,7 +52,7 @@ struct DevOom : std::runtime_error
 struct Rt
 {
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t ev[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	int device = 0;
 	int sms = 148;
 	size_t smem_optin = 0;
@@ -141,7 +141,7 @@ struct Rt
 	int sms = 2;
 	bool async_alloc = false;
 	size_t smem_optin = 227 * 1024;
-	double tm[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	double tm[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 	void init(int) {}
 	void use_stream(void*) {}
 	void fini() {}
@@ -737,6 +737,8 @@ struct dyn_aligner
 	double rib_recs_per_row = 2.5;   // lane records per lattice row budgeted (measured use: 1.2; a read that needs more faults to the full-band kernels)
 	int rib_min_bw = 0;        // reads whose half band is narrower than this skip the ribbon tier (0: none; the band is clipped exactly inside the window)
 	int rib_two_level = -1;    // checkpoints of every 8th group only: -1 when the scratch would not fit otherwise, 0 never, 1 always
+	int rib_log = 1;           // 1: reads the linear-domain ribbon loses to FP32 range are re-run by the log2-domain ribbon (align)
+	uint64_t n_rib_log = 0, n_rib_log_fault = 0;  // last batch: reads given to the log2-domain ribbon / reads it handed on
 	int rib_gather = -1;       // records-free scratch + second forward sweep for the path posteriors (implies two-level):
 	                           // -1 when the resident warps' scratch would not fit otherwise, 0 never, 1 always
 	double rib_last_two_level = 0;
@@ -1113,6 +1115,8 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 	A.n_retry_lin = 0;
 	A.n_ribbon = 0;
 	A.n_rib_fault = 0;
+	A.n_rib_log = 0;
+	A.n_rib_log_fault = 0;
 	A.ribbon_ms = 0.0;
 	int launches = 1;
 	// reads the ribbon kernels lost COMPLETELY (every value of a group underflowed, or Zb is not finite): the same FP32
@@ -1265,8 +1269,116 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				A.rib_last_two_level = gather ? 2.0 : (two_level ? 1.0 : 0.0);
 				A.rib_recs_used = nrow > 0 ? nrec / nrow : 0.0;
 			}
+			// ---- tier 0b: the log2-domain ribbon (RCfg<2, true>) for the reads whose loss is one of RANGE — everything
+			// underflowed (an alignment forced along the band's edge multiplies by 2^-600 per row), the posterior mass or the
+			// Viterbi scores died, Zf != Zb, the range guard tripped.  Same window, same passes, unlimited range; the reads whose
+			// mass sits at the window's EDGE (reasons 2, 7: a window problem, not a range problem) go to the full-band kernels.
+			std::vector<uint32_t> logq;
+			const bool force_log = (A.rib_log == 2);  // test hook: every read of the tier through the log2-domain ribbon as well
+			if (mode == 1 && A.rib_log != 0)
+				for (uint32_t r : rorder)
+				{
+					if (res.out[r].status == ST_LIN_FAULT)
+					{
+						const uint32_t why = res.out[r].nrec;
+						if (force_log || why == 1u || why == 5u || why == 6u || why == 8u || why == 9u || why == 12u) logq.push_back(r);
+					}
+					else if (force_log && res.out[r].status == ST_OK) logq.push_back(r);
+				}
+			std::vector<uint32_t> first_why(logq.size());
+			if (!logq.empty())
+			{
+				dyn_aligner& R = A.root ? *A.root : A;
+				uint32_t maxTl = 0;
+				for (size_t i = 0; i < logq.size(); ++i)
+				{
+					maxTl = std::max(maxTl, res.desc[logq[i]].S + 1);
+					first_why[i] = (res.out[logq[i]].status == ST_LIN_FAULT) ? res.out[logq[i]].nrec : 0u;
+				}
+				// records-free layout with two-level checkpoints (the only one the log2-domain kernel is built for)
+				const size_t ngr = (size_t)maxTl / rg.ck + 2, nck = ngr / 8 + 2;
+				size_t o = 0;
+				const size_t l_sch = o; o = align_up(o + ngr * 8, 256);
+				const size_t l_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
+				const size_t l_ob = o; o = align_up(o + nck * 32 * 4, 256);
+				const size_t l_ring = o; o = align_up(o + 8 * ((size_t)rg.ckf * 4 + 128), 256);
+				const size_t l_hdr = o; o = align_up(o + ((size_t)maxTl + 32) * rg.cpl * 4, 256);
+				const size_t l_pp = o; o = align_up(o + ((size_t)maxTl + 32) * 4, 256);
+				const size_t per_l = o;
+				std::lock_guard<std::mutex> cl(R.compute_mu);
+				const size_t budget = (size_t)((double)(rt.free_bytes() + R.d_rib_scratch.cap) * A.mem_fraction);
+				const unsigned gridl = (unsigned)std::max<size_t>(1, std::min<size_t>(logq.size(), budget / per_l));
+				if (per_l * gridl > R.d_rib_scratch.cap)
+				{
+					R.rt.sync();
+					rt.sync();
+				}
+				unsigned char* base = (unsigned char*)R.d_rib_scratch.get(R.rt, per_l * gridl);
+				std::vector<SlotScratch> slots(gridl);
+				memset(slots.data(), 0, slots.size() * sizeof(SlotScratch));
+				for (unsigned q = 0; q < gridl; ++q)
+				{
+					unsigned char* b = base + per_l * q;
+					slots[q].sched = (uint2*)(b + l_sch);
+					slots[q].ckpt = (float*)(b + l_ck);
+					slots[q].ckpt_ob = (double*)(b + l_ob);
+					slots[q].ring = (float*)(b + l_ring);
+					slots[q].hdr = (uint32_t*)(b + l_hdr);
+					slots[q].pp = (float*)(b + l_pp);
+				}
+				SlotScratch* d_slots = (SlotScratch*)A.d_slots.get(rt, (size_t)gridl * sizeof(SlotScratch));
+				A.h2d_staged(d_slots, slots.data(), (size_t)gridl * sizeof(SlotScratch));
+				A.h2d_staged(d_order, logq.data(), logq.size() * 4);
+				rt.zero(d_queue, 64);
+				BatchArgs rb = ba;
+				rb.n_reads = (uint32_t)logq.size();
+				rb.slots = d_slots;
+				rb.n_slots = gridl;
+				rb.rec_cap = 0;
+				const bool cross = (&R != &A);
+				if (cross)
+				{
+					rt.mark(8);
+					rt.wait_on(R.rt, 8);
+				}
+				rt.mark_on(10, R.rt);
+#ifndef DYN_HOST_EMU
+				const int le = rib::launch((void*)R.rt.stream, rb, gridl, 3, 2, 0, true, true);
+				if (le != 0) throw std::runtime_error(std::string("CUDA error launching the log2-domain ribbon kernel: ") + cudaGetErrorString((cudaError_t)le));
+#else
+				rib::launch(nullptr, rb, gridl, 3, 2, 0, true, true);
+#endif
+				rt.mark_on(11, R.rt);
+				if (cross) rt.wait_self(11);
+				++launches;
+				rt.d2h(h_out_stage, d_out, (size_t)n * sizeof(ReadOut));
+				rt.sync();
+				std::memcpy(res.out.data(), h_out_stage, (size_t)n * sizeof(ReadOut));
+				A.ribbon_ms += rt.elapsed(10, 11);
+				A.n_rib_log = logq.size();
+				tm.lap("log_ribbon_kernel");
+			}
+			{
+				// a read the log2-domain ribbon kept is no longer a fault of the tier; one it lost too keeps its FIRST reason
+				size_t i = 0;
+				for (uint32_t r : logq)
+				{
+					if (first_why[i] != 0u)
+					{
+						++A.rib_reason[std::min<uint32_t>(first_why[i], 15u)];
+						++A.n_rib_fault;
+					}
+					if (res.out[r].status == ST_LIN_FAULT)
+					{
+						++A.n_rib_log_fault;
+						direct_log2.push_back(r);  // the linear full-band tiers would lose it for the same reason
+					}
+					else ++A.rib_reason[15];  // [15]: cumulative reads the log2-domain ribbon kept
+					++i;
+				}
+			}
 			for (uint32_t r : rorder)
-				if (res.out[r].status == ST_LIN_FAULT)
+				if (res.out[r].status == ST_LIN_FAULT && std::find(logq.begin(), logq.end(), r) == logq.end())
 				{
 					const uint32_t why = res.out[r].nrec;
 					// ... and so do long reads whatever the reason: a full-band tier is one warp for seconds per read
@@ -2804,7 +2916,8 @@ void dyn_last_ribbon(const dyn_aligner* A, uint64_t* out2)
 void dyn_ribbon_fault_reasons(const dyn_aligner* A, uint64_t* out16)
 {
 	for (int i = 0; i < 16; ++i) out16[i] = A->rib_reason[i];
-	// [13]: records per row of the last batch x 1000, [14]: the last batch ran with two-level checkpoints
+	// [13]: records per row of the last batch x 1000, [14]: the last batch ran with two-level checkpoints,
+	// [15]: cumulative reads the log2-domain ribbon kept (of those counted under their reason codes)
 	out16[13] = (uint64_t)(A->rib_recs_used * 1000.0);
 	out16[14] = (uint64_t)A->rib_last_two_level;
 }
@@ -2849,6 +2962,7 @@ int dyn_set_option(dyn_aligner* A, const char* key, double value)
 	else if (k == "rib_bps") A->rib_bps = (int)value;
 	else if (k == "rib_two_level") A->rib_two_level = (int)value;
 	else if (k == "rib_gather") A->rib_gather = (int)value;
+	else if (k == "rib_log") A->rib_log = (int)value;
 	else if (k == "rib_min_bw") A->rib_min_bw = (int)value;
 	else return -1;
 	return 0;

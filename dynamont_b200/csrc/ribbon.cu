@@ -15,6 +15,8 @@ constexpr int WPB = 4;  // warps per CTA; the warps of a CTA are independent (ea
 
 using RC2 = RCfg<2>;
 using RC4 = RCfg<4>;
+using RC2L = RCfg<2, true>;  // the log2-domain tier behind the linear-domain ribbon (align, records-free layout, two-level checkpoints)
+constexpr int BPSL = 4;
 constexpr int BPS2 = 5;  // 20 resident warps per SM: <= 96 registers per thread, no spills (measured: 6 -> 80 registers: -4 %, 8 -> 64: -13 %)
 constexpr int BPS4 = 4;  // 16 resident warps per SM: <= 128 registers per thread
 
@@ -112,13 +114,25 @@ bool geometry(int cpl, int bps, Geometry& g)
 	return true;
 }
 
-int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps, bool two_level)
+int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps, bool two_level, bool log_domain)
 {
 #ifndef DYN_HOST_EMU
 	cudaStream_t s = (cudaStream_t)stream;
 #else
 	void* s = stream;
 #endif
+	if (log_domain)
+	{
+		if (mode != 3 || !two_level) return -1;
+#ifndef DYN_HOST_EMU
+		const unsigned ctas = (n_warps + WPB - 1) / WPB;
+		k_ribbon<RC2L, 3, BPSL, true><<<ctas, 32 * WPB, RC2L::SMEM_BYTES * WPB, s>>>(args);
+		return (int)cudaGetLastError();
+#else
+		simt::launch(n_warps, RC2L::SMEM_BYTES, [&]() { worker<RC2L, 3, true>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+		return 0;
+#endif
+	}
 	if (cpl == 2)
 	{
 		if (two_level) return launch_t<RC2, BPS2, true>(s, args, n_warps, mode);

@@ -81,6 +81,55 @@ def test_emulated_range_fault_falls_back(emu_lib):
     np.testing.assert_allclose(pooled_lin["w"], pooled_log["w"], rtol=1e-12)
 
 
+def test_emulated_log2_ribbon_keeps_what_the_linear_ribbon_loses(emu_lib):
+    """the log2-domain ribbon (tier 0b): (1) forced on every golden case it must reproduce the reference; (2) a read with
+    samples no kmer explains and a read whose band (16 columns) cuts its alignment underflow the FP32 products of the
+    linear-domain ribbon — the log2-domain ribbon keeps them on the narrow window (no full-band launch), identical to
+    the oracle; (3) with the tier switched off the same reads come back from the full-band log2 kernels, same results"""
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import native_model, synth_read
+    from oracle import Oracle
+    for case in [c for c in load_golden() if c.name in SMALL and c.name != "rna002_dinuc"]:
+        al = _aligner(emu_lib, case, -1)
+        al.set_option("rib_log", 2)
+        r = al.align(case.signal, case.sequence, True)
+        assert al.ribbon_fault_reasons()["kept_by_log2_ribbon"] == 1 and al.last_timing()["log2_fallback_reads"] == 0
+        check_alignment(r, case.signal_positions, case.sequence_positions, case.probabilities, case.Z, case.name)
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    nm, ns = native_model(case.model_path, case.pore)
+    s, q, _ = synth_read(np.random.default_rng(11), nm, ns, 5, 120, 9)
+    s[200] += 9.0
+    s[201] -= 8.0
+    s = s.astype(np.float32).astype(np.float64)
+    o = Oracle(case.model_path, case.pore).align(s, q, True)
+    got = {}
+    for rib_log in (1, 0):
+        al = _aligner(emu_lib, case, -1)
+        al.set_option("rib_log", rib_log)
+        r = al.align(s, q, True)
+        tm, why = al.last_timing(), al.ribbon_fault_reasons()
+        assert tm["ribbon_faults"] == 1
+        assert (why["kept_by_log2_ribbon"], tm["log2_fallback_reads"]) == ((1, 0) if rib_log else (0, 1)), (why, tm)
+        check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"], "spikes rib_log=%d" % rib_log)
+        got[rib_log] = r
+    assert np.array_equal(got[0]["signal_positions"], got[1]["signal_positions"])
+    # a band that cuts the alignment: whatever the reference does (forced alignment or "scores do not match"), so do we
+    kept = 0
+    for band, seed in ((16, 16), (16, 3), (24, 5), (12, 8)):
+        aln = Aligner(case.model_path, case.pore, band=band, _lib_path=emu_lib)
+        orn = Oracle(case.model_path, case.pore, band=band)
+        s, q, _ = synth_read(np.random.default_rng(seed), nm, ns, 5, 150, 8)
+        try:
+            o = orn.align(s, q, True)
+        except RuntimeError as e:
+            with pytest.raises(RuntimeError, match=str(e)[:20]):
+                aln.align(s, q, True)
+            continue
+        check_alignment(aln.align(s, q, True), o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"], "band %d" % band)
+        kept += aln.ribbon_fault_reasons()["kept_by_log2_ribbon"]
+    print("band-cut reads kept by the log2-domain ribbon:", kept)
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 8, 9, 10, 11, 12, 13, -1])
 def test_emulated_variants(variant, emu_lib):
     """build variants: general kernels (0-3, 9, 11, 13), uniform-sigma kernels (4-8, 10, 12), library default (-1)"""
