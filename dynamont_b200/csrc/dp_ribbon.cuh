@@ -52,14 +52,15 @@ namespace rib
 // log-sum-exp on MUFU): the tier for reads the linear-domain ribbon cannot represent — an alignment that leaves the
 // reference band is forced through emissions of 2^-600 per row, which no FP32 product survives.  Rows run one by one with
 // a lane-local renormalisation after every row; align only, records-free layout (MODE 0 / 3 / 4).
-template <int C_, bool LOG_ = false>
+template <int C_, bool LOG_ = false, int GR_ = 8>
 struct RCfg
 {
 	static constexpr bool LOGD = LOG_;
 	static constexpr int CPL = C_;
 	static constexpr int SLOTS = 32 * C_;
 	static constexpr int HW = (SLOTS - 2) / 2;  // live columns of a group: [mid - HW, mid + HW]; one ring slot stays dead
-	static constexpr int GR = 8;                // samples per group
+	static constexpr int GR = GR_;              // samples per group (8 or 16: lanes 0 .. GR hold a group's samples / path cells)
+	static_assert(GR_ == 8 || GR_ == 16, "group size");
 	static constexpr int CKF = 2 * C_ * 32;     // floats per checkpoint
 	static constexpr int ROWF = C_ * 32;        // floats per shared-memory row
 	static constexpr int HDRW = (2 + C_ + 3) / 4 * 4;  // words of a row header: first record, hot-lane mask, C decision words
@@ -299,13 +300,13 @@ DYN_DEV int extent_centre2(int mid, int first, int last)
 template <class RC>
 DYN_DEV bool group_needs_clip(const RWarp<RC>& w, int mid, int g)
 {
-	const uint32_t t0 = 8u * (uint32_t)g, t1 = min(t0 + 8u, w.T - 1u);
+	const uint32_t t0 = (uint32_t)RC::GR * (uint32_t)g, t1 = min(t0 + (uint32_t)RC::GR, w.T - 1u);
 	// cheap FP32 estimate of the band centre first (t * ratio < 2^17 for any read that fits the device: off by << 1 column);
 	// the exact double-precision centres of the reference only when the window is within two columns of the band's edge
 	const float c0 = (float)t0 * w.ratio_f;
 	const int lo_room = (mid - RC::HW) - ((int)c0 - w.bw_ref), hi_room = ((int)c0 + w.bw_ref) - (mid + RC::HW);
-	// (the estimate is within one column of band_mid(t0); the centre moves <= 5 columns over the group's rows: ratio <= 1/2)
-	if (lo_room > 8 && hi_room > 3) return false;
+	// (the estimate is within one column of band_mid(t0); the centre moves <= GR/2 + 1 columns over the group's rows: ratio <= 1/2)
+	if (lo_room > RC::GR / 2 + 4 && hi_room > 3) return false;
 	const int m0 = (int)band_mid(t0, w.ratio), m1 = (int)band_mid(t1, w.ratio);  // band centres are non-decreasing in t
 	return (mid + RC::HW > m0 + w.bw_ref) || (mid - RC::HW < m1 - w.bw_ref);
 }
@@ -497,7 +498,8 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 	const int lane = w.lane;
 	const int G = args.rib_guard;
 	const int S = (int)w.S;
-	const int gl = (S - 1) >> 3;  // last group
+	constexpr int GR = RC::GR;
+	const int gl = (S - 1) / GR;  // last group
 	Bw<C> b;
 	int mid = (int)w.N - 1;  // = the reference's band centre of row T-1
 	w.load_window(mid);
@@ -516,27 +518,27 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 	}
 	float x8;
 	{
-		const int i = 8 * gl + (lane & 7);
+		const int i = GR * gl + (lane & (GR - 1));
 		x8 = (i < S) ? w.sig[i] : 0.0f;
 	}
 	for (int g = gl; g >= 0; --g)
 	{
 		const float xg = x8;
-		if (g > 0) x8 = w.sig[8 * (g - 1) + (lane & 7)];
+		if (g > 0) x8 = w.sig[GR * (g - 1) + (lane & (GR - 1))];
 		const bool clip = group_needs_clip<RC>(w, mid, g);
 		__syncwarp();  // (the compiler then knows the warp is converged: plain SHFL instead of WARPSYNC + SHFL + ENDCOLLECTIVE per row)
 		if (!RC::LOGD && g < gl && !clip)
 		{
 #pragma unroll
-			for (int k = 7; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
+			for (int k = GR - 1; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
 		}
 		else
 		{
 #pragma unroll 1
-			for (int k = ((g < gl) ? 8 : S - 8 * gl) - 1; k >= 0; --k)
+			for (int k = ((g < gl) ? GR : S - GR * gl) - 1; k >= 0; --k)
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
-				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, 8u * (uint32_t)g + (uint32_t)k);
+				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, (uint32_t)GR * (uint32_t)g + (uint32_t)k);
 				if (RC::LOGD) lane_renorm_b<RC>(w, b);
 			}
 		}
@@ -544,12 +546,14 @@ DYN_DEV double backward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArg
 		// ---- group boundary: row 8g.  Renormalise, decide the window of group g-1, move there, checkpoint -----
 		int cand, kmax;
 		bwd_stats<RC>(b, cand, kmax);
-		if (kmax == NONE) { fault = 1; RIB_DBG("p1 g=%d nothing alive\n", g); return NAN; }
+		// (inside a group clipped to the reference band that is reason 3: the alignment has left the band — the forward and
+		// backward ridges then separate by up to the band's width, which no window holds: full-band kernels)
+		if (kmax == NONE) { fault = clip ? 3 : 1; RIB_DBG("p1 g=%d nothing alive (clip %d)\n", g, (int)clip); return NAN; }
 		int first, last;
 		mass_extent<RC>(cand, kmax, mid, G, first, last);
 		if ((first == 0 || last == 31) && !fault) { fault = 2; RIB_DBG("p1 g=%d mid=%d edge first=%d last=%d\n", g, mid, first, last); }
 		int s = (2 * mid - extent_centre2<RC>(mid, first, last)) / 2;  // window centre above the mass centre: move down
-		s = max(0, min(s, min(8, mid)));
+		s = max(0, min(s, min(GR, mid)));
 		bwd_boundary<RC>(w, b, cand, kmax, mid, mid - s);
 		if (fault) return NAN;
 		if (STORE)
@@ -906,7 +910,8 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 	const int G = args.rib_guard;
 	const int lane = w.lane;
 	const int S = (int)w.S;
-	const int gl = (S - 1) >> 3;
+	constexpr int GR = RC::GR;
+	const int gl = (S - 1) / GR;
 	// row k, slot pair h (slots 2h, 2h+1) of this lane: rows2[(k * H2 + h) * 32] — one 64-bit shared-memory access per pair
 	constexpr int H2 = C / 2;
 	float2* const rows2 = reinterpret_cast<float2*>(smem_raw) + lane;
@@ -1007,22 +1012,22 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 #pragma unroll 1
 		for (int gp = gs; gp > g0; --gp)
 		{
-			const int i = 8 * gp + (lane & 7);
+			const int i = GR * gp + (lane & (GR - 1));
 			const float xr = (i < S) ? w.sig[i] : 0.0f;
 			const int target = (int)sc.sched[gp - 1].x;
 			const bool clipr = group_needs_clip<RC>(w, mr, gp);
 			if (!RC::LOGD && gp < gl && !clipr)
 			{
 #pragma unroll
-				for (int k = 7; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
+				for (int k = GR - 1; k >= 0; --k) bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
 			}
 			else
 			{
 #pragma unroll 1
-				for (int k = ((gp < gl) ? 8 : S - 8 * gl) - 1; k >= 0; --k)
+				for (int k = ((gp < gl) ? GR : S - GR * gl) - 1; k >= 0; --k)
 				{
 					bwd_row<RC>(w, b, __shfl_sync(FULL, xr, k), m1, e2);
-					if (clipr) clip_row<RC>(w, b.bM, b.bE, mr, 8u * (uint32_t)gp + (uint32_t)k);
+					if (clipr) clip_row<RC>(w, b.bM, b.bE, mr, (uint32_t)GR * (uint32_t)gp + (uint32_t)k);
 					if (RC::LOGD) lane_renorm_b<RC>(w, b);
 				}
 			}
@@ -1042,13 +1047,13 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			ckE[j] = cf[(C + j) * 32 + lane];
 		}
 		ckO = TL ? ring_ob[(size_t)(g % SG) * 32 + lane] : reinterpret_cast<const int*>(sc.ckpt_ob)[(size_t)g * 32 + lane];
-		const int i = 8 * g + (lane & 7);
+		const int i = GR * g + (lane & (GR - 1));
 		x8 = (i < S) ? w.sig[i] : 0.0f;
 		if (MODE == 4)
 		{
 			// (read before this group's posteriors overwrite the same words: the stores depend on these values)
-			const int r = 8 * g + (lane & 15);
-			cg8 = ((lane & 15) <= 8 && r <= S) ? __float_as_uint(sc.pp[r]) : 0xffffffffu;
+			const int r = GR * g + lane;
+			cg8 = (lane <= GR && r <= S) ? __float_as_uint(sc.pp[r]) : 0xffffffffu;
 		}
 		mid_next = (g < gl) ? (int)sc.sched[g + 1].x : 0;
 	};
@@ -1059,8 +1064,8 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 
 	for (int g = 0; g <= gl; ++g)
 	{
-		const int nr = (g < gl) ? 8 : S - 8 * gl;  // samples of this group
-		if (MODE == 1 && rs.n + 9u * 32u > rs.cap)
+		const int nr = (g < gl) ? GR : S - GR * gl;  // samples of this group
+		if (MODE == 1 && rs.n + (uint32_t)(GR + 1) * 32u > rs.cap)
 		{
 			// not enough room for the records this group can produce at most (pathological record density)
 			rs.overflow = true;
@@ -1086,9 +1091,9 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		__syncwarp();  // (as in pass 1)
 		if (!RC::LOGD && g < gl && !clip)
 		{
-			put_row(8, b, kap);
+			put_row(GR, b, kap);
 #pragma unroll
-			for (int k = 7; k >= 0; --k)
+			for (int k = GR - 1; k >= 0; --k)
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
 				put_row(k, b, kap);
@@ -1101,7 +1106,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			for (int k = nr - 1; k >= 0; --k)
 			{
 				bwd_row<RC>(w, b, __shfl_sync(FULL, xg, k), m1, e2);
-				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, 8u * (uint32_t)g + (uint32_t)k);
+				if (clip) clip_row<RC>(w, b.bM, b.bE, mid, (uint32_t)GR * (uint32_t)g + (uint32_t)k);
 				if (RC::LOGD) lane_renorm_b<RC>(w, b);
 				put_row(k, b, kap);
 			}
@@ -1111,7 +1116,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 
 		// ---- step b: forward rows 8g .. 8g+nr-1 -------------------------------------------------------------
 		// where row 8g+k's header goes (MODE 4: its path posterior)
-		uint32_t* const hdr_g = (MODE == 4) ? reinterpret_cast<uint32_t*>(sc.pp) + (size_t)(8 * g) : sc.hdr + (size_t)(8 * g) * HDRS;
+		uint32_t* const hdr_g = (MODE == 4) ? reinterpret_cast<uint32_t*>(sc.pp) + (size_t)(GR * g) : sc.hdr + (size_t)(GR * g) * HDRS;
 		constexpr int HSTR = (MODE == 4) ? 1 : HDRS;
 		float bc[C], bn[C];
 		get_row(0, bc);
@@ -1119,14 +1124,14 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		if (!RC::LOGD && g < gl && !clip)
 		{
 #pragma unroll
-			for (int k = 0; k < 8; ++k)
+			for (int k = 0; k < GR; ++k)
 			{
 				get_row(k + 1, bn);
 				const float x = __shfl_sync(FULL, xg, k);
 				// the posterior mass is measured on the group's last row: offsets and the posterior factor are fixed inside
 				// a group, so a lane that lost its values or whose factor left the float range shows there
 				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, k) : 0u;
-				if (k == 7) macc += fwd_row<RC, MODE, true, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
+				if (k == GR - 1) macc += fwd_row<RC, MODE, true, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
 				else fwd_row<RC, MODE, true, false>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
 				xprev = x;
 #pragma unroll
@@ -1149,7 +1154,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 					obc = obn;
 				}
 				else macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
-				if (clip) clip_row<RC>(w, f.fM, f.fE, mid, 8u * (uint32_t)g + (uint32_t)k + 1u);  // f now holds row t+1
+				if (clip) clip_row<RC>(w, f.fM, f.fE, mid, (uint32_t)GR * (uint32_t)g + (uint32_t)k + 1u);  // f now holds row t+1
 				if constexpr (RC::LOGD) lane_renorm_f<RC>(w, f);
 				xprev = x;
 #pragma unroll
@@ -1416,7 +1421,8 @@ DYN_DEV void ribbon_read(const BatchArgs& args, const ReadDesc& rd, uint32_t rid
 	out.xi_e = 0.0;
 
 	// why a read is handed to the full-band kernels (ReadOut.nrec of a faulted read; dyn_last_ribbon counts them):
-	//  1 nothing alive  2 backward mass at a window edge  3 window outside the reference band  4 window misses row 0
+	//  1 nothing alive  2 backward mass at a window edge  3 nothing alive in a group clipped to the reference band (the
+	//  alignment leaves the band)  4 window misses row 0
 	//  5 posterior mass of a group != 1  6 range guard  7 forward mass at a window edge  8 posterior-Viterbi scores died
 	//  9 Zf != Zb  10 record buffer full  11 traceback incomplete  12 Zb not finite
 	int fault = 0;

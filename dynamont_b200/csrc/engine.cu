@@ -1176,7 +1176,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 					}
 					else if (mode == 1)
 					{
-						rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64 + 9 * 32;
+						rcap = (uint64_t)std::min<double>((double)maxTr * A.rib_recs_per_row, (double)maxTr * 32.0) + 64 + (uint64_t)(rg.ck + 1) * 32;
 						o_hdr = o; o = align_up(o + ((size_t)maxTr + 32) * rg.hdrw * 4, 256);
 						o_rec = o; o = align_up(o + rcap * rg.recf * 4, 256);
 						o_pp = o; o = align_up(o + ((size_t)maxTr + 32) * 4, 256);
@@ -1296,7 +1296,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 					first_why[i] = (res.out[logq[i]].status == ST_LIN_FAULT) ? res.out[logq[i]].nrec : 0u;
 				}
 				// records-free layout with two-level checkpoints (the only one the log2-domain kernel is built for)
-				const size_t ngr = (size_t)maxTl / rg.ck + 2, nck = ngr / 8 + 2;
+				const size_t ngr = (size_t)maxTl / rib::LOG_GROUP_ROWS + 2, nck = ngr / 8 + 2;
 				size_t o = 0;
 				const size_t l_sch = o; o = align_up(o + ngr * 8, 256);
 				const size_t l_ck = o; o = align_up(o + nck * rg.ckf * 4, 256);
@@ -1383,7 +1383,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 					const uint32_t why = res.out[r].nrec;
 					// ... and so do long reads whatever the reason: a full-band tier is one warp for seconds per read
 					// (config 4: ~3 s per tier for 2 M rows), not worth two attempts that usually fail for the same reason
-					if (why == 1u || why == 12u || res.desc[r].S > 400000u) direct_log2.push_back(r);
+					if (why == 1u || why == 3u || why == 12u || res.desc[r].S > 400000u) direct_log2.push_back(r);
 					else rest.push_back(r);
 					++A.n_rib_fault;
 					++A.rib_reason[std::min<uint32_t>(why, 15u)];

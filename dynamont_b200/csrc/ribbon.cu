@@ -13,9 +13,12 @@ namespace
 
 constexpr int WPB = 4;  // warps per CTA; the warps of a CTA are independent (each pulls its own reads)
 
-using RC2 = RCfg<2>;
+#ifndef DYN_RIB_GR
+#define DYN_RIB_GR 16  // rows per group of the 2-columns-per-lane kernels (8: the first version of round 2)
+#endif
+using RC2 = RCfg<2, false, DYN_RIB_GR>;
 using RC4 = RCfg<4>;
-using RC2L = RCfg<2, true>;  // the log2-domain tier behind the linear-domain ribbon (align, records-free layout, two-level checkpoints)
+using RC2L = RCfg<2, true, LOG_GROUP_ROWS>;  // the log2-domain tier behind the linear-domain ribbon (align, records-free layout, two-level checkpoints)
 constexpr int BPSL = 4;
 constexpr int BPS2 = 5;  // 20 resident warps per SM: <= 96 registers per thread, no spills (measured: 6 -> 80 registers: -4 %, 8 -> 64: -13 %)
 constexpr int BPS4 = 4;  // 16 resident warps per SM: <= 128 registers per thread

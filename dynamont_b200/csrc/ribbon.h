@@ -11,6 +11,8 @@ struct BatchArgs;
 namespace rib
 {
 
+constexpr int LOG_GROUP_ROWS = 8;  // rows per group of the log2-domain ribbon (its scratch is sized on the host from this)
+
 struct Geometry
 {
 	int cpl;              // lattice columns per lane

@@ -215,8 +215,10 @@ def test_emulated_narrow_band_and_errors(emu_lib):
             continue
         check_alignment(al.align(s, q, True), o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
         # a band this narrow clips the alignment: forward and backward ridges separate by hundreds of bits, which the
-        # linear-domain kernel must detect (range guard) and hand to the log2-domain kernels
-        assert al.last_timing()["log2_fallback_reads"] == 1
+        # linear-domain kernels must detect and hand to a log2-domain tier (the log2-domain ribbon, which holds the whole
+        # band in its window here, or the full-band log2-domain kernels)
+        tm, why = al.last_timing(), al.ribbon_fault_reasons()
+        assert tm["ribbon_faults"] == 1 and why["kept_by_log2_ribbon"] + tm["log2_fallback_reads"] == 1
     al = Aligner(path, "rna002", _lib_path=emu_lib)
     bad = [(np.zeros(0), "ACGTACGT", "Signal is empty"), (s[:50], "ACG", "Sequence shorter than model kmer size"),
            (s[:20], q[:40], "Signal too short compared to sequence"), (s, q[:30] + "N" + q[31:], "Invalid nucleotide: N")]
