@@ -607,7 +607,7 @@ def main():
         pass
     counters = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r2_ribbon_counters.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r2f_ribbon_counters.json")) as fh:
             counters = json.load(fh)
     except Exception:
         pass
@@ -628,8 +628,8 @@ def main():
         # sweep (and its replay) for the path posteriors
         sweeps = 7.0 if rib_info.get("records_free_layout") else (4.0 if rib_info.get("two_level_checkpoints") else 3.0)
         exe_mufu = sweeps * 64.0 * rows / dp_s / 1e9
-        kern = "k_ribbon<RCfg<2>,%d,5> (ribbon: 63-column window that follows the probability mass, groups of 8 rows, linear-domain FP32 " \
-               "block floating point, 1 MUFU per evaluated cell-update, %d sweeps%s)" % (
+        kern = "k_ribbon<RCfg<2,false,16>,%d,5> (ribbon: 63-column window that follows the probability mass, groups of 16 rows, linear-domain " \
+               "FP32 block floating point in packed FP32x2 (FFMA2 / FMUL2), 1 MUFU per evaluated cell-update, %d sweeps%s)" % (
                    3 if rib_info.get("records_free_layout") else (2 if train else 1), int(sweeps),
                    "; long reads: two-level checkpoints, records-free scratch, path posteriors from a second forward sweep"
                    if rib_info.get("records_free_layout") else "")

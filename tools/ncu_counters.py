@@ -19,7 +19,8 @@ def to_bytes(k):
     v, u = f(k), unit[k].lower()
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}[u]
 entry = {
-    "source": "profiles/" + {"prof_r2m_align": "r2m_k_ribbon_align_full.md", "prof_r2m_train": "r2m_k_ribbon_train_full.md"}.get(os.path.basename(rep).replace(".ncu-rep", ""), os.path.basename(rep)),
+    "source": "profiles/" + {"prof_r2m_align": "r2m_k_ribbon_align_full.md", "prof_r2m_train": "r2m_k_ribbon_train_full.md",
+                             "prof_r2f_align": "r2f_k_ribbon_align_full.md", "prof_r2f_train": "r2f_k_ribbon_train_full.md"}.get(os.path.basename(rep).replace(".ncu-rep", ""), os.path.basename(rep)),
     "kernel": d["Kernel Name"],
     "lattice_rows_in_capture": lattice_rows,
     "kernel_ms_in_capture": f("gpu__time_duration.sum") * ({"ms": 1.0, "msecond": 1.0, "us": 1e-3, "usecond": 1e-3, "s": 1e3, "second": 1e3, "ns": 1e-6, "nsecond": 1e-6}[unit["gpu__time_duration.sum"].lower()]),
