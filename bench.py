@@ -286,7 +286,7 @@ def run_ntk(args):
         al = Aligner(path, pore, mode="resquiggle", device=local_rank)
         cells = sum((s.size + 1) * (len(q) - k + 2) + (s.size + 1) * 4 ** k for s, q in zip(sigs, seqs))
         for _ in range(max(1, args.warmup)):
-            al.align_batch(sigs[:4], seqs[:4], True)
+            al.align_batch(sigs, seqs, True)  # the same batch shape: the worker pool's lattices are allocated (and kept) here
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ok = 0
