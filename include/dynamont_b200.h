@@ -215,12 +215,17 @@ int dyn_last_variant(const dyn_aligner*);
  * checked on the device): out2[0] = reads of the last batch call they were given, out2[1] = reads they handed on to
  * the full-band kernels (window / range checks failed); results are identical either way */
 void dyn_last_ribbon(const dyn_aligner*, uint64_t* out2);
-/* cumulative count of those hand-overs by reason code 1..12 (csrc/dp_ribbon.cuh, ribbon_read), out16[reason] */
+/* cumulative count of the reads the linear-domain ribbon kernels lost, by reason code 1..12 (csrc/dp_ribbon.cuh,
+ * ribbon_read), out16[reason]; out16[13] = posterior records per lattice row of the last batch x 1000, out16[14] = scratch
+ * layout of the last batch (0: a checkpoint per group, 1: two-level checkpoints, 2: two-level + records-free),
+ * out16[15] = how many of the lost reads the log2-domain ribbon (the tier before the full-band kernels) kept */
 void dyn_ribbon_fault_reasons(const dyn_aligner*, uint64_t* out16);
 /* run all work of this handle on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
  * of the handle's own stream, so that the caller's CUDA events bracket it */
 int dyn_set_stream(dyn_aligner*, void* cuda_stream);
-/* tuning: resident warps per SM for the DP kernel (default chosen by the build), sparse threshold etc. */
+/* tuning / experiments, INTEGRATION.md 3c: "ribbon" (0 | 2 | 4 columns per lane), "rib_guard", "rib_two_level", "rib_gather"
+ * (records-free scratch layout), "rib_log" (0: no log2-domain ribbon tier, 2: every read through it as well — test hook),
+ * "arith", "variant", "warps_per_sm", "mem_fraction", "thr2", ...; returns -1 for an unknown key */
 int dyn_set_option(dyn_aligner*, const char* key, double value);
 
 #ifdef __cplusplus
