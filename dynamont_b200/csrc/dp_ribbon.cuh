@@ -1128,10 +1128,14 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 			{
 				get_row(k + 1, bn);
 				const float x = __shfl_sync(FULL, xg, k);
-				// the posterior mass is measured on the group's last row: offsets and the posterior factor are fixed inside
-				// a group, so a lane that lost its values or whose factor left the float range shows there
+				// the posterior mass is measured on the group's FIRST and LAST row: offsets and the posterior factor are fixed
+				// inside a group and the drift of the stored values is monotone in the row (backward values shrink towards the
+				// group's first row, forward values towards its last), so a lane that lost its values, or whose factor left
+				// the float range (the clamp of lin::kappa), shows at one of the two ends.  (With 8-row groups the last row was
+				// enough; at 16 rows a 2.5x-noise read lost 2^-128 over one group on the backward side only, and one of 24 such
+				// reads came back with a posterior of 2^-10 instead of 1 and no fault — gpu_soak, third session.)
 				const uint32_t cell = (MODE == 4) ? __shfl_sync(FULL, cgq, k) : 0u;
-				if (k == GR - 1) macc += fwd_row<RC, MODE, true, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
+				if (k == GR - 1 || k == 0) macc += fwd_row<RC, MODE, true, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
 				else fwd_row<RC, MODE, true, false>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
 				xprev = x;
 #pragma unroll
@@ -1177,7 +1181,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 		// ---- group boundary: state row 8g+8 ------------------------------------------------------------------
 		// closed loop: the posterior mass of every row is 1; a row that lost mass is a fault, the mean deviation (slow
 		// common-mode FP32 drift) is folded into the posterior factor of the next group
-		const float cnt = (!RC::LOGD && g < gl && !clip) ? 1.0f : ((g < gl) ? (float)nr : (float)(nr + 1));  // rows whose mass was summed
+		const float cnt = (!RC::LOGD && g < gl && !clip) ? 2.0f : ((g < gl) ? (float)nr : (float)(nr + 1));  // rows whose mass was summed
 		const float mass = warp_sum(macc, lane);
 		macc = 0.0f;
 		if (!(fabsf(mass - cnt) <= RIB_MASS_TOL) && !fault) { fault = 5; RIB_DBG("p2 g=%d mass=%g of %g\n", g, mass, cnt); }

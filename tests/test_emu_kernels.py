@@ -130,6 +130,27 @@ def test_emulated_log2_ribbon_keeps_what_the_linear_ribbon_loses(emu_lib):
     print("band-cut reads kept by the log2-domain ribbon:", kept)
 
 
+def test_emulated_noisy_read_16_row_groups(emu_lib):
+    """the read that slipped through the 16-row ribbon before the posterior mass was checked on the FIRST row of a group as
+    well (2.5x noise: the backward values lose 2^-128 over one group; one segment came back with a posterior of 2^-10
+    instead of 1, borders identical, no fault — tools/gpu_soak.py, kind "noisy", read 8): it must fault in the
+    linear-domain ribbon and come back right from the log2-domain ribbon, and from the full-band tiers without it"""
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import materialize_model
+    from conftest import MODELS_DIR, ROOT
+    from oracle import Oracle
+    path = materialize_model("rna002_5mer", MODELS_DIR)
+    s = np.load(os.path.join(ROOT, "tests", "golden", "noisy_read8_signal.npy"))
+    q = open(os.path.join(ROOT, "tests", "golden", "noisy_read8_sequence.txt")).read().strip()
+    o = Oracle(path, "rna002").align(s.astype(np.float64), q, True)
+    for rib_log in (1, 0):
+        al = Aligner(path, "rna002", _lib_path=emu_lib)
+        al.set_option("rib_log", rib_log)
+        r = al.align(s, q, True)
+        check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"], "noisy read 8, rib_log=%d" % rib_log)
+        assert al.last_timing()["ribbon_faults"] == 1 and al.ribbon_fault_reasons().get(5) == 1
+
+
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 8, 9, 10, 11, 12, 13, -1])
 def test_emulated_variants(variant, emu_lib):
     """build variants: general kernels (0-3, 9, 11, 13), uniform-sigma kernels (4-8, 10, 12), library default (-1)"""
