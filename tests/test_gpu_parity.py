@@ -277,3 +277,24 @@ def test_full_band_tiers_match_reference_golden(case):
     heavy = case.stat_w > 1e-3
     np.testing.assert_allclose(pooled["w"][km][heavy], case.stat_w[heavy], rtol=TRAIN_RTOL)
     np.testing.assert_allclose(per_read[0]["emission_model"]["stdev"][km][heavy], case.train_stdev[heavy], rtol=TRAIN_RTOL, atol=1e-6)
+
+
+def test_noisy_read_that_needs_the_first_row_mass_check(models_dir):
+    """tools/gpu_soak.py, kind "noisy", read 8 (tests/golden/noisy_read8_*): 2.5x noise loses 2^-128 of backward range over
+    one 16-row group; before the posterior mass was checked on the first row of a group as well, the linear-domain ribbon
+    returned it with one segment posterior of 2^-10 instead of 1 and no fault"""
+    import os
+    from conftest import ROOT
+    from dynamont_b200 import Aligner
+    from dynamont_b200.synth import materialize_model
+    from oracle import Oracle
+    path = materialize_model("rna002_5mer", models_dir)
+    s = np.load(os.path.join(ROOT, "tests", "golden", "noisy_read8_signal.npy"))
+    q = open(os.path.join(ROOT, "tests", "golden", "noisy_read8_sequence.txt")).read().strip()
+    o = Oracle(path, "rna002").align(s.astype(np.float64), q, True)
+    for rib_log in (1, 0):
+        al = Aligner(path, "rna002")
+        al.set_option("rib_log", rib_log)
+        r = al.align(s, q, True)
+        check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"])
+        assert al.last_timing()["ribbon_faults"] == 1
