@@ -27,7 +27,13 @@ KINDS = [  # name, pore, model, (min,max) length, spb, dwell, sd_scale, kind, ou
     ("homop", "rna002", "rna002_5mer", (200, 500), 8, "geometric", 1.5, "homopolymer", 0.0),
     ("dinuc", "rna002", "rna002_5mer", (200, 400), 6, "geometric", 2.0, "dinuc", 0.0),
     ("mixed9", "rna004", "synthetic_rna004_9mer", (300, 700), 9, "geometric", 1.5, "mixed", 0.0),
+    # long noisy reads (many 16-row groups at 1.5x / 2x the model's noise); the oracle needs ~10 s per read: run them with
+    # DYN_SOAK_KINDS="noisy_long noisy2_long" and a small count
+    ("noisy_long", "rna004", "synthetic_rna004_9mer", (2000, 4000), 30, "geometric", 1.5, "rand", 0.0),
+    ("noisy2_long", "rna002", "rna002_5mer", (1500, 3000), 20, "gamma", 2.0, "rand", 0.0),
 ]
+if not ONLY:
+    KINDS = [kd for kd in KINDS if not kd[0].endswith("_long")]
 tot_seg = tot_same = tot_fb = tot_reads = 0
 worst_dp = worst_z = 0.0
 for name, pore, model, (lo, hi), spb, dwell, sds, kind, outl in KINDS:

@@ -46,7 +46,10 @@ for name, pore, model, (lo, hi), spb, sds in KINDS:
         return m, np.sqrt(np.maximum(p["xx"][heavy] / p["w"][heavy] - m * m, 0.0))
     (m1_, s1_), (m2_, s2_) = mstep(pooled), mstep(pooled2)
     rel["x"] = float(np.max(np.maximum(np.abs(m1_ - m2_) - 1e-5, 0.0) / np.maximum(np.abs(m2_), 1e-12)))
-    rel["xx"] = float(np.max(np.abs(s1_ - s2_) / s2_))
+    # the stdev of a kmer that got its weight from one or two samples is sqrt(xx/w - mean^2) ~ sqrt(0): rounding noise in the
+    # reference as well (NT:523-528 floors the variance at 1e-12); compare it where a kmer was actually occupied
+    occ = pooled2["w"][heavy] > 5.0
+    rel["xx"] = float(np.max(np.abs(s1_[occ] - s2_[occ]) / s2_[occ])) if occ.any() else 0.0
     # a few reads against the oracle's per-read transitions
     orc = Oracle(path, pore)
     dm = 0.0
@@ -56,6 +59,6 @@ for name, pore, model, (lo, hi), spb, sds in KINDS:
         for key in ("m1", "e1", "e2"):
             dm = max(dm, abs(r["transition_params"][key] - o["transition_params"][key]) / o["transition_params"][key])
     worst = max(worst, max(rel.values()), dm)
-    print("%-8s %3d reads  ribbon faults %2d  log2 fallback %2d  vs full-band log2: rel weight %.2e  mean (beyond atol 1e-5) %.2e  stdev %.2e  transitions vs oracle %.2e"
+    print("%-8s %3d reads  ribbon faults %2d  log2 fallback %2d  vs full-band log2: rel weight %.2e  mean (beyond atol 1e-5) %.2e  stdev (weight > 5) %.2e  transitions vs oracle %.2e"
           % (name, n_per, tm["ribbon_faults"], tm["log2_fallback_reads"], rel["w"], rel["x"], rel["xx"], dm))
 print("WORST relative difference %.2e (gate 1e-4)" % worst)
