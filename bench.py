@@ -454,6 +454,9 @@ def main():
 
     from collections import deque
     pending = deque()
+    # batches in flight: two hide the host side of a batch; config 4 keeps three, so that the seconds-long full-band hand-over of
+    # the few reads whose alignment leaves the reference band overlaps the ribbon kernels of the next two batches
+    depth = 3 if args.config == "c4" else 2
     acc = {"ok": 0, "kms": 0.0, "nl": 0, "fb": 0, "rl": 0}
 
     outsets = deque()
@@ -483,7 +486,7 @@ def main():
             out = outsets.popleft() if outsets else None  # result buffers of a completed job, rotated
             pending.append((al.submit_packed(b["sig"].data_ptr(), b["sig_off"], b["bases"].data_ptr(), b["seq_off"],
                                              not args.z_only, device=True, out=out), b))
-            if len(pending) >= 2:
+            if len(pending) >= depth:
                 collect(pending.popleft())
         while drain and pending:
             collect(pending.popleft())

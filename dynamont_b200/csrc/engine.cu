@@ -780,8 +780,8 @@ struct dyn_aligner
 	// asynchronous entry points (dyn_align_submit / dyn_align_wait): calls alternate between LANES child handles on the
 	// same device, each with its own stream and buffers, so that the host-to-device copy of call i+1 and the result
 	// copy + fan-out of call i-1 overlap the kernels of call i
-	static constexpr int LANES = 2;
-	dyn_aligner* lane[LANES] = {nullptr, nullptr};
+	static constexpr int LANES = 3;  // (a third lane lets a long full-band hand-over of one batch overlap two ribbon kernels: config 4)
+	dyn_aligner* lane[LANES] = {nullptr, nullptr, nullptr};
 	// The lanes run their ribbon kernels on the ROOT handle's stream and in the root's scratch: kernels of successive
 	// batches execute one after the other anyway (each fills the GPU), so one scratch pool — the largest allocation by
 	// far, tens of GB — serves all of them.  compute_mu orders "size the pool, build the slot table, enqueue the kernel".
@@ -1438,9 +1438,12 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 		per_slot = o;
 		size_t budget = (size_t)((double)(rt.free_bytes() + A.d_scratch.cap) * A.mem_fraction);
 		size_t fit = std::max<size_t>(1, budget / per_slot);
-		if (fit < grid)
+		if (fit < (grid + 3) / 4)
 		{
-			// long reads handed on by the ribbon kernels: their full-band scratch needs the room of the (shared) ribbon pool.
+			// long reads handed on by the ribbon kernels: their full-band scratch needs the room of the (shared) ribbon pool
+			// — taken only when the reads would otherwise need more than four rounds: giving the pool back drains the root's
+			// stream (the other lanes' ribbon kernels) and costs its re-allocation, a second or third round of a few warps
+			// runs beside those kernels.
 			// Nothing enqueued may still use it: hold compute_mu (no lane can enqueue) and drain the root's stream.
 			dyn_aligner& R = A.root ? *A.root : A;
 			std::lock_guard<std::mutex> cl(R.compute_mu);
