@@ -642,11 +642,11 @@ DYN_DEV void slide_up(RWarp<RC>& w, Fw<RC::CPL>& f, TrainAcc<RC::CPL>& ta, const
 // their lane offsets; kc / kn = (OF + OB(row t / t+1) - floor(Z2)) + log2 c0 of this lane, so that fE + bc + kc and
 // fM + bn + e + kn ARE the log2 posteriors.  m1, e2: log2 transition scores.
 template <class RC, int MODE, bool STEP>
-DYN_DEV float fwd_row_log(const RWarp<RC>& w, Fw<RC::CPL>& f, uint32_t* hdr_row, float x, const float (&bc)[RC::CPL],
-	const float (&bn)[RC::CPL], float kc, float kn, float m1, float e2, uint32_t cell)
+DYN_DEV float fwd_row_log(const RWarp<RC>& w, Fw<RC::CPL>& f, TrainAcc<RC::CPL>& ta, uint32_t* hdr_row, float x, float xprev,
+	const float (&bc)[RC::CPL], const float (&bn)[RC::CPL], float kc, float kn, float m1, float e2, uint32_t cell)
 {
 	constexpr int C = RC::CPL;
-	static_assert(MODE == 3 || MODE == 4, "the log2-domain ribbon aligns with the records-free layout only");
+	static_assert(MODE == 2 || MODE == 3 || MODE == 4, "the log2-domain ribbon: training statistics, or alignment with the records-free layout");
 	const int lane = w.lane;
 	const float vlraw = (MODE == 3) ? __shfl_sync(FULL, f.VE[C - 1], (lane + 31) & 31) : NEG;
 	const float flraw = STEP ? __shfl_sync(FULL, f.fE[C - 1], (lane + 31) & 31) : NEG;
@@ -658,7 +658,20 @@ DYN_DEV float fwd_row_log(const RWarp<RC>& w, Fw<RC::CPL>& f, uint32_t* hdr_row,
 		e[j] = STEP ? w.emis_log(j, x) : 0.0f;
 		PE[j] = f.fE[j] + (bc[j] + kc);
 		PM[j] = STEP ? f.fM[j] + ((bn[j] + e[j]) + kn) : NEG;  // bM[t][n] = bE[t+1][n] * p(t,n) (NT:200); no match state in the last row
-		msum += ex2(PM[j]) + ex2(PE[j]);
+		const float gm = ex2(PM[j]), ge = ex2(PE[j]);
+		msum += gm + ge;
+		if (MODE == 2)
+		{
+			// training statistics (NT:494-514), as in the linear domain: gamma = pM + pE weighs sample x[t-1]
+			const float g = gm + ge;
+			const float dx = xprev - ta.mu[j];
+			const float gd = g * dx;
+			ta.gw[j] += g;
+			ta.gx[j] += gd;
+			ta.gxx[j] = fmaf(gd, dx, ta.gxx[j]);
+			ta.sM += gm;
+			ta.sE += ge;
+		}
 	}
 	if (MODE == 3)
 	{
@@ -689,7 +702,7 @@ DYN_DEV float fwd_row_log(const RWarp<RC>& w, Fw<RC::CPL>& f, uint32_t* hdr_row,
 			}
 		}
 	}
-	else
+	else if (MODE == 4)
 	{
 		const int q = (int)((cell & 0x7fffffffu) % (uint32_t)RC::SLOTS);
 		const int ql = q / C, jq = q - ql * C;
@@ -1154,7 +1167,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 				{
 					obn = rows_ob[(k + 1) * 32];
 					const float kc = (float)(f.OF + obc - Z2i) + c0l, kn = (float)(f.OF + obn - Z2i) + c0l;
-					macc += fwd_row_log<RC, MODE, true>(w, f, hdr_g + k * HSTR, x, bc, bn, kc, kn, m1, e2, cell);
+					macc += fwd_row_log<RC, MODE, true>(w, f, ta, hdr_g + k * HSTR, x, xprev, bc, bn, kc, kn, m1, e2, cell);
 					obc = obn;
 				}
 				else macc += fwd_row<RC, MODE, true>(w, f, rs, ta, hdr_g + k * HSTR, recs, thr, x, xprev, bc, bn, m1, e2, cell);
@@ -1171,7 +1184,7 @@ DYN_DEV double forward_pass(RWarp<RC>& w, const SlotScratch& sc, const BatchArgs
 				if constexpr (RC::LOGD)
 				{
 					const float kc = (float)(f.OF + obc - Z2i) + c0l;
-					macc += fwd_row_log<RC, MODE, false>(w, f, hdr_g + nr * HSTR, 0.0f, bc, bn, kc, kc, m1, e2, cell);
+					macc += fwd_row_log<RC, MODE, false>(w, f, ta, hdr_g + nr * HSTR, 0.0f, xprev, bc, bn, kc, kc, m1, e2, cell);
 				}
 				else macc += fwd_row<RC, MODE, false>(w, f, rs, ta, hdr_g + nr * HSTR, recs, thr, 0.0f, xprev, bc, bn, m1, e2, cell);
 			}

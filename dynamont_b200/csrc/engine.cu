@@ -1275,7 +1275,7 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 			// mass sits at the window's EDGE (reasons 2, 7: a window problem, not a range problem) go to the full-band kernels.
 			std::vector<uint32_t> logq;
 			const bool force_log = (A.rib_log == 2);  // test hook: every read of the tier through the log2-domain ribbon as well
-			if (mode == 1 && A.rib_log != 0)
+			if ((mode == 1 || mode == 2) && A.rib_log != 0)
 				for (uint32_t r : rorder)
 				{
 					if (res.out[r].status == ST_LIN_FAULT)
@@ -1330,6 +1330,15 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				A.h2d_staged(d_slots, slots.data(), (size_t)gridl * sizeof(SlotScratch));
 				A.h2d_staged(d_order, logq.data(), logq.size() * 4);
 				rt.zero(d_queue, 64);
+				if (mode == 2)
+					for (uint32_t r : logq)
+					{
+						// columns the read flushed before its fault was detected: the re-run accumulates from zero
+						const ReadDesc& d = res.desc[r];
+						rt.zero(ba.read_w + d.pc_off, (size_t)d.N * 8);
+						rt.zero(ba.read_x + d.pc_off, (size_t)d.N * 8);
+						rt.zero(ba.read_xx + d.pc_off, (size_t)d.N * 8);
+					}
 				BatchArgs rb = ba;
 				rb.n_reads = (uint32_t)logq.size();
 				rb.slots = d_slots;
@@ -1343,10 +1352,10 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 				}
 				rt.mark_on(10, R.rt);
 #ifndef DYN_HOST_EMU
-				const int le = rib::launch((void*)R.rt.stream, rb, gridl, 3, 2, 0, true, true);
+				const int le = rib::launch((void*)R.rt.stream, rb, gridl, mode == 2 ? 2 : 3, 2, 0, true, true);
 				if (le != 0) throw std::runtime_error(std::string("CUDA error launching the log2-domain ribbon kernel: ") + cudaGetErrorString((cudaError_t)le));
 #else
-				rib::launch(nullptr, rb, gridl, 3, 2, 0, true, true);
+				rib::launch(nullptr, rb, gridl, mode == 2 ? 2 : 3, 2, 0, true, true);
 #endif
 				rt.mark_on(11, R.rt);
 				if (cross) rt.wait_self(11);
@@ -1372,6 +1381,13 @@ void run_batch_t(dyn_aligner& A, const BatchIO& io, int mode, BatchResult& res, 
 					{
 						++A.n_rib_log_fault;
 						direct_log2.push_back(r);  // the linear full-band tiers would lose it for the same reason
+						if (mode == 2)
+						{
+							const ReadDesc& d = res.desc[r];
+							rt.zero(ba.read_w + d.pc_off, (size_t)d.N * 8);
+							rt.zero(ba.read_x + d.pc_off, (size_t)d.N * 8);
+							rt.zero(ba.read_xx + d.pc_off, (size_t)d.N * 8);
+						}
 					}
 					else ++A.rib_reason[15];  // [15]: cumulative reads the log2-domain ribbon kept
 					++i;

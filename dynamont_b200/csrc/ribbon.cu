@@ -126,13 +126,15 @@ int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int 
 #endif
 	if (log_domain)
 	{
-		if (mode != 3 || !two_level) return -1;
+		if ((mode != 3 && mode != 2) || !two_level) return -1;
 #ifndef DYN_HOST_EMU
 		const unsigned ctas = (n_warps + WPB - 1) / WPB;
-		k_ribbon<RC2L, 3, BPSL, true><<<ctas, 32 * WPB, RC2L::SMEM_BYTES * WPB, s>>>(args);
+		if (mode == 3) k_ribbon<RC2L, 3, BPSL, true><<<ctas, 32 * WPB, RC2L::SMEM_BYTES * WPB, s>>>(args);
+		else k_ribbon<RC2L, 2, BPSL, true><<<ctas, 32 * WPB, RC2L::SMEM_BYTES * WPB, s>>>(args);
 		return (int)cudaGetLastError();
 #else
-		simt::launch(n_warps, RC2L::SMEM_BYTES, [&]() { worker<RC2L, 3, true>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+		if (mode == 3) simt::launch(n_warps, RC2L::SMEM_BYTES, [&]() { worker<RC2L, 3, true>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
+		else simt::launch(n_warps, RC2L::SMEM_BYTES, [&]() { worker<RC2L, 2, true>(args, simt::dyn_smem(), threadIdx.x, blockIdx.x); });
 		return 0;
 #endif
 	}

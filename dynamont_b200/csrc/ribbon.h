@@ -34,7 +34,7 @@ bool geometry(int cpl, int bps, Geometry& g);  // bps: resident CTAs per SM (0 =
 // second forward sweep after the traceback; needs two_level).
 // Returns 0 or the cudaError_t of the launch.
 // two_level: checkpoints of every 8th group only (dp_ribbon.cuh SG), the rest replayed into a per-warp ring in pass 2
-// log_domain: the log2-domain build of the same passes (mode 3, two_level only; 2 columns per lane whatever cpl says)
+// log_domain: the log2-domain build of the same passes (mode 3 or 2, two_level only; 2 columns per lane whatever cpl says)
 int launch(void* stream, const BatchArgs& args, unsigned n_warps, int mode, int cpl, int bps, bool two_level, bool log_domain = false);
 
 } // namespace rib

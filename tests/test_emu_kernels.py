@@ -149,6 +149,21 @@ def test_emulated_noisy_read_16_row_groups(emu_lib):
         r = al.align(s, q, True)
         check_alignment(r, o["signal_positions"], o["sequence_positions"], o["probabilities"], o["Z"], "noisy read 8, rib_log=%d" % rib_log)
         assert al.last_timing()["ribbon_faults"] == 1 and al.ribbon_fault_reasons().get(5) == 1
+    # training takes the same route: the linear-domain ribbon faults, the log2-domain ribbon (MODE 2) returns the statistics
+    ot = Oracle(path, "rna002").train(s.astype(np.float64), q)
+    for rib_log in (1, 0):
+        al = Aligner(path, "rna002", _lib_path=emu_lib)
+        al.set_option("rib_log", rib_log)
+        per, pooled = al.train_batch([s], [q], per_read_model=True)
+        r = per[0]
+        tm, why = al.last_timing(), al.ribbon_fault_reasons()
+        assert tm["ribbon_faults"] == 1 and why["kept_by_log2_ribbon"] == (1 if rib_log else 0) and tm["log2_fallback_reads"] == 0
+        assert abs(r["Z"] - ot["Z"]) <= 1e-6 * abs(ot["Z"])
+        for key in ("m1", "e1", "e2"):
+            assert abs(r["transition_params"][key] - ot["transition_params"][key]) <= TRAIN_RTOL * ot["transition_params"][key]
+        heavy = pooled["w"] > 1e-3
+        np.testing.assert_allclose(r["emission_model"]["mean"][heavy], ot["emission_model"]["mean"][heavy], rtol=TRAIN_RTOL, atol=1e-5)
+        np.testing.assert_allclose(r["emission_model"]["stdev"][heavy], ot["emission_model"]["stdev"][heavy], rtol=TRAIN_RTOL, atol=1e-6)
 
 
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 6, 8, 9, 10, 11, 12, 13, -1])
