@@ -71,3 +71,23 @@ def test_streaming_binary_protocol(tmp_path):
     assert [int(f[1]) for f in fields] == case.signal_positions.tolist()
     assert np.allclose([float(f[2]) for f in fields], case.probabilities, atol=1e-4)
     assert abs(float(z[2:]) - case.Z) < 1e-5 * abs(case.Z)
+
+
+@pytest.mark.gpu
+def test_streaming_binary_protocol_gpu():
+    """the product binary (dynamont_b200/csrc/dynamont-NT-b200, linked against the CUDA library): same protocol, same answers"""
+    exe = os.path.join(ROOT, "dynamont_b200", "csrc", "dynamont-NT-b200")
+    assert os.path.exists(exe), "dynamont-NT-b200 is built by dynamont_b200.build (graft entry build())"
+    case = [c for c in load_golden() if c.name == "rna002_short"][0]
+    sig = ",".join(repr(float(v)) for v in case.signal)
+    text = f"{sig}\n{case.sequence}\n1.0,2.0\nACGTACGTAC\n{sig}\n{case.sequence}\n"
+    out = subprocess.run([exe, "-m", case.model_path, "-r", case.pore, "-p", "--batch", "2"], input=text,
+                         capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    assert len(out) == 3 and out[0] == out[2]
+    assert out[1] == "error:Signal too short compared to sequence"
+    segs, z = out[0].split("\t")
+    fields = [s.split(",") for s in segs.strip(";").split(";")]
+    assert [int(f[0][1:]) for f in fields] == case.sequence_positions.tolist()
+    assert [int(f[1]) for f in fields] == case.signal_positions.tolist()
+    assert np.allclose([float(f[2]) for f in fields], case.probabilities, atol=1e-4)
+    assert abs(float(z[2:]) - case.Z) < 1e-5 * abs(case.Z)
